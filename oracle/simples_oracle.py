@@ -1,0 +1,765 @@
+"""NumPy restatement of SIMPLEs' EM imputation hot path (TEST INFRASTRUCTURE).
+
+Follows, line by line, ``R/EM_impute.R:75-339`` and ``R/do_impute.R:29-160`` of
+JunLiuLab/SIMPLEs (paths relative to /root/reference), including the quirks
+listed in SURVEY.md section 8(c).  PARITY UNPINNED (see ``oracle/__init__``).
+
+Two M-step formulations are provided and cross-checked by the tests:
+
+* ``em_impute_ref``  -- literal: per gene the ``(M0*n+K0) x K0`` augmented design
+  ``W_aug``/``Y_aug`` of ``R/EM_impute.R:238-270`` and the dense ``G x G`` ``bigM``
+  of ``R/EM_impute.R:311-314``.
+* ``em_impute_fast`` -- cell-additive sufficient statistics (what the CUDA
+  path computes and all-reduces across GPUs).
+
+Third-party arithmetic on the path that is NOT in /root/reference (no version
+pins, DESCRIPTION:14-24): glmnet (lasso, replaced by an exact minimiser of the
+same objective), Rsolnp::solnp (replaced by a deterministic damped Newton
+started from ``lam_init``), mixtools::rmvnorm (symmetric eigen square root),
+msm::rtnorm / stats::rnorm / rbinom / rmultinom (replaced by inverse-CDF draws
+from a Philox4x32-10 counter tape shared bit-for-bit with the CUDA kernels).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from scipy import special
+
+__all__ = [
+    "PI_REF", "COMPAT_STALE_DT", "COMPAT_PI", "COMPAT_MU_DIV_N",
+    "COMPAT_PRIORB_PREV", "COMPAT_DEFAULT",
+    "philox4x32", "cell_uniforms", "entry_uniforms", "trunc_z", "sym_sqrt",
+    "lasso_solve", "lasso_solve_batch", "lambda_solve_k", "lambda_step",
+    "cluster_terms", "epass", "factor_means", "sample_sweep",
+    "local_stats", "stats_pack", "stats_unpack", "mstep_from_stats",
+    "em_impute_ref", "em_impute_fast", "do_impute_ref",
+    "simulate", "bench_state", "expected_impute",
+]
+
+PI_REF = 3.14159265359          # R/EM_impute.R:80, R/do_impute.R:31  (Q2)
+
+# ref_compat bits (default: all on = reproduce the reference's behaviour)
+COMPAT_STALE_DT = 1             # Q1  R/EM_impute.R:206,212
+COMPAT_PI = 2                   # Q2  R/EM_impute.R:80
+COMPAT_MU_DIV_N = 4             # Q3  R/EM_impute.R:95
+COMPAT_PRIORB_PREV = 8          # Q5  R/EM_impute.R:119,144-146,275
+COMPAT_DEFAULT = 15
+
+_U32 = np.uint64(0xFFFFFFFF)
+
+
+# ----------------------------------------------------------------------------
+# Counter-based variate tape (shared with csrc/rng.cuh)
+# ----------------------------------------------------------------------------
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=10):
+    """Philox4x32-10 (Salmon et al. 2011).  All inputs broadcastable, uint32
+    values carried in uint64 arrays.  Returns four uint64 arrays (< 2**32)."""
+    m0 = np.uint64(0xD2511F53)
+    m1 = np.uint64(0xCD9E8D57)
+    w0 = np.uint64(0x9E3779B9)
+    w1 = np.uint64(0xBB67AE85)
+    c0, c1, c2, c3 = np.broadcast_arrays(*[np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3)])
+    k0 = np.uint64(k0)
+    k1 = np.uint64(k1)
+    sh = np.uint64(32)
+    for _ in range(rounds):
+        p0 = m0 * c0
+        p1 = m1 * c2
+        hi0, lo0 = p0 >> sh, p0 & _U32
+        hi1, lo1 = p1 >> sh, p1 & _U32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + w0) & _U32
+        k1 = (k1 + w1) & _U32
+    return c0, c1, c2, c3
+
+
+def _u52(hi, lo):
+    """Two 32-bit words -> uniform in (0,1): ((x >> 12) + 0.5) * 2**-52."""
+    x = (hi << np.uint64(32)) | lo
+    return ((x >> np.uint64(12)).astype(np.float64) + 0.5) * (2.0 ** -52)
+
+
+def _seed_key(seed):
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return seed & 0xFFFFFFFF, seed >> 32
+
+
+def cell_uniforms(seed, sweep, cells, nu):
+    """Per-cell uniforms: stream tag 1, block j gives uniforms 2j, 2j+1.
+    Uniform 0 = membership draw, uniform 1+k = factor normal k."""
+    cells = np.asarray(cells, dtype=np.uint64)
+    k0, k1 = _seed_key(seed)
+    nb = (nu + 1) // 2
+    out = np.empty((cells.shape[0], 2 * nb))
+    for j in range(nb):
+        x0, x1, x2, x3 = philox4x32(np.uint64(j), cells & _U32, np.uint64(sweep),
+                                     ((cells >> np.uint64(32)) << np.uint64(8)) | np.uint64(1), k0, k1)
+        out[:, 2 * j] = _u52(x0, x1)
+        out[:, 2 * j + 1] = _u52(x2, x3)
+    return out[:, :nu]
+
+
+def entry_uniforms(seed, sweep, cells, genes):
+    """Per-entry uniforms (u_a: Bernoulli dropout draw, u_b: value draw).
+    Stream tag 0, counter (gene, cell_lo, sweep, cell_hi<<8)."""
+    cells = np.asarray(cells, dtype=np.uint64)
+    genes = np.asarray(genes, dtype=np.uint64)
+    k0, k1 = _seed_key(seed)
+    x0, x1, x2, x3 = philox4x32(genes, cells & _U32, np.uint64(sweep),
+                                 (cells >> np.uint64(32)) << np.uint64(8), k0, k1)
+    return _u52(x0, x1), _u52(x2, x3)
+
+
+_SQRT2 = math.sqrt(2.0)
+_SQRT2PI = math.sqrt(2.0 * math.pi)
+TRUNC_LOG_BRANCH = -30.0
+
+
+def trunc_z(u, r):
+    """Inverse-CDF draw of a standard normal truncated to (-inf, r]:
+    z with Phi(z) = u * Phi(r).  Replaces msm::rtnorm(upper=cutoff)
+    (R/EM_impute.R:191-192, R/do_impute.R:130-131) -- same distribution, one
+    uniform per draw.  For r < -30 the product underflows, so the equation is
+    solved in log space by 4 Newton steps on log Phi (erfcx form)."""
+    u = np.asarray(u, dtype=np.float64)
+    r = np.asarray(r, dtype=np.float64)
+    u, r = np.broadcast_arrays(u, r)
+    z = special.ndtri(u * special.ndtr(r))
+    deep = r < TRUNC_LOG_BRANCH
+    if np.any(deep):
+        rd = r[deep]
+        ud = u[deep]
+        # log Phi(x) = log(erfcx(-x/sqrt2)/2) - x^2/2
+        t = np.log(ud) + np.log(0.5 * special.erfcx(-rd / _SQRT2)) - 0.5 * rd * rd
+        zd = -np.sqrt(rd * rd - 2.0 * np.log(ud))
+        for _ in range(4):
+            e = 0.5 * special.erfcx(-zd / _SQRT2)
+            zd = zd - (np.log(e) - 0.5 * zd * zd - t) * e * _SQRT2PI
+        z = z.copy()
+        z[deep] = zd
+    return np.minimum(z, r)
+
+
+def sym_sqrt(M):
+    """Symmetric PSD square root (mixtools::rmvnorm uses V diag(sqrt(ev)) V^T)."""
+    w, V = np.linalg.eigh(0.5 * (M + M.T))
+    return (V * np.sqrt(np.maximum(w, 0.0))) @ V.T
+
+
+# ----------------------------------------------------------------------------
+# Lasso (replaces glmnet, R/EM_impute.R:256-261): exact minimiser of
+#   0.5 b'Ab - rhs'b + kappa |b|_1
+# ----------------------------------------------------------------------------
+def _polish(A, rhs, kappa, beta):
+    S = beta != 0.0
+    if not S.any():
+        return beta if np.all(np.abs(rhs) <= kappa * (1 + 1e-12)) else None
+    sgn = np.sign(beta[S])
+    try:
+        x = np.linalg.solve(A[np.ix_(S, S)], rhs[S] - kappa * sgn)
+    except np.linalg.LinAlgError:
+        return None
+    if np.any(np.sign(x) != sgn):
+        return None
+    full = np.zeros_like(beta)
+    full[S] = x
+    grad = rhs - A @ full
+    if np.any(np.abs(grad[~S]) > kappa * (1 + 1e-10) + 1e-300):
+        return None
+    return full
+
+
+def lasso_solve_batch(A, rhs, kappa, max_sweeps=20000, tol=1e-15):
+    """A: (K,K) shared or (G,K,K); rhs (G,K); kappa (G,).  Cyclic coordinate
+    descent from 0 (glmnet's start), then an exact active-set polish."""
+    rhs = np.asarray(rhs, dtype=np.float64)
+    G, K = rhs.shape
+    shared = (A.ndim == 2)
+    kappa = np.broadcast_to(np.asarray(kappa, dtype=np.float64), (G,))
+    beta = np.zeros((G, K))
+    r = rhs.copy()
+    live = np.arange(G)
+    for sweep in range(max_sweeps):
+        Al = A if shared else A[live]
+        bl = beta[live]
+        rl = r[live]
+        kl = kappa[live]
+        maxd = np.zeros(live.shape[0])
+        for k in range(K):
+            akk = Al[k, k] if shared else Al[:, k, k]
+            t = rl[:, k] + akk * bl[:, k]
+            bn = np.sign(t) * np.maximum(np.abs(t) - kl, 0.0) / akk
+            d = bn - bl[:, k]
+            col = Al[:, k] if shared else Al[:, :, k]
+            rl -= d[:, None] * col
+            bl[:, k] = bn
+            maxd = np.maximum(maxd, np.abs(d))
+        beta[live] = bl
+        r[live] = rl
+        scale = np.maximum(1.0, np.abs(bl).max(axis=1))
+        done = maxd <= tol * scale
+        if sweep >= 3 and (sweep % 4 == 3 or done.all()):
+            # try the exact polish; genes that verify leave the live set
+            keep = np.ones(live.shape[0], dtype=bool)
+            for j, g in enumerate(live):
+                Ag = A if shared else A[g]
+                p = _polish(Ag, rhs[g], kappa[g], beta[g])
+                if p is not None:
+                    beta[g] = p
+                    keep[j] = False
+                elif done[j]:
+                    keep[j] = False
+            live = live[keep]
+            if live.size == 0:
+                break
+    return beta
+
+
+def lasso_solve(A, rhs, kappa):
+    return lasso_solve_batch(np.asarray(A), np.asarray(rhs)[None, :], np.array([kappa]))[0]
+
+
+# ----------------------------------------------------------------------------
+# lambda step (replaces Rsolnp::solnp, R/EM_impute.R:278-304)
+# ----------------------------------------------------------------------------
+def lambda_solve_k(E, c, x0, T, max_it=500):
+    """min sum(E/x + c log x)  s.t. sum x = T, x > 0, from x0 (sum x0 = T).
+    Damped Newton on the equality-constrained problem with |f''| curvature
+    and Armijo backtracking.  Mirrored operation-for-operation by
+    csrc/mstep.cu::lambda_solve_k."""
+    E = np.asarray(E, dtype=np.float64)
+    c = np.asarray(c, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64)
+    mt = x.shape[0]
+
+    def F(v):
+        s = 0.0
+        for m in range(mt):
+            s += E[m] / v[m] + c[m] * math.log(v[m])
+        return s
+
+    f = F(x)
+    for _ in range(max_it):
+        g = np.empty(mt)
+        hm = np.empty(mt)
+        sg = 0.0
+        sh = 0.0
+        for m in range(mt):
+            xi = x[m]
+            g[m] = -E[m] / (xi * xi) + c[m] / xi
+            h = 2.0 * E[m] / (xi * xi * xi) - c[m] / (xi * xi)
+            h = abs(h)
+            if h < 1e-300:
+                h = 1e-300
+            hm[m] = h
+            sg += g[m] / h
+            sh += 1.0 / h
+        nu = -sg / sh
+        dx = np.empty(mt)
+        gd = 0.0
+        amax = 1.0
+        dmax = 0.0
+        for m in range(mt):
+            dx[m] = -(g[m] + nu) / hm[m]
+            gd += g[m] * dx[m]
+            if dx[m] < 0.0:
+                a = -0.9 * x[m] / dx[m]
+                if a < amax:
+                    amax = a
+            if abs(dx[m]) > dmax:
+                dmax = abs(dx[m])
+        if dmax <= 1e-15 * T:
+            break
+        a = amax
+        accepted = False
+        for _bt in range(60):
+            xn = x + a * dx
+            fn = F(xn)
+            if fn <= f + 1e-4 * a * gd + 1e-14 * abs(f):
+                accepted = True
+                break
+            a *= 0.5
+        if not accepted:
+            break
+        x = xn
+        f = fn
+    return x
+
+
+def lambda_step(Em_full, nz, beta, lam, M0, K0):
+    """R/EM_impute.R:279-303.  Em_full: (K0, M0) with
+    Em[k,m] = sum_i z_im W_m[i,k]^2 + M_m[k,k] nz_m."""
+    lam = lam.copy()
+    ind = np.nonzero((nz > K0 + 1) & (nz > 3))[0]                 # :279
+    mt = ind.shape[0]
+    if mt > 1:                                                    # :281
+        Em = Em_full[:, ind]                                      # (K0, mt)   :282-285
+        not_ind = np.setdiff1d(np.arange(M0), ind)
+        lam[not_ind, :] = 1.0 / M0                                # :288
+        lam_init = (Em + 1.0).T / (nz[ind] + 1.0)[:, None]        # (mt, K0)   :289
+        lam_init = lam_init / lam_init.sum(axis=0)[None, :] * mt / M0   # :290
+        for k in range(K0):                                       # :292
+            if np.all(beta[:, k] == 0):                           # :293
+                lam[:, k] = 1.0 / M0
+            else:
+                lam[ind, k] = lambda_solve_k(Em[k, :], nz[ind] - 2.0, lam_init[:, k], mt / M0)
+    else:
+        lam = np.full((M0, K0), 1.0 / M0)                         # :302
+    return lam
+
+
+# ----------------------------------------------------------------------------
+# E-pass pieces
+# ----------------------------------------------------------------------------
+def cluster_terms(beta, sigma, lam, m):
+    """R/EM_impute.R:123-125 (= R/do_impute.R:70-72)."""
+    beta2 = beta / sigma[:, m][:, None]
+    Mm = np.linalg.inv(beta.T @ beta2 + np.diag(1.0 / lam[m]))
+    sgn, logdet = np.linalg.slogdet(Mm)
+    dt = np.sum(np.log(sigma[:, m])) + np.sum(np.log(lam[m])) - logdet
+    return beta2, Mm, dt
+
+
+def epass(Yc, beta, sigma, lam, mu, pi, pi_const=PI_REF, M_list=None, beta2_fix=None, dt_fix=None):
+    """One E-pass: loglik (n,M0) incl. log pi, lik, sconst.  With
+    ``beta2_fix``/``dt_fix`` it is the MC-loop pass of R/EM_impute.R:202-213
+    (stale beta2, dt of cluster M0 -- Q1) reusing ``M_list``."""
+    G, n = Yc.shape
+    M0 = mu.shape[1]
+    ll = np.empty((n, M0))
+    Ms, b2s, dts = [], [], []
+    for m in range(M0):
+        if M_list is None:
+            beta2, Mm, dt = cluster_terms(beta, sigma, lam, m)
+        else:
+            Mm = M_list[m]
+            beta2, dt = beta2_fix, dt_fix
+        R = Yc - mu[:, m][:, None]
+        y = np.sum(R / sigma[:, m][:, None] * R, axis=0)                      # :128
+        x2 = R.T @ beta2                                                     # :129
+        y = y - np.sum((x2 @ Mm) * x2, axis=1)                               # :130
+        ll[:, m] = (-y - dt - G * math.log(2 * pi_const)) / 2                # :135
+        Ms.append(Mm)
+        b2s.append(beta2)
+        dts.append(dt)
+    ll = ll + np.log(pi)[None, :]                                            # :138
+    sconst = ll.max(axis=1)                                                  # :139
+    lik = np.exp(ll - sconst[:, None])                                       # :140-141
+    return ll, lik, sconst, Ms, b2s, dts
+
+
+def factor_means(Yc, beta, sigma, mu, Ms):
+    """R/EM_impute.R:155-157: Wm[[m]] = t(M_m B' ((Y-mu_m)/sigma_m)), n x K0."""
+    return [(Ms[m] @ beta.T @ ((Yc - mu[:, m][:, None]) / sigma[:, m][:, None])).T
+            for m in range(len(Ms))]
+
+
+def sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, gene_mean, gene_sd,
+                 cutoff, seed, sweep, cell0=0, draw_membership=True, lower=-np.inf,
+                 upper=np.inf, clip=True):
+    """One MC imputation sweep, R/EM_impute.R:163-199 / R/do_impute.R:107-136,
+    with every random variate taken from the Philox tape.  Modifies Yc in
+    place; returns the sampled membership (0-based) and factors."""
+    G, n = Yc.shape
+    M0 = len(Ms)
+    K0 = beta.shape[1]
+    cells = np.arange(n, dtype=np.uint64) + np.uint64(cell0)
+    U = cell_uniforms(seed, sweep, cells, 1 + K0)
+    if draw_membership:
+        cum = np.cumsum(z, axis=1)
+        im = np.minimum((U[:, :1] >= cum).sum(axis=1), M0 - 1)               # :164
+    else:
+        im = np.zeros(n, dtype=np.int64)                                     # :166
+    eps = special.ndtri(U[:, 1:1 + K0])
+    Mh = [sym_sqrt(Mm) for Mm in Ms]
+    f = np.empty((n, K0))
+    for m in range(M0):
+        sel = im == m
+        if sel.any():
+            f[sel] = Wm[m][sel] + eps[sel] @ Mh[m]                            # :171
+    gi, ci = np.nonzero(mask)                                                # :173
+    mm = im[ci]
+    ms = (mu[gi, mm] + np.einsum("ek,ek->e", beta[gi], f[ci])) * gene_sd[gi] + gene_mean[gi]   # :175
+    sds = np.sqrt(sigma[gi, mm]) * gene_sd[gi]                               # :176
+    p = pg[gi, celltype0[ci]]                                                # :177
+    r = (cutoff - ms) / sds
+    prob = special.ndtr(r)                                                   # :179
+    prob_drop = (1 - p) / (prob * p + (1 - p))                               # :180
+    ua, ub = entry_uniforms(seed, sweep, cells[ci], gi)
+    drop = ua < prob_drop                                                    # :181
+    x = np.where(drop, ms + sds * special.ndtri(ub),                         # :186
+                 ms + sds * trunc_z(ub, r))                                  # :191-192
+    if clip:
+        x = np.minimum(x, upper)                                             # :195
+        x = np.maximum(x, lower)                                             # :196
+    Yc[gi, ci] = (x - gene_mean[gi]) / gene_sd[gi]                           # :198
+    return im, f
+
+
+def expected_impute(ms, sds, p, cutoff):
+    """Closed-form E[x] of one zero entry (north_star's 'conditional
+    expectation'; hinted at in R/SIMPLE.R:59) -- used by distributional tests."""
+    r = (cutoff - ms) / sds
+    prob = special.ndtr(r)
+    pd = (1 - p) / (prob * p + (1 - p))
+    mills = np.exp(-0.5 * r * r) / _SQRT2PI / np.maximum(prob, 1e-300)
+    return pd * ms + (1 - pd) * (ms - sds * mills)
+
+
+# ----------------------------------------------------------------------------
+# Sufficient statistics (cell-additive => one all-reduce per EM iteration)
+# ----------------------------------------------------------------------------
+def local_stats(Yc, z, Wm, shared_sigma):
+    """Statistics of SURVEY.md section 3.3 for one shard of cells."""
+    G, n = Yc.shape
+    M0 = z.shape[1]
+    K0 = Wm[0].shape[1]
+    st = {}
+    st["nz"] = z.sum(axis=0)
+    st["c"] = np.sqrt(z).sum(axis=0)
+    st["S"] = np.stack([(Wm[m] * z[:, m][:, None]).T @ Wm[m] for m in range(M0)])
+    st["a"] = np.stack([(Wm[m] * z[:, m][:, None]).sum(axis=0) for m in range(M0)])
+    st["U"] = Yc @ z
+    st["Uh"] = Yc @ np.sqrt(z)
+    if shared_sigma:
+        Wbar = sum(Wm[m] * z[:, m][:, None] for m in range(M0))
+        st["Tbar"] = Yc @ Wbar                                   # sum_m T_m
+        st["R2"] = (Yc * Yc) @ z.sum(axis=1)                     # sum_m U2[,m]
+    else:
+        st["T"] = np.stack([Yc @ (Wm[m] * z[:, m][:, None]) for m in range(M0)])
+        st["U2"] = (Yc * Yc) @ z
+    return st
+
+
+_ORDER_SHARED = ("Tbar", "U", "Uh", "R2", "S", "a", "nz", "c")
+_ORDER_GENERAL = ("T", "U", "Uh", "U2", "S", "a", "nz", "c")
+
+
+def stats_pack(st):
+    order = _ORDER_SHARED if "Tbar" in st else _ORDER_GENERAL
+    return np.concatenate([np.ravel(st[k]) for k in order])
+
+
+def stats_unpack(buf, G, M0, K0, shared_sigma):
+    order = _ORDER_SHARED if shared_sigma else _ORDER_GENERAL
+    shapes = {"Tbar": (G, K0), "T": (M0, G, K0), "U": (G, M0), "Uh": (G, M0), "R2": (G,),
+              "U2": (G, M0), "S": (M0, K0, K0), "a": (M0, K0), "nz": (M0,), "c": (M0,)}
+    st, o = {}, 0
+    for k in order:
+        sz = int(np.prod(shapes[k]))
+        st[k] = buf[o:o + sz].reshape(shapes[k])
+        o += sz
+    return st
+
+
+def mstep_from_stats(st, n, Ms, beta, sigma, lam, mu, M0, K0, it, penl, max_lambda, est_lam,
+                     sigma0, pi_alpha):
+    """M-step of R/EM_impute.R:234-318 from global statistics (n = total cells)."""
+    G = beta.shape[0]
+    nz = st["nz"]
+    C = np.stack([st["S"][m] + nz[m] * Ms[m] for m in range(M0)])            # S_m + Vm_m  (:234)
+    N = M0 * n + K0
+    shared = "Tbar" in st
+    D = (st["U2"] if not shared else None)
+    if shared:
+        sg0 = sigma[:, 0]
+        A = C.sum(axis=0)                                                    # Gram * sigma_g
+        bt = st["Tbar"] - mu @ st["a"]                                       # sum_m (T_m - mu a_m)
+        d2 = st["R2"] + np.sum(-2 * mu * st["U"] + mu * mu * nz[None, :], axis=1)
+        sumY = np.sum(st["Uh"] - mu * st["c"][None, :], axis=1) / np.sqrt(sg0)
+        sumY2 = d2 / sg0
+        var = (sumY2 - sumY * sumY / N) / (N - 1)                            # var(Y_aug)  (Q7)
+        kappa = penl * var                                                   # :258
+        nb = lasso_solve_batch(A, bt, kappa * sg0)
+        quad = np.einsum("gj,jk,gk->g", nb, A, nb)
+        sg = (d2 - 2 * np.sum(nb * bt, axis=1) + quad + 1) / (n + 3)         # :263-267
+    else:
+        D2 = D - 2 * mu * st["U"] + mu * mu * nz[None, :]                    # (G,M0)
+        bm = st["T"] - mu.T[:, :, None] * st["a"][:, None, :]                # (M0,G,K0)
+        A = np.einsum("mjk,gm->gjk", C, 1.0 / sigma)
+        rhs = np.einsum("mgk,gm->gk", bm, 1.0 / sigma)
+        sumY = np.sum((st["Uh"] - mu * st["c"][None, :]) / np.sqrt(sigma), axis=1)
+        sumY2 = np.sum(D2 / sigma, axis=1)
+        var = (sumY2 - sumY * sumY / N) / (N - 1)
+        kappa = penl * var
+        nb = lasso_solve_batch(A, rhs, kappa)
+        quad = np.einsum("gj,mjk,gk->g", nb, C, nb)
+        sg = (D2.sum(axis=1) - 2 * np.einsum("gk,mgk->g", nb, bm) + quad + 1) / (n + 3)
+    priorB = float(np.sum(penl * var / sg * np.abs(nb).sum(axis=1)))         # :268,275
+    beta = nb
+    sigma = np.repeat(np.clip(sg, 1e-4, 9.0)[:, None], M0, axis=1)           # :269,273-274
+    if max_lambda and it >= est_lam:                                         # :278
+        Em = np.stack([np.diag(st["S"][m]) + np.diag(Ms[m]) * nz[m] for m in range(M0)], axis=1)
+        lam = lambda_step(Em, nz, beta, lam, M0, K0)
+    mu = mu.copy()
+    for m in range(M0):                                                      # :307-315 (Woodbury, no GxG)
+        s = nz[m] + sigma[:, m] / sigma0
+        b2 = beta / s[:, None]
+        v = st["U"][:, m]
+        Cm = np.diag(sigma0 / lam[m]) + b2.T @ beta
+        mu[:, m] = v / s - b2 @ np.linalg.solve(Cm, b2.T @ v)
+    pi = (nz + pi_alpha - 1) / (n + pi_alpha * M0 - M0)                      # :318
+    return beta, sigma, lam, mu, pi, priorB
+
+
+# ----------------------------------------------------------------------------
+# EM_impute
+# ----------------------------------------------------------------------------
+def _prologue(Y, z, mu, M0, lower, upper, compat):
+    Y = np.array(Y, dtype=np.float64, order="F")
+    Y = np.minimum(Y, upper)                                                 # :82
+    Y = np.maximum(Y, lower)                                                 # :83
+    G, n = Y.shape
+    gene_mean = Y.mean(axis=1)                                               # :88
+    gene_sd = np.ones(G)                                                     # :89
+    Yc = Y - gene_mean[:, None]                                              # :90
+    if mu is None:
+        if M0 > 1 and z is not None:
+            mu = Yc @ z / (n if compat & COMPAT_MU_DIV_N else 1.0)           # :95  (Q3)
+            if not compat & COMPAT_MU_DIV_N:
+                mu = mu / np.maximum(z.sum(axis=0), 1e-300)[None, :]
+        else:
+            mu = np.zeros((G, M0))                                           # :97
+    return Yc, gene_mean, gene_sd, np.array(mu, dtype=np.float64)
+
+
+def _mstep_literal(Yc, z, Wm, Ms, nz, beta, sigma, lam, mu, M0, K0, it, penl, max_lambda,
+                   est_lam, sigma0, pi_alpha):
+    """R/EM_impute.R:234-318 with the explicit augmented design."""
+    G, n = Yc.shape
+    Vm = [Ms[m] * nz[m] for m in range(M0)]                                  # :234
+    nbs = np.empty((G, K0))
+    sgs = np.empty(G)
+    prs = np.empty(G)
+    sq = np.sqrt(z)
+    for g in range(G):                                                       # :238
+        V = sum(Vm[m] / sigma[g, m] for m in range(M0))                      # :240
+        Wt = np.concatenate([Wm[m] * sq[:, m][:, None] / math.sqrt(sigma[g, m]) for m in range(M0)])  # :247
+        Yt = np.concatenate([(Yc[g] - mu[g, m]) * sq[:, m] / math.sqrt(sigma[g, m]) for m in range(M0)])  # :245
+        ML = np.linalg.cholesky(V).T                                         # :250 (upper)
+        W_aug = np.concatenate([Wt, ML])                                     # :252
+        Y_aug = np.concatenate([Yt, np.zeros(K0)])                           # :253
+        kappa = penl * np.var(Y_aug, ddof=1)                                 # :258 (x N of glmnet's lambda)
+        nb = lasso_solve(W_aug.T @ W_aug, W_aug.T @ Y_aug, kappa)            # :257-261
+        sg = 0.0
+        for m in range(M0):                                                  # :263-266
+            sg += np.sum((Yc[g] - mu[g, m] - Wm[m] @ nb) ** 2 * z[:, m]) + nb @ Vm[m] @ nb
+        sg = (sg + 1) / (n + 3)                                              # :267
+        prs[g] = penl * np.var(Y_aug, ddof=1) / sg * np.sum(np.abs(nb))      # :268
+        nbs[g] = nb
+        sgs[g] = sg
+    beta = nbs                                                               # :271
+    sigma = np.repeat(np.clip(sgs, 1e-4, 9.0)[:, None], M0, axis=1)          # :272-274
+    priorB = float(prs.sum())                                                # :275
+    if max_lambda and it >= est_lam:                                         # :278
+        Em = np.stack([np.sum(Wm[m] ** 2 * z[:, m][:, None], axis=0) + np.diag(Ms[m]) * nz[m]
+                       for m in range(M0)], axis=1)                          # :282-285
+        lam = lambda_step(Em, nz, beta, lam, M0, K0)
+    mu = mu.copy()
+    for m in range(M0):                                                      # :307-315
+        st = nz[m] + sigma[:, m] / sigma0
+        b2 = beta / st[:, None]
+        bigM = np.diag(1.0 / st) - b2 @ np.linalg.solve(np.diag(sigma0 / lam[m]) + b2.T @ beta, b2.T)
+        mu[:, m] = bigM @ (Yc @ z[:, m])
+    pi = (nz + pi_alpha - 1) / (n + pi_alpha * M0 - M0)                      # :318
+    return beta, sigma, lam, mu, pi, priorB
+
+
+def _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
+               est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
+               seed, compat, literal, shards=None, trace=None):
+    pi_const = PI_REF if compat & COMPAT_PI else math.pi
+    z = None if z is None else np.array(z, dtype=np.float64)
+    Yc, gene_mean, gene_sd, mu = _prologue(Y, z, mu, M0, lower, upper, compat)
+    G, n = Yc.shape
+    beta = np.array(beta, dtype=np.float64)
+    sigma = np.array(sigma, dtype=np.float64)
+    lam = np.array(lam, dtype=np.float64)
+    pi = np.array(pi, dtype=np.float64)
+    pg = np.asarray(pg, dtype=np.float64)
+    if pg.ndim == 1:
+        pg = pg[:, None]
+    celltype0 = np.zeros(n, dtype=np.int64) if celltype is None else np.asarray(celltype, dtype=np.int64) - 1  # :101-102
+    mask = np.asarray(Y0) <= cutoff
+    tot = np.zeros(iter)
+    priorB = 0.0                                                             # :119
+    sweep = 0
+    Wm, Ms = None, None
+    for it in range(1, iter + 1):                                            # :120
+        ll, lik, sconst, Ms, b2s, dts = epass(Yc, beta, sigma, lam, mu, pi, pi_const)
+        tot[it - 1] = np.sum(np.log(lik.sum(axis=1)) + sconst)               # :144
+        tot[it - 1] -= priorB if compat & COMPAT_PRIORB_PREV else 0.0        # :146
+        if it >= est_z or z is None:                                         # :148
+            z = lik / lik.sum(axis=1)[:, None]
+        nz = z.sum(axis=0)                                                   # :152
+        Wm = factor_means(Yc, beta, sigma, mu, Ms)                           # :155-157
+        if it >= impt_it + 1:                                                # :161
+            for _ in range(num_mc):                                          # :162
+                sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, gene_mean,
+                             gene_sd, cutoff, seed, sweep, 0, draw_membership=(M0 > 1),
+                             lower=lower, upper=upper, clip=True)
+                sweep += 1
+                if compat & COMPAT_STALE_DT:                                 # :202-213  (Q1)
+                    ll, lik, sconst, _, _, _ = epass(Yc, beta, sigma, lam, mu, pi, pi_const,
+                                                     M_list=Ms, beta2_fix=b2s[M0 - 1], dt_fix=dts[M0 - 1])
+                else:
+                    ll, lik, sconst, _, _, _ = epass(Yc, beta, sigma, lam, mu, pi, pi_const)
+                if it >= est_z or z is None:                                 # :220
+                    z = lik / lik.sum(axis=1)[:, None]
+                nz = z.sum(axis=0)                                           # :224
+                Wm = factor_means(Yc, beta, sigma, mu, Ms)                   # :227-229
+        if trace is not None:
+            trace.append(dict(it=it, z=z.copy(), Wm=[w.copy() for w in Wm], Ms=[m.copy() for m in Ms],
+                              Yc=Yc.copy(), tot=tot[it - 1]))
+        if literal:
+            beta, sigma, lam, mu, pi, priorB = _mstep_literal(
+                Yc, z, Wm, Ms, nz, beta, sigma, lam, mu, M0, K0, it, penl, max_lambda, est_lam,
+                sigma0, pi_alpha)
+        else:
+            shared = bool(np.all(sigma == sigma[:, :1]))
+            bounds = [0, n] if shards is None else list(shards)
+            buf = None
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                st = local_stats(Yc[:, a:b], z[a:b], [w[a:b] for w in Wm], shared)
+                buf = stats_pack(st) if buf is None else buf + stats_pack(st)   # the all-reduce
+            st = stats_unpack(buf, G, M0, K0, shared)
+            beta, sigma, lam, mu, pi, priorB = mstep_from_stats(
+                st, n, Ms, beta, sigma, lam, mu, M0, K0, it, penl, max_lambda, est_lam, sigma0,
+                pi_alpha)
+    Yout = Yc * gene_sd[:, None] + gene_mean[:, None]                        # :335
+    return dict(loglik=tot, pi=pi, mu=mu, sigma=sigma, beta=beta, **{"lambda": lam}, z=z, Ef=Wm,
+                Varf=Ms, Y=Yout, geneM=gene_mean, geneSd=gene_sd, priorB=priorB)   # :337-338
+
+
+def em_impute_ref(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=None, celltype=None,
+                  penl=1, est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1,
+                  num_mc=3, lower=-np.inf, upper=np.inf, seed=0, compat=COMPAT_DEFAULT, trace=None):
+    """Literal restatement of EM_impute (R/EM_impute.R:75-339)."""
+    return _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
+                      est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
+                      seed, compat, literal=True, trace=trace)
+
+
+def em_impute_fast(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=None, celltype=None,
+                   penl=1, est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1,
+                   num_mc=3, lower=-np.inf, upper=np.inf, seed=0, compat=COMPAT_DEFAULT,
+                   shards=None, trace=None):
+    """Same algorithm with the sufficient-statistic M-step; ``shards`` = list of
+    cell boundaries emulating the multi-GPU partition + all-reduce."""
+    return _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
+                      est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
+                      seed, compat, literal=False, shards=shards, trace=trace)
+
+
+# ----------------------------------------------------------------------------
+# do_impute
+# ----------------------------------------------------------------------------
+def do_impute_ref(dat, Y, beta, lam, sigma, mu, pi, pos_mean=None, pos_sd=None, celltype=None,
+                  mcmc=10, burnin=2, pg=0.5, cutoff=0.1, seed=0, compat=COMPAT_DEFAULT,
+                  consensus=True):
+    """Restatement of do_impute (R/do_impute.R:29-160)."""
+    pi_const = PI_REF if compat & COMPAT_PI else math.pi
+    Y = np.array(Y, dtype=np.float64)
+    G, n = Y.shape
+    M0 = mu.shape[1]
+    K0 = beta.shape[1]
+    pos_mean = np.zeros(G) if pos_mean is None else np.asarray(pos_mean, dtype=np.float64)   # :38-39
+    pos_sd = np.ones(G) if pos_sd is None else np.asarray(pos_sd, dtype=np.float64)          # :40-41
+    celltype0 = np.zeros(n, dtype=np.int64) if celltype is None else np.asarray(celltype, dtype=np.int64) - 1
+    MB = int(celltype0.max()) + 1                                            # :45
+    pg = np.asarray(pg, dtype=np.float64)
+    if pg.ndim == 0 or pg.size == 1:
+        pg = np.full((G, MB), float(pg))                                     # :47-48
+    Yc = (Y - pos_mean[:, None]) / pos_sd[:, None]                           # :50
+    mask = np.asarray(dat) <= cutoff
+    tot = np.zeros(mcmc + burnin)
+    rec1 = np.zeros((G, n))
+    rec2 = np.zeros((G, n))
+    rEF = np.zeros((n, K0))
+    rF2 = np.zeros((n, K0))
+    rVF = np.zeros((n, K0))          # only the diagonal of record_varF is used (:156-157)
+    cons = np.zeros((n, n)) if consensus else None
+    for it in range(1, mcmc + burnin + 1):                                   # :67
+        ll, lik, sconst, Ms, _, _ = epass(Yc, beta, sigma, lam, mu, pi, pi_const)
+        tot[it - 1] = np.sum(np.log(lik.sum(axis=1)) + sconst)               # :89
+        z = lik / lik.sum(axis=1)[:, None]                                   # :91
+        if it > burnin and consensus:
+            cons += z @ z.T                                                  # :96
+        Wm = factor_means(Yc, beta, sigma, mu, Ms)                           # :102-104
+        sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, pos_mean, pos_sd,
+                     cutoff, seed, it - 1, 0, draw_membership=True, clip=False)   # :107-136
+        if it > burnin:                                                      # :139
+            rec1 += Yc
+            rec2 += Yc * Yc
+            for m in range(M0):
+                rEF += Wm[m] * z[:, m][:, None]
+                rF2 += Wm[m] ** 2 * z[:, m][:, None]
+                rVF += z[:, m][:, None] * np.diag(Ms[m])[None, :]
+    varF = rF2 / mcmc - (rEF / mcmc) ** 2 + rVF / mcmc                       # :156-157
+    return dict(loglik=float(np.mean(tot[burnin:])),                          # :158
+                impt=(rec1 / mcmc) * pos_sd[:, None] + pos_mean[:, None],
+                impt_var=rec2 / mcmc - (rec1 / mcmc) ** 2, EF=rEF / mcmc, varF=varF,
+                consensus_cluster=None if cons is None else cons / mcmc)
+
+
+# ----------------------------------------------------------------------------
+# Synthetic inputs (restates utils/utils.R:2-92 simulation_bulk, scaled)
+# ----------------------------------------------------------------------------
+def simulate(n=300, S0=20, K=6, MC=3, block_size=32, overlap=0, indepG=None, G=1000, dropr=0.3,
+             seed=1, filter_genes=True):
+    rng = np.random.default_rng(seed)
+    Z = np.sort(rng.integers(0, MC, size=n))                                 # :8-10
+    if indepG is None:
+        indepG = G - (block_size + (K - 1) * (block_size - overlap))
+    G = block_size + (K - 1) * (block_size - overlap) + indepG               # :14
+    Sigma = rng.gamma(2.0, 0.3, size=G)                                      # :20
+    Mu = np.repeat(np.exp(rng.normal(0.5, 0.5, size=G))[:, None], MC, axis=1)  # :23
+    act = rng.permutation(G)[:S0 * MC]                                       # :25
+    for m in range(MC):                                                      # :28-33
+        ss = act[m * S0:(m + 1) * S0]
+        Mu[ss, m] *= rng.choice(np.array([0.2, 0.5, 1.2, 1.5, 2.0]), size=S0)
+    Gamma = np.zeros((G, K))
+    for i in range(K):                                                       # :38-45
+        a = (block_size - overlap) * i
+        Gamma[a:a + block_size, i] = 1
+    B = Gamma / 4                                                            # :47
+    W = rng.standard_normal((K, n))                                          # :54
+    Y = Mu[:, Z] + B @ W
+    Y += rng.standard_normal((G, n)) * Sigma[:, None]                        # :55-56
+    Y2 = Y.copy()
+    pdrop = np.exp(-dropr * Mu.mean(axis=1) ** 2)                            # :66
+    dZ = rng.random((G, n)) < pdrop[:, None]
+    Y2[dZ] = 0
+    Y2[Y2 < 0] = 0                                                           # :67-68
+    if filter_genes:
+        ind = np.nonzero((Y2 != 0).sum(axis=1) > 4)[0]                       # :70
+        Y2, Y, B, Mu, Sigma = Y2[ind], Y[ind], B[ind], Mu[ind], Sigma[ind]
+    return dict(Y2=np.asfortranarray(Y2), Y=Y, B=B, W=W, Mu=Mu, Sigma=Sigma, Z=Z + 1,
+                bulk=Mu[:, Z].mean(axis=1))
+
+
+def bench_state(sim, K0, M0, cutoff=0.1, pgv=0.6, seed=1):
+    """EM-state initialisation for kernel benches/tests:
+    beta ~ N(0, M0/K0), sigma=1, lambda=1/M0, pi=1/M0, z=one-hot(Z),
+    pg=0.6, initial Y = Y2 with zeros replaced by truncated-normal draws."""
+    rng = np.random.default_rng(seed + 1000)
+    Y2 = sim["Y2"]
+    G, n = Y2.shape
+    beta = rng.standard_normal((G, K0)) * math.sqrt(M0 / K0)
+    sigma = np.ones((G, M0))
+    lam = np.full((M0, K0), 1.0 / M0)
+    pi = np.full(M0, 1.0 / M0)
+    clus = ((sim["Z"] - 1) % M0) + 1
+    z = np.zeros((n, M0))
+    z[np.arange(n), clus - 1] = 1.0
+    pg = np.full((G, M0), pgv)
+    mask = Y2 <= cutoff
+    gm = np.array([Y2[g][~mask[g]].mean() if (~mask[g]).any() else 1.0 for g in range(G)])
+    gs = np.array([Y2[g][~mask[g]].std() + 0.1 if (~mask[g]).any() else 1.0 for g in range(G)])
+    gi, ci = np.nonzero(mask)
+    r = (cutoff - gm[gi]) / gs[gi]
+    Yi = np.array(Y2, order="F")
+    Yi[gi, ci] = gm[gi] + gs[gi] * trunc_z(rng.random(gi.shape[0]) * 0.999 + 0.0005, r)
+    return dict(Y=np.asfortranarray(Yi), Y0=Y2, pg=pg, beta=beta, sigma=sigma, lam=lam, pi=pi, z=z,
+                celltype=clus.astype(np.int32))
