@@ -1,0 +1,184 @@
+/*
+ * simples_b200 -- C ABI of the B200-native SIMPLEs EM imputation hot path.
+ *
+ * The reference (JunLiuLab/SIMPLEs) is a pure-R package with no FFI
+ * (NAMESPACE:1-14).  The boundary this library replaces is therefore the R
+ * function boundary of the two internal hot-path functions
+ *
+ *   EM_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda, pi, z,
+ *             mu, celltype, penl, est_z, max_lambda, est_lam, impt_it,
+ *             sigma0, pi_alpha, verbose, num_mc, lower, upper)
+ *                                                    R/EM_impute.R:75-78
+ *   do_impute(dat, Y, beta, lambda, sigma, mu, pi, pos_mean, pos_sd,
+ *             celltype, mcmc, burnin, verbose, pg, cutoff)
+ *                                                    R/do_impute.R:29-30
+ *
+ * A `.Call` shim (r/simples_rcall.c, shipped as source) marshals the R
+ * arguments 1:1 into the structs below; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - All matrices are FP64, COLUMN-MAJOR (R layout), owned by the caller.
+ *     Inputs are never modified (R value semantics).
+ *   - `celltype` is 1-based (R), NULL = all cells are type 1.
+ *   - Every entry point returns 0 on success, a negative SIMPLES_E* code on
+ *     failure; simples_last_error() gives the message (thread-local).
+ *   - There is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with SIMPLES_ENODEV.
+ *   - Multi-GPU: one process per GPU.  Each process passes its contiguous
+ *     shard of cells (columns of Y/Y0, rows of z, slice of celltype),
+ *     `n_total`/`cell_offset`, and an `allreduce` callback that sums a device
+ *     buffer of doubles over all ranks in place (the host layer wires it to
+ *     NCCL through torch.distributed).  Exactly one all-reduce per EM
+ *     iteration plus two at call start (gene means, default mu).
+ */
+#ifndef SIMPLES_B200_H
+#define SIMPLES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMPLES_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SIMPLES_API __attribute__((visibility("default")))
+#else
+#define SIMPLES_API
+#endif
+
+#define SIMPLES_OK        0
+#define SIMPLES_EINVAL   -1   /* bad argument                          */
+#define SIMPLES_ENODEV   -2   /* no CUDA device / not initialised      */
+#define SIMPLES_ECUDA    -3   /* CUDA runtime error                    */
+#define SIMPLES_ENOMEM   -4   /* device or host allocation failed      */
+#define SIMPLES_ENUMERIC -5   /* non-finite log-likelihood             */
+#define SIMPLES_ECOMM    -6   /* all-reduce callback failed            */
+
+/* ref_compat_flags: reproduce reference quirks; default all on */
+#define SIMPLES_COMPAT_STALE_DT     1u  /* Q1  R/EM_impute.R:206,212          */
+#define SIMPLES_COMPAT_PI           2u  /* Q2  PI = 3.14159265359, :80        */
+#define SIMPLES_COMPAT_MU_DIV_N     4u  /* Q3  default mu = Y z / n, :95      */
+#define SIMPLES_COMPAT_PRIORB_PREV  8u  /* Q5  tot[it] -= previous priorB     */
+#define SIMPLES_COMPAT_DEFAULT     15u
+
+/* Sum `count` doubles at device pointer `dev_buf` over all ranks, in place,
+ * ordered after prior work on `stream` (a cudaStream_t) and before later
+ * work on it.  Return 0 on success. */
+typedef int (*simples_allreduce_fn)(void *user, double *dev_buf, size_t count, void *stream);
+
+/* ---- EM_impute (R/EM_impute.R:75-339) ---------------------------------- */
+typedef struct simples_em_args {
+    int32_t G, n, M0, K0, MB;       /* genes, local cells, clusters, factors, ncol(pg) */
+    const double *Y;                /* G x n   initial imputed matrix                  */
+    const double *Y0;               /* G x n   observed matrix (mask = Y0 <= cutoff)   */
+    const double *pg;               /* G x MB  P(normal component) per cell type       */
+    double cutoff;
+    int32_t iter;
+    const double *beta;             /* G x K0 */
+    const double *sigma;            /* G x M0 */
+    const double *lambda;           /* M0 x K0 */
+    const double *pi;               /* M0 */
+    const double *z;                /* n x M0, or NULL (=> computed at it = 1)         */
+    const double *mu;               /* G x M0, or NULL (=> Y z / n, R/EM_impute.R:93-99) */
+    const int32_t *celltype;        /* n, 1-based, or NULL                             */
+    double penl;
+    int32_t est_z, max_lambda, est_lam, impt_it;
+    double sigma0, pi_alpha;
+    int32_t num_mc;
+    double lower, upper;
+    uint64_t seed;                  /* Philox key of the variate tape                  */
+    uint32_t ref_compat_flags;
+    int64_t n_total;                /* global cell count (0 => n)                      */
+    int64_t cell_offset;            /* global index of local cell 0                    */
+    simples_allreduce_fn allreduce; /* NULL => single rank                             */
+    void *allreduce_user;
+    void *stream;                   /* cudaStream_t, NULL => library-owned stream      */
+} simples_em_args;
+
+/* Return list of EM_impute (R/EM_impute.R:337-338); any pointer may be NULL
+ * to skip that output. */
+typedef struct simples_em_out {
+    double *loglik;                 /* iter                                            */
+    double *pi;                     /* M0                                              */
+    double *mu;                     /* G x M0                                          */
+    double *sigma;                  /* G x M0                                          */
+    double *beta;                   /* G x K0                                          */
+    double *lambda;                 /* M0 x K0                                         */
+    double *z;                      /* n x M0                                          */
+    double *Ef;                     /* M0 matrices n x K0, back to back                */
+    double *Varf;                   /* M0 matrices K0 x K0, back to back               */
+    double *Y;                      /* G x n   last imputed sample, un-centred         */
+    double *geneM;                  /* G                                               */
+    double *geneSd;                 /* G (all 1, R/EM_impute.R:89)                     */
+    double *priorB;                 /* 1                                               */
+} simples_em_out;
+
+/* ---- do_impute (R/do_impute.R:29-160) ---------------------------------- */
+typedef struct simples_mi_args {
+    int32_t G, n, M0, K0, MB;
+    const double *dat;              /* G x n observed                                  */
+    const double *Y;                /* G x n initial imputed (un-centred)              */
+    const double *beta, *lambda, *sigma, *mu, *pi;
+    const double *pos_mean;         /* G or NULL (=> 0)                                */
+    const double *pos_sd;           /* G or NULL (=> 1)                                */
+    const int32_t *celltype;        /* n, 1-based, or NULL                             */
+    int32_t mcmc, burnin;
+    const double *pg;               /* G x MB (scalar pg is broadcast by the host layer, :47-48) */
+    double cutoff;
+    uint64_t seed;
+    uint32_t ref_compat_flags;
+    int32_t want_consensus;         /* materialise the n x n consensus matrix (single rank only) */
+    int64_t n_total, cell_offset;
+    simples_allreduce_fn allreduce;
+    void *allreduce_user;
+    void *stream;
+} simples_mi_args;
+
+typedef struct simples_mi_out {     /* R/do_impute.R:158-159 */
+    double *loglik;                 /* 1: mean(tot[-1:-burnin])                        */
+    double *impt;                   /* G x n                                           */
+    double *impt_var;               /* G x n                                           */
+    double *EF;                     /* n x K0                                          */
+    double *varF;                   /* n x K0                                          */
+    double *consensus_cluster;      /* n x n or NULL                                   */
+} simples_mi_out;
+
+/* ---- lifecycle / errors ------------------------------------------------ */
+SIMPLES_API int simples_abi_version(void);
+/* Select the device this process drives (ndev must be 1: one process per GPU). */
+SIMPLES_API int simples_init(int ndev, const int *devs);
+SIMPLES_API void simples_shutdown(void);
+SIMPLES_API const char *simples_last_error(void);
+
+/* ---- one-shot calls with HOST buffers (what the .Call shim binds) ------- */
+SIMPLES_API int simples_em_impute(const simples_em_args *args, simples_em_out *out);
+SIMPLES_API int simples_do_impute(const simples_mi_args *args, simples_mi_out *out);
+
+/* ---- resident-context API (keeps Y/mask/state in HBM between calls; used
+ *      by SIMPLE()-level drivers and by bench.py's device-resident timing) -- */
+typedef struct simples_ctx simples_ctx;
+
+SIMPLES_API int simples_em_create(const simples_em_args *args, simples_ctx **ctx);   /* alloc + H2D + prologue */
+SIMPLES_API int simples_em_run(simples_ctx *ctx, int iters);                         /* next `iters` EM iterations */
+SIMPLES_API int simples_em_fetch(simples_ctx *ctx, simples_em_out *out);             /* D2H of the return list */
+SIMPLES_API int simples_em_sync(simples_ctx *ctx);
+/* Device time of the last simples_em_run, per iteration (ms, CUDA events on
+ * the context's stream).  `cap` = capacity of ms_per_iter; returns count. */
+SIMPLES_API int simples_em_iter_ms(simples_ctx *ctx, double *ms_per_iter, int cap);
+/* Per-kernel profile of the last run when enabled: for each kernel class k,
+ * launches[k] and total_ms[k].  Classes are listed by simples_kernel_name(). */
+SIMPLES_API int simples_em_set_profile(simples_ctx *ctx, int enable);
+SIMPLES_API int simples_em_profile(simples_ctx *ctx, int64_t *launches, double *total_ms, int cap);
+SIMPLES_API const char *simples_kernel_name(int k);
+SIMPLES_API int simples_kernel_count(void);
+/* Number of entries with Y0 <= cutoff in this context's shard. */
+SIMPLES_API int64_t simples_em_nnz0(simples_ctx *ctx);
+SIMPLES_API void simples_ctx_destroy(simples_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPLES_B200_H */

@@ -1,0 +1,15 @@
+"""simples_b200 -- B200-native EM imputation hot path of JunLiuLab/SIMPLEs.
+
+Public surface mirrors the reference's R functions for this path
+(``EM_impute``: R/EM_impute.R:75, ``do_impute``: R/do_impute.R:29) above a
+C ABI (include/simples_b200.h) implemented in hand-written sm_100a CUDA.
+Importing this package never imports the test oracle and never falls back to
+CPU arithmetic.
+"""
+from ._lib import (COMPAT_DEFAULT, COMPAT_MU_DIV_N, COMPAT_PI, COMPAT_PRIORB_PREV, COMPAT_STALE_DT, LIB_PATH,
+                   SimplesError, load)
+from .api import EM_impute, EMContext, do_impute
+from .dist import CellShard, partition
+
+__all__ = ["EM_impute", "do_impute", "EMContext", "CellShard", "partition", "SimplesError", "load", "LIB_PATH",
+           "COMPAT_DEFAULT", "COMPAT_STALE_DT", "COMPAT_PI", "COMPAT_MU_DIV_N", "COMPAT_PRIORB_PREV"]

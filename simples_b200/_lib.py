@@ -1,0 +1,120 @@
+"""ctypes binding of libsimples_b200.so (include/simples_b200.h).
+
+The CUDA library is the product.  There is no CPU fallback: if the shared
+library is missing this module raises, and if no sm_100 device is usable every
+compute entry point returns SIMPLES_ENODEV which is raised as SimplesError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsimples_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+COMPAT_STALE_DT = 1
+COMPAT_PI = 2
+COMPAT_MU_DIV_N = 4
+COMPAT_PRIORB_PREV = 8
+COMPAT_DEFAULT = 15
+
+
+class SimplesError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"simples_b200 error {code}: {msg}")
+        self.code = code
+
+
+class EmArgs(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("n", C.c_int32), ("M0", C.c_int32), ("K0", C.c_int32), ("MB", C.c_int32),
+        ("Y", C.c_void_p), ("Y0", C.c_void_p), ("pg", C.c_void_p),
+        ("cutoff", C.c_double), ("iter", C.c_int32),
+        ("beta", C.c_void_p), ("sigma", C.c_void_p), ("lambda_", C.c_void_p), ("pi", C.c_void_p),
+        ("z", C.c_void_p), ("mu", C.c_void_p), ("celltype", C.c_void_p),
+        ("penl", C.c_double),
+        ("est_z", C.c_int32), ("max_lambda", C.c_int32), ("est_lam", C.c_int32), ("impt_it", C.c_int32),
+        ("sigma0", C.c_double), ("pi_alpha", C.c_double),
+        ("num_mc", C.c_int32),
+        ("lower", C.c_double), ("upper", C.c_double),
+        ("seed", C.c_uint64), ("ref_compat_flags", C.c_uint32),
+        ("n_total", C.c_int64), ("cell_offset", C.c_int64),
+        ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+class EmOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("loglik", "pi", "mu", "sigma", "beta", "lambda_", "z", "Ef", "Varf", "Y", "geneM", "geneSd", "priorB")]
+
+
+class MiArgs(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("n", C.c_int32), ("M0", C.c_int32), ("K0", C.c_int32), ("MB", C.c_int32),
+        ("dat", C.c_void_p), ("Y", C.c_void_p),
+        ("beta", C.c_void_p), ("lambda_", C.c_void_p), ("sigma", C.c_void_p), ("mu", C.c_void_p), ("pi", C.c_void_p),
+        ("pos_mean", C.c_void_p), ("pos_sd", C.c_void_p), ("celltype", C.c_void_p),
+        ("mcmc", C.c_int32), ("burnin", C.c_int32),
+        ("pg", C.c_void_p), ("cutoff", C.c_double),
+        ("seed", C.c_uint64), ("ref_compat_flags", C.c_uint32), ("want_consensus", C.c_int32),
+        ("n_total", C.c_int64), ("cell_offset", C.c_int64),
+        ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+class MiOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("loglik", "impt", "impt_var", "EF", "varF", "consensus_cluster")]
+
+
+EXPORTS = [
+    "simples_abi_version", "simples_init", "simples_shutdown", "simples_last_error",
+    "simples_em_impute", "simples_do_impute", "simples_em_create", "simples_em_run", "simples_em_fetch",
+    "simples_em_sync", "simples_em_iter_ms", "simples_em_set_profile", "simples_em_profile",
+    "simples_kernel_name", "simples_kernel_count", "simples_em_nnz0", "simples_ctx_destroy",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(simples_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.simples_abi_version.restype = C.c_int
+    lib.simples_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    lib.simples_last_error.restype = C.c_char_p
+    lib.simples_em_impute.argtypes = [C.POINTER(EmArgs), C.POINTER(EmOut)]
+    lib.simples_do_impute.argtypes = [C.POINTER(MiArgs), C.POINTER(MiOut)]
+    lib.simples_em_create.argtypes = [C.POINTER(EmArgs), C.POINTER(C.c_void_p)]
+    lib.simples_em_run.argtypes = [C.c_void_p, C.c_int]
+    lib.simples_em_fetch.argtypes = [C.c_void_p, C.POINTER(EmOut)]
+    lib.simples_em_sync.argtypes = [C.c_void_p]
+    lib.simples_em_iter_ms.argtypes = [C.c_void_p, c_double_p, C.c_int]
+    lib.simples_em_set_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.simples_em_profile.argtypes = [C.c_void_p, C.POINTER(C.c_int64), c_double_p, C.c_int]
+    lib.simples_kernel_name.argtypes = [C.c_int]
+    lib.simples_kernel_name.restype = C.c_char_p
+    lib.simples_kernel_count.restype = C.c_int
+    lib.simples_em_nnz0.argtypes = [C.c_void_p]
+    lib.simples_em_nnz0.restype = C.c_int64
+    lib.simples_ctx_destroy.argtypes = [C.c_void_p]
+    lib.simples_ctx_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc < 0:
+        raise SimplesError(rc, load().simples_last_error().decode("utf-8", "replace"))
+    return rc

@@ -1,0 +1,260 @@
+"""Host-side mirror of the reference's hot-path R functions.
+
+``EM_impute`` and ``do_impute`` keep the names, argument order, defaults and
+return-list layout of ``R/EM_impute.R:75-78,337-338`` and
+``R/do_impute.R:29-30,158-159`` (R is not available in this image, so the
+reference's host language is mirrored in Python above the C ABI; the R glue is
+shipped as source under ``r/``).  Matrices follow R's orientation: ``Y`` is
+``G x n`` (genes x cells), ``z`` is ``n x M0``, ``beta`` is ``G x K0`` ...
+
+All compute happens in libsimples_b200.so (CUDA, sm_100a).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import COMPAT_DEFAULT, EmArgs, EmOut, MiArgs, MiOut, SimplesError, check  # noqa: F401
+
+
+def _f(a, shape=None, name=""):
+    """float64, column-major (R layout) view/copy."""
+    a = np.asarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return np.asfortranarray(a)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _Comm:
+    """Adapter: any object with ``allreduce_sum_(dev_ptr, count, stream)`` plus
+    ``n_total`` / ``cell_offset`` (see simples_b200.dist.CellShard)."""
+
+    def __init__(self, comm):
+        self.comm = comm
+        self.error = None
+
+        def _cb(user, buf, count, stream):
+            try:
+                comm.allreduce_sum_(buf, count, stream)
+                return 0
+            except Exception as e:  # noqa: BLE001 - must not propagate through C frames
+                self.error = e
+                return 1
+
+        self.cb = _lib.ALLREDUCE_FN(_cb)
+
+
+def _em_args(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu, celltype, penl, est_z,
+             max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper, seed, ref_compat, comm, stream):
+    Y = _f(Y)
+    if Y.ndim != 2:
+        raise ValueError("Y must be a G x n matrix")
+    G, n = Y.shape
+    Y0 = _f(Y0, (G, n), "Y0")
+    pg = _f(pg)
+    if pg.ndim == 1:
+        pg = _f(pg.reshape(G, -1))
+    if pg.shape[0] != G:
+        raise ValueError("pg must have G rows")
+    MB = pg.shape[1]
+    keep = dict(Y=Y, Y0=Y0, pg=pg,
+                beta=_f(beta, (G, K0), "beta"), sigma=_f(sigma, (G, M0), "sigma"),
+                lambda_=_f(lambda_, (M0, K0), "lambda"), pi=_f(np.ravel(pi), (M0,), "pi"),
+                z=None if z is None else _f(z, (n, M0), "z"),
+                mu=None if mu is None else _f(mu, (G, M0), "mu"),
+                celltype=None if celltype is None else np.ascontiguousarray(np.asarray(celltype).astype(np.int32)))
+    if keep["celltype"] is not None and keep["celltype"].shape != (n,):
+        raise ValueError("celltype must have length n")
+    a = EmArgs()
+    a.G, a.n, a.M0, a.K0, a.MB = G, n, int(M0), int(K0), MB
+    for k in ("Y", "Y0", "pg", "beta", "sigma", "lambda_", "pi", "z", "mu", "celltype"):
+        setattr(a, k, _ptr(keep[k]))
+    a.cutoff, a.iter = float(cutoff), int(iter)
+    a.penl = float(penl)
+    a.est_z, a.max_lambda, a.est_lam, a.impt_it = int(est_z), int(bool(max_lambda)), int(est_lam), int(impt_it)
+    a.sigma0, a.pi_alpha, a.num_mc = float(sigma0), float(pi_alpha), int(num_mc)
+    a.lower, a.upper = float(lower), float(upper)
+    a.seed, a.ref_compat_flags = int(seed) & 0xFFFFFFFFFFFFFFFF, int(ref_compat)
+    if comm is not None:
+        cw = _Comm(comm)
+        keep["_comm"] = cw
+        a.n_total, a.cell_offset = int(comm.n_total), int(comm.cell_offset)
+        a.allreduce = cw.cb
+    else:
+        a.n_total, a.cell_offset = 0, 0
+    a.stream = stream
+    return a, keep, (G, n, MB)
+
+
+def _em_out(G, n, M0, K0, iter):
+    bufs = dict(loglik=np.zeros(max(iter, 1)), pi=np.zeros(M0), mu=np.zeros((G, M0), order="F"),
+                sigma=np.zeros((G, M0), order="F"), beta=np.zeros((G, K0), order="F"),
+                lambda_=np.zeros((M0, K0), order="F"), z=np.zeros((n, M0), order="F"),
+                Ef=np.zeros((M0, K0, n)), Varf=np.zeros((M0, K0, K0)), Y=np.zeros((G, n), order="F"),
+                geneM=np.zeros(G), geneSd=np.zeros(G), priorB=np.zeros(1))
+    o = EmOut()
+    for k, v in bufs.items():
+        setattr(o, k, _ptr(v))
+    return o, bufs
+
+
+def _em_result(bufs, M0, iter):
+    # Ef buffer holds M0 column-major n x K0 matrices back to back == C-order (M0, K0, n)
+    Ef = [np.asfortranarray(bufs["Ef"][m].T) for m in range(M0)]
+    Varf = [bufs["Varf"][m].copy() for m in range(M0)]
+    return {"loglik": bufs["loglik"][:iter], "pi": bufs["pi"], "mu": bufs["mu"], "sigma": bufs["sigma"],
+            "beta": bufs["beta"], "lambda": bufs["lambda_"], "z": bufs["z"], "Ef": Ef, "Varf": Varf,
+            "Y": bufs["Y"], "geneM": bufs["geneM"], "geneSd": bufs["geneSd"], "priorB": float(bufs["priorB"][0])}
+
+
+def EM_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu=None, celltype=None, penl=1,
+              est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1, verbose=False, num_mc=3,
+              lower=-math.inf, upper=math.inf, *, seed=0, ref_compat=COMPAT_DEFAULT, comm=None, stream=None):
+    """Monte-Carlo EM imputation on B200 -- drop-in for ``EM_impute`` (R/EM_impute.R:75-339).
+
+    Returns a dict with the reference's list names in the reference's order:
+    loglik, pi, mu, sigma, beta, lambda, z, Ef, Varf, Y, geneM, geneSd, priorB.
+    ``verbose`` is accepted and ignored (the reference's verbose block uses
+    undefined globals, R/EM_impute.R:327-329).  Keyword-only extras: ``seed``
+    (Philox key replacing R's global RNG), ``ref_compat`` (quirk bits),
+    ``comm`` (a simples_b200.dist.CellShard when cells are sharded over GPUs).
+    """
+    lib = _lib.load()
+    a, keep, (G, n, _) = _em_args(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu, celltype, penl,
+                                  est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper, seed,
+                                  ref_compat, comm, stream)
+    o, bufs = _em_out(G, n, int(M0), int(K0), int(iter))
+    rc = lib.simples_em_impute(C.byref(a), C.byref(o))
+    if rc < 0 and "_comm" in keep and keep["_comm"].error is not None:
+        raise keep["_comm"].error
+    check(rc)
+    return _em_result(bufs, int(M0), int(iter))
+
+
+class EMContext:
+    """Device-resident EM_impute state (simples_em_create / run / fetch): keeps
+    Y, the zero mask and the parameters in HBM between calls."""
+
+    def __init__(self, Y, Y0, pg, M0, K0, cutoff, beta, sigma, lambda_, pi, z, mu=None, celltype=None, penl=1,
+                 est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1, num_mc=3,
+                 lower=-math.inf, upper=math.inf, *, iter=1, seed=0, ref_compat=COMPAT_DEFAULT, comm=None, stream=None):
+        self._lib = _lib.load()
+        a, keep, (G, n, _) = _em_args(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu, celltype,
+                                      penl, est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower,
+                                      upper, seed, ref_compat, comm, stream)
+        self._keep = keep
+        self.G, self.n, self.M0, self.K0 = G, n, int(M0), int(K0)
+        self.iters_done = 0
+        h = C.c_void_p()
+        check(self._lib.simples_em_create(C.byref(a), C.byref(h)))
+        self._h = h
+
+    def run(self, iters):
+        check(self._lib.simples_em_run(self._h, int(iters)))
+        self.iters_done += int(iters)
+
+    def sync(self):
+        check(self._lib.simples_em_sync(self._h))
+
+    def iter_ms(self):
+        buf = (C.c_double * 4096)()
+        k = check(self._lib.simples_em_iter_ms(self._h, buf, 4096))
+        return [buf[i] for i in range(min(k, 4096))]
+
+    def set_profile(self, on):
+        check(self._lib.simples_em_set_profile(self._h, int(bool(on))))
+
+    def profile(self):
+        k = self._lib.simples_kernel_count()
+        la = (C.c_int64 * k)()
+        ms = (C.c_double * k)()
+        check(self._lib.simples_em_profile(self._h, la, ms, k))
+        return {self._lib.simples_kernel_name(i).decode(): (int(la[i]), float(ms[i])) for i in range(k)}
+
+    @property
+    def nnz0(self):
+        return int(self._lib.simples_em_nnz0(self._h))
+
+    def fetch(self, big=True):
+        o, bufs = _em_out(self.G, self.n, self.M0, self.K0, self.iters_done)
+        if not big:
+            o.Y = None
+            o.Ef = None
+        check(self._lib.simples_em_fetch(self._h, C.byref(o)))
+        return _em_result(bufs, self.M0, self.iters_done)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.simples_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, celltype=None, mcmc=10, burnin=2,
+              verbose=False, pg=0.5, cutoff=0.1, *, seed=0, ref_compat=COMPAT_DEFAULT, consensus=True, comm=None,
+              stream=None):
+    """Multiple imputation at fixed parameters on B200 -- drop-in for
+    ``do_impute`` (R/do_impute.R:29-160).  Returns loglik, impt, impt_var, EF,
+    varF, consensus_cluster.  ``consensus=False`` (or sharded cells) returns
+    ``consensus_cluster=None``: the n x n matrix (R/do_impute.R:61) is only
+    materialised on request and on a single rank."""
+    lib = _lib.load()
+    Y = _f(Y)
+    G, n = Y.shape
+    dat = _f(dat, (G, n), "dat")
+    mu = _f(mu)
+    beta = _f(beta)
+    M0, K0 = mu.shape[1], beta.shape[1]                                  # :35-36
+    ct = None if celltype is None else np.ascontiguousarray(np.asarray(celltype).astype(np.int32))
+    MB = 1 if ct is None else int(ct.max())                              # :45
+    pg = np.asarray(pg, dtype=np.float64)
+    if pg.size == 1:
+        pg = np.full((G, MB), float(pg))                                 # :47-48
+    pg = _f(pg.reshape(G, -1))
+    keep = dict(dat=dat, Y=Y, beta=_f(beta, (G, K0)), lambda_=_f(lambda_, (M0, K0), "lambda"),
+                sigma=_f(sigma, (G, M0), "sigma"), mu=_f(mu, (G, M0)), pi=_f(np.ravel(pi), (M0,), "pi"),
+                pos_mean=None if pos_mean is None else _f(np.ravel(pos_mean), (G,), "pos_mean"),
+                pos_sd=None if pos_sd is None else _f(np.ravel(pos_sd), (G,), "pos_sd"), celltype=ct, pg=pg)
+    a = MiArgs()
+    a.G, a.n, a.M0, a.K0, a.MB = G, n, M0, K0, pg.shape[1]
+    for k in ("dat", "Y", "beta", "lambda_", "sigma", "mu", "pi", "pos_mean", "pos_sd", "celltype", "pg"):
+        setattr(a, k, _ptr(keep[k]))
+    a.mcmc, a.burnin, a.cutoff = int(mcmc), int(burnin), float(cutoff)
+    a.seed, a.ref_compat_flags = int(seed) & 0xFFFFFFFFFFFFFFFF, int(ref_compat)
+    want_cons = bool(consensus) and comm is None
+    a.want_consensus = int(want_cons)
+    cw = None
+    if comm is not None:
+        cw = _Comm(comm)
+        a.n_total, a.cell_offset, a.allreduce = int(comm.n_total), int(comm.cell_offset), cw.cb
+    a.stream = stream
+    bufs = dict(loglik=np.zeros(1), impt=np.zeros((G, n), order="F"), impt_var=np.zeros((G, n), order="F"),
+                EF=np.zeros((n, K0), order="F"), varF=np.zeros((n, K0), order="F"),
+                consensus_cluster=np.zeros((n, n), order="F") if want_cons else None)
+    o = MiOut()
+    for k, v in bufs.items():
+        setattr(o, k, _ptr(v))
+    rc = lib.simples_do_impute(C.byref(a), C.byref(o))
+    if rc < 0 and cw is not None and cw.error is not None:
+        raise cw.error
+    check(rc)
+    return {"loglik": float(bufs["loglik"][0]), "impt": bufs["impt"], "impt_var": bufs["impt_var"], "EF": bufs["EF"],
+            "varF": bufs["varF"], "consensus_cluster": bufs["consensus_cluster"]}

@@ -1,0 +1,907 @@
+// Host orchestration + C ABI (include/simples_b200.h) of the B200 EM imputation hot path.
+// One context = one EM_impute (R/EM_impute.R:75-339) or do_impute (R/do_impute.R:29-160) call on
+// this process's shard of cells.  The EM loop is enqueued on one CUDA stream without any
+// host <-> device synchronisation: all data-dependent decisions (lambda eligibility, lasso active
+// sets, priorB bookkeeping) happen on the device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/simples_b200.h"
+#include "state.h"
+
+using namespace sb;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char buf_[512];                                                                            \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                     cudaGetErrorString(e_));                                                          \
+            return fail(e_ == cudaErrorMemoryAllocation ? SIMPLES_ENOMEM : SIMPLES_ECUDA, buf_);       \
+        }                                                                                              \
+    } while (0)
+
+#define CKR(expr)                  \
+    do {                           \
+        int r_ = (expr);           \
+        if (r_ != SIMPLES_OK) return r_; \
+    } while (0)
+
+const char* kKernelNames[KC_COUNT] = {"estep_project", "cell_post",  "impute_sweep",     "mstep_stats", "sstats", "reduce",
+                                      "cluster_prep",  "gene_solve", "lambda_mu_pi",     "misc",        "allreduce"};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct EvRec {
+    int cls;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct simples_ctx {
+    int kind = 0;   // 0 = EM, 1 = MI
+    DevState s{};
+    std::vector<void*> allocs;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // scalars of the call
+    double cutoff = 0, penl = 1, sigma0 = 100, pi_alpha = 1, lower = -INFINITY, upper = INFINITY;
+    int est_z = 2, max_lambda = 1, est_lam = 2, impt_it = 5, num_mc = 3;
+    uint64_t seed = 0;
+    uint32_t compat = SIMPLES_COMPAT_DEFAULT;
+    simples_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    bool z_null = false;
+    int it = 0;             // EM iterations done
+    unsigned sweep = 0;     // MC sweeps done (tape position)
+    int iter_cap = 0;
+    int n_alloc = 0;
+    int NS_max = 1;
+    long long nnz0 = 0;
+    double* cellsum_main = nullptr;   // [2 M0 + 1] of the main E-pass of the current iteration
+    double* stage = nullptr;          // staging buffer for chunked H2D / D2H
+    size_t stage_elems = 0;
+    unsigned long long* d_nnz = nullptr;
+    // general path scratch
+    double* part_g = nullptr;
+    int nsplit_g = 0;
+    // MI
+    int mcmc = 0, burnin = 0, want_consensus = 0;
+    double *rec1 = nullptr, *rec2 = nullptr, *rEF = nullptr, *rF2 = nullptr, *rVF = nullptr, *cons = nullptr, *tot_mi = nullptr;
+    // timing
+    std::vector<cudaEvent_t> iter_ev;
+    std::vector<double> iter_ms;
+    bool profile = false;
+    std::vector<EvRec> evs;
+    long long prof_launches[KC_COUNT] = {0};
+    double prof_ms[KC_COUNT] = {0};
+
+    template <typename T>
+    int dalloc(T** p, size_t count, bool zero = true) {
+        void* q = nullptr;
+        if (count == 0) count = 1;
+        CK(cudaMalloc(&q, count * sizeof(T)));
+        allocs.push_back(q);
+        if (zero) CK(cudaMemsetAsync(q, 0, count * sizeof(T), stream));
+        *p = static_cast<T*>(q);
+        return SIMPLES_OK;
+    }
+    void prof_begin(int cls) {
+        if (!profile) return;
+        EvRec r;
+        r.cls = cls;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, stream);
+        evs.push_back(r);
+    }
+    void prof_end() {
+        if (!profile) return;
+        cudaEventRecord(evs.back().b, stream);
+    }
+    void prof_collect() {
+        for (auto& r : evs) {
+            float ms = 0;
+            cudaEventSynchronize(r.b);
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            prof_launches[r.cls] += 1;
+            prof_ms[r.cls] += ms;
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        evs.clear();
+    }
+    ~simples_ctx() {
+        for (auto& r : evs) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        for (auto e : iter_ev) cudaEventDestroy(e);
+        for (void* p : allocs) cudaFree(p);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+struct P {   // RAII profile scope
+    simples_ctx* c;
+    P(simples_ctx* c_, int cls) : c(c_) { c->prof_begin(cls); }
+    ~P() { c->prof_end(); }
+};
+
+int ensure_device() {
+    if (g_device < 0) {
+        int cnt = 0;
+        cudaError_t e = cudaGetDeviceCount(&cnt);
+        if (e != cudaSuccess || cnt == 0)
+            return fail(SIMPLES_ENODEV, std::string("no CUDA device available (no CPU fallback): ") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        g_device = dev;
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    if (prop.major != 10) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "device %d (%s) is sm_%d%d; this library is built for sm_100a (B200) only", g_device,
+                 prop.name, prop.major, prop.minor);
+        return fail(SIMPLES_ENODEV, buf);
+    }
+    CK(cudaSetDevice(g_device));
+    return SIMPLES_OK;
+}
+
+int allreduce(simples_ctx* c, double* buf, size_t count) {
+    if (!c->allreduce) return SIMPLES_OK;
+    P p(c, KC_COMM);
+    if (c->allreduce(c->allreduce_user, buf, count, (void*)c->stream) != 0)
+        return fail(SIMPLES_ECOMM, "all-reduce callback failed");
+    return SIMPLES_OK;
+}
+
+// host col-major (rows x cols, ld = rows) -> gene-major padded [ldrows][cols]
+std::vector<double> to_rowmajor(const double* src, int rows, int cols, int ldrows, double padval) {
+    std::vector<double> out(size_t(ldrows) * cols, padval);
+    for (int c = 0; c < cols; ++c)
+        for (int r = 0; r < rows; ++r) out[size_t(r) * cols + c] = src[size_t(c) * rows + r];
+    return out;
+}
+
+void set_dims(Dims& d, int G, int n, int M0, int K0, int MB, long long n_total, long long cell_offset) {
+    d.G = G;
+    d.ldG = round_up(G, GPAD);
+    d.n = n;
+    d.M0 = M0;
+    d.K0 = K0;
+    d.MB = MB;
+    d.NS = 1;
+    d.NQ = K0 + M0;
+    d.NQP = round_up(d.NQ, 8);
+    d.QS = d.NQP + 4;
+    d.NF = K0 + M0 + 1;
+    d.NFP = round_up(d.NF, 8);
+    d.FS = d.NFP + 4;
+    d.NV = K0 + 2 * M0;
+    d.NVP = round_up(d.NV, 8);
+    d.VS = d.NVP + 4;
+    d.n_total = n_total > 0 ? n_total : n;
+    d.cell_offset = cell_offset;
+}
+
+int check_common(int G, int n, int M0, int K0, int MB) {
+    if (G < 1 || n < 1) return fail(SIMPLES_EINVAL, "G and n must be >= 1");
+    if (K0 < 1 || K0 > MAXK) return fail(SIMPLES_EINVAL, "K0 must be in [1, 32]");
+    if (M0 < 1 || M0 > MAXM) return fail(SIMPLES_EINVAL, "M0 must be in [1, 32]");
+    if (MB < 1) return fail(SIMPLES_EINVAL, "MB (ncol(pg)) must be >= 1");
+    return SIMPLES_OK;
+}
+
+// Allocate and upload everything EM and MI share.
+int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long n_total, long long cell_offset,
+                 const double* Y, const double* Y0, const double* pg, const double* beta, const double* sigma,
+                 const double* lambda, const double* pi, const int32_t* celltype, double cutoff, bool sigma_shared) {
+    DevState& s = c->s;
+    set_dims(s.d, G, n, M0, K0, MB, n_total, cell_offset);
+    Dims& d = s.d;
+    c->NS_max = sigma_shared ? 1 : M0;
+    d.NS = c->NS_max;
+    c->n_alloc = round_up(n, 128);
+    const size_t na = c->n_alloc;
+    const int ldG = d.ldG, nwords = ldG / 32;
+
+    CKR(c->dalloc(&s.Y, na * ldG));
+    CKR(c->dalloc(&s.mask, na * nwords));
+    CKR(c->dalloc(&s.celltype0, na));
+    CKR(c->dalloc(&s.beta, size_t(ldG) * K0));
+    CKR(c->dalloc(&s.sigma, size_t(ldG) * M0));
+    CKR(c->dalloc(&s.mu, size_t(ldG) * M0));
+    CKR(c->dalloc(&s.pg, size_t(ldG) * MB));
+    CKR(c->dalloc(&s.gmean, size_t(ldG)));
+    CKR(c->dalloc(&s.gsd, size_t(ldG)));
+    CKR(c->dalloc(&s.lam, size_t(M0) * K0));
+    CKR(c->dalloc(&s.pi, size_t(M0)));
+    CKR(c->dalloc(&s.z, na * M0));
+    CKR(c->dalloc(&s.Q, size_t(c->NS_max) * ldG * d.QS));
+    CKR(c->dalloc(&s.isg, size_t(c->NS_max) * ldG));
+    CKR(c->dalloc(&s.Qs, size_t(ldG) * d.FS));
+    CKR(c->dalloc(&s.P, size_t(c->NS_max) * na * d.NQP));
+    CKR(c->dalloc(&s.S2, size_t(c->NS_max) * na));
+    CKR(c->dalloc(&s.V, na * d.VS));
+    CKR(c->dalloc(&s.zsum, na));
+    CKR(c->dalloc(&s.Fh, na * d.FS));
+    CKR(c->dalloc(&s.W, size_t(M0) * na * K0));
+    CKR(c->dalloc(&s.im, na));
+    CKR(c->dalloc(&s.cc.Mm, size_t(M0) * K0 * K0));
+    CKR(c->dalloc(&s.cc.Mh, size_t(M0) * K0 * K0));
+    CKR(c->dalloc(&s.cc.dt, size_t(M0)));
+    CKR(c->dalloc(&s.cc.off, size_t(M0) * K0));
+    CKR(c->dalloc(&s.cc.offq, size_t(M0) * K0));
+    CKR(c->dalloc(&s.cc.cmu, size_t(M0)));
+    CKR(c->dalloc(&s.cc.logpi, size_t(M0)));
+    s.ncta_cell = std::min((n + 7) / 8, NUM_SMS_B200 * 4);
+    CKR(c->dalloc(&s.part_cell, size_t(s.ncta_cell) * (2 * M0 + 1)));
+    CKR(c->dalloc(&c->cellsum_main, size_t(2 * M0 + 1)));
+    CKR(c->dalloc(&c->d_nnz, 1));
+
+    // staging buffer: whole cells, at most 32 Mi doubles (256 MB)
+    size_t cells_per_chunk = std::max<size_t>(1, (size_t(32) << 20) / size_t(G));
+    cells_per_chunk = std::min<size_t>(cells_per_chunk, size_t(n));
+    c->stage_elems = cells_per_chunk * G;
+    CKR(c->dalloc(&c->stage, c->stage_elems, false));
+
+    // ---- uploads ----
+    if (ldG == G) {
+        CK(cudaMemcpyAsync(s.Y, Y, size_t(n) * G * 8, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CK(cudaMemcpy2DAsync(s.Y, size_t(ldG) * 8, Y, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyHostToDevice, c->stream));
+    }
+    for (size_t c0 = 0; c0 < size_t(n); c0 += cells_per_chunk) {
+        const size_t nc = std::min(cells_per_chunk, size_t(n) - c0);
+        CK(cudaMemcpyAsync(c->stage, Y0 + c0 * G, nc * G * 8, cudaMemcpyHostToDevice, c->stream));
+        launch_build_mask(c->stage, s.mask + c0 * nwords, int(nc), G, ldG, cutoff, c->d_nnz, c->stream);
+    }
+    {
+        std::vector<double> hb = to_rowmajor(beta, G, K0, ldG, 0.0);
+        std::vector<double> hs = to_rowmajor(sigma, G, M0, ldG, 1.0);
+        std::vector<double> hp = to_rowmajor(pg, G, MB, ldG, 0.5);
+        std::vector<double> hl = to_rowmajor(lambda, M0, K0, M0, 0.0);
+        std::vector<int32_t> ct(n, 0);
+        if (celltype) {
+            for (int i = 0; i < n; ++i) {
+                if (celltype[i] < 1 || celltype[i] > MB) return fail(SIMPLES_EINVAL, "celltype must be in 1..ncol(pg)");
+                ct[i] = celltype[i] - 1;
+            }
+        }
+        CK(cudaMemcpyAsync(s.beta, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.sigma, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.pg, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.lam, hl.data(), hl.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.pi, pi, size_t(M0) * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.celltype0, ct.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   // host vectors go out of scope
+    }
+    unsigned long long h_nnz = 0;
+    CK(cudaMemcpy(&h_nnz, c->d_nnz, 8, cudaMemcpyDeviceToHost));
+    c->nnz0 = (long long)h_nnz;
+    return SIMPLES_OK;
+}
+
+bool sigma_is_shared(const double* sigma, int G, int M0) {
+    for (int m = 1; m < M0; ++m)
+        for (int g = 0; g < G; ++g)
+            if (sigma[size_t(m) * G + g] != sigma[g]) return false;
+    return true;
+}
+
+// upload an n x M0 col-major host matrix into the [n][M0] device layout (through the staging buffer)
+int upload_z(simples_ctx* c, const double* z) {
+    DevState& s = c->s;
+    const int n = s.d.n, M0 = s.d.M0;
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, size_t(n) * M0 * 8));
+    CK(cudaMemcpyAsync(tmp, z, size_t(n) * M0 * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_transpose(tmp, s.z, M0, n, n, M0, c->stream);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(tmp));
+    return SIMPLES_OK;
+}
+
+// one E-pass: projections + cell epilogue
+int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_membership, bool write_W, bool write_Vg,
+           double pi_const) {
+    DevState& s = c->s;
+    const Dims& d = s.d;
+    for (int sc = 0; sc < d.NS; ++sc) {
+        P p(c, KC_PROJ);
+        ProjArgs pa{s.Y, s.Q + size_t(sc) * d.ldG * d.QS, s.isg + size_t(sc) * d.ldG, s.P + size_t(sc) * d.n * d.NQP,
+                    s.S2 + size_t(sc) * d.n, d.n, d.ldG, d.NQP, d.QS};
+        launch_proj(pa, c->stream);
+    }
+    {
+        P p(c, KC_CELL);
+        CellArgs ca{};
+        ca.d = d;
+        ca.P = s.P;
+        ca.S2 = s.S2;
+        ca.cc = s.cc;
+        ca.z = s.z;
+        ca.V = s.V;
+        ca.zsum = s.zsum;
+        ca.W = s.W;
+        ca.Fh = s.Fh;
+        ca.Vg = s.Vg;
+        ca.im = s.im;
+        ca.part = s.part_cell;
+        ca.ncta = s.ncta_cell;
+        ca.update_z = update_z;
+        ca.stale_q = stale_q;
+        ca.write_W = write_W;
+        ca.write_Vg = write_Vg && s.Vg;
+        ca.sample = sample;
+        ca.draw_membership = draw_membership;
+        ca.ll_const = double(d.G) * std::log(2.0 * pi_const);
+        ca.seed = c->seed;
+        ca.sweep = c->sweep;
+        launch_cell(ca, c->stream);
+    }
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
+int run_prep(simples_ctx* c) {
+    DevState& s = c->s;
+    P p(c, KC_PREP);
+    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.cc, 0};
+    launch_prep(pa, c->stream);
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
+int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2) {
+    DevState& s = c->s;
+    P p(c, KC_SWEEP);
+    SweepArgs sa{};
+    sa.d = s.d;
+    sa.Y = s.Y;
+    sa.mask = s.mask;
+    sa.Qs = s.Qs;
+    sa.Fh = s.Fh;
+    sa.sigma = s.sigma;
+    sa.pg = s.pg;
+    sa.gmean = s.gmean;
+    sa.gsd = s.gsd;
+    sa.im = s.im;
+    sa.celltype0 = s.celltype0;
+    sa.cutoff = c->cutoff;
+    sa.lower = c->lower;
+    sa.upper = c->upper;
+    sa.clip = clip;
+    sa.seed = c->seed;
+    sa.sweep = c->sweep;
+    sa.rec1 = rec1;
+    sa.rec2 = rec2;
+    launch_sweep(sa, c->stream);
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
+int em_iteration(simples_ctx* c) {
+    DevState& s = c->s;
+    Dims& d = s.d;
+    const int it = c->it + 1;
+    const double pi_const = (c->compat & SIMPLES_COMPAT_PI) ? 3.14159265359 : M_PI;
+    const bool general = d.NS > 1;
+    const bool update_z = (it >= c->est_z) || c->z_null;
+    const bool sampling = (it >= c->impt_it + 1) && c->num_mc > 0;
+    const bool draw_mem = d.M0 > 1;
+
+    CKR(run_prep(c));
+    CKR(e_pass(c, update_z, false, sampling, draw_mem, !sampling, general && !sampling, pi_const));
+    {
+        P p(c, KC_REDUCE);
+        launch_finalize_cell(s.part_cell, s.ncta_cell, d.M0, c->cellsum_main, c->stream);
+    }
+    if (sampling) {
+        for (int mc = 0; mc < c->num_mc; ++mc) {
+            CKR(run_sweep(c, true, nullptr, nullptr));
+            c->sweep += 1;
+            const bool last = (mc == c->num_mc - 1);
+            CKR(e_pass(c, update_z, (c->compat & SIMPLES_COMPAT_STALE_DT) != 0, !last, draw_mem, last, general && last,
+                       pi_const));
+        }
+    }
+    c->z_null = false;
+
+    // ---- sufficient statistics ----
+    double* stats;
+    size_t count;
+    if (!general) {
+        {
+            P p(c, KC_MSTATS);
+            MstatsArgs ma{s.Y, s.V, s.zsum, s.part_ms, d.n, d.ldG, d.NVP, d.VS, s.splitK};
+            launch_mstats(ma, c->stream);
+        }
+        {
+            P p(c, KC_SSTATS);
+            SstatsArgs sa{d, s.W, s.z, s.part_ss, s.nsplit_ss};
+            launch_sstats(sa, c->stream);
+        }
+        {
+            P p(c, KC_REDUCE);
+            FinalizeArgs fa{d, s.part_ms, s.part_cell, s.part_ss, s.splitK, s.ncta_cell, s.nsplit_ss, s.stats, 0, 0};
+            launch_finalize_stats(fa, c->stream);
+        }
+        stats = s.stats;
+        count = s.stats_count;
+    } else {
+        const int ncg = d.K0 * d.M0 + 2 * d.M0;
+        const size_t nC = size_t(d.ldG) * ncg, nU2 = size_t(d.ldG) * d.M0;
+        {
+            P p(c, KC_MSTATS);
+            launch_ygemm_simple(s.Y, s.Vg, c->part_g, d.n, d.ldG, ncg, ncg, 0, c->nsplit_g, c->stream);
+            launch_reduce_parts(c->part_g, s.statsg, nC, c->nsplit_g, c->stream);
+            launch_ygemm_simple(s.Y, s.Vg + size_t(d.K0) * d.M0, c->part_g, d.n, d.ldG, d.M0, ncg, 1, c->nsplit_g, c->stream);
+            launch_reduce_parts(c->part_g, s.statsg + nC, nU2, c->nsplit_g, c->stream);
+        }
+        {
+            P p(c, KC_SSTATS);
+            SstatsArgs sa{d, s.W, s.z, s.part_ss, s.nsplit_ss};
+            launch_sstats(sa, c->stream);
+        }
+        {
+            P p(c, KC_REDUCE);
+            FinalizeArgs fa{d, nullptr, s.part_cell, s.part_ss, 0, s.ncta_cell, s.nsplit_ss, s.statsg, nC + nU2, 1};
+            launch_finalize_stats(fa, c->stream);
+        }
+        stats = s.statsg;
+        count = s.statsg_count;
+    }
+    // tot[it] comes from the main E-pass, not from the MC passes (R/EM_impute.R:144 vs :215-224)
+    CK(cudaMemcpyAsync(stats + count - 1, c->cellsum_main + 2 * d.M0, 8, cudaMemcpyDeviceToDevice, c->stream));
+    CKR(allreduce(c, stats, count));
+
+    // ---- M-step ----
+    {
+        P p(c, KC_GENE);
+        MstepArgs ma{};
+        ma.d = d;
+        ma.stats = stats;
+        ma.general = general;
+        ma.beta = s.beta;
+        ma.sigma = s.sigma;
+        ma.mu = s.mu;
+        ma.lam = s.lam;
+        ma.pi = s.pi;
+        ma.Mm = s.cc.Mm;
+        ma.loglik_slot = s.loglik + (it - 1);
+        ma.priorB = s.priorB;
+        ma.part_gene = s.part_gene;
+        ma.ncta_gene = s.ncta_gene;
+        ma.penl = c->penl;
+        ma.sigma0 = c->sigma0;
+        ma.pi_alpha = c->pi_alpha;
+        ma.do_lambda = c->max_lambda && it >= c->est_lam;
+        ma.compat_priorb_prev = (c->compat & SIMPLES_COMPAT_PRIORB_PREV) != 0;
+        launch_mstep(ma, c->stream);
+    }
+    CK(cudaGetLastError());
+    d.NS = 1;   // sigma is cluster-shared after every M-step (R/EM_impute.R:269)
+    c->it = it;
+    return SIMPLES_OK;
+}
+
+// chunked D2H of a per-entry G x n result produced by `fill(chunk_dev_out, cell0, ncells)`
+template <typename F>
+int fetch_big(simples_ctx* c, double* host_out, F fill) {
+    const Dims& d = c->s.d;
+    const size_t cpc = c->stage_elems / d.G;
+    for (size_t c0 = 0; c0 < size_t(d.n); c0 += cpc) {
+        const size_t nc = std::min(cpc, size_t(d.n) - c0);
+        fill(c->stage, c0, nc);
+        CK(cudaMemcpyAsync(host_out + c0 * d.G, c->stage, nc * d.G * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return SIMPLES_OK;
+}
+
+// gene-major [ldG][cols] device -> col-major host G x cols
+int fetch_genemajor(simples_ctx* c, const double* dev, int cols, double* host) {
+    const Dims& d = c->s.d;
+    std::vector<double> tmp(size_t(d.ldG) * cols);
+    CK(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int cidx = 0; cidx < cols; ++cidx)
+        for (int g = 0; g < d.G; ++g) host[size_t(cidx) * d.G + g] = tmp[size_t(g) * cols + cidx];
+    return SIMPLES_OK;
+}
+
+// device [rows][cols] -> host col-major rows x cols via device transpose
+int fetch_transposed(simples_ctx* c, const double* dev, int rows, int cols, int ld, double* host) {
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, size_t(rows) * cols * 8));
+    launch_transpose(dev, tmp, rows, cols, ld, rows, c->stream);
+    CK(cudaMemcpyAsync(host, tmp, size_t(rows) * cols * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(tmp));
+    return SIMPLES_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int simples_abi_version(void) { return SIMPLES_ABI_VERSION; }
+
+const char* simples_last_error(void) { return g_err.c_str(); }
+
+int simples_init(int ndev, const int* devs) {
+    if (ndev != 1 || !devs) return fail(SIMPLES_EINVAL, "simples_init: exactly one device per process (one process per GPU)");
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) return fail(SIMPLES_ENODEV, "simples_init: no CUDA device available (no CPU fallback)");
+    if (devs[0] < 0 || devs[0] >= cnt) return fail(SIMPLES_EINVAL, "simples_init: device index out of range");
+    g_device = devs[0];
+    return ensure_device();
+}
+
+void simples_shutdown(void) { g_device = -1; }
+
+int simples_kernel_count(void) { return KC_COUNT; }
+const char* simples_kernel_name(int k) { return (k >= 0 && k < KC_COUNT) ? kKernelNames[k] : ""; }
+
+void simples_ctx_destroy(simples_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    delete ctx;
+}
+
+int simples_em_create(const simples_em_args* a, simples_ctx** out) {
+    if (!a || !out) return fail(SIMPLES_EINVAL, "null argument");
+    *out = nullptr;
+    CKR(check_common(a->G, a->n, a->M0, a->K0, a->MB));
+    if (!a->Y || !a->Y0 || !a->pg || !a->beta || !a->sigma || !a->lambda || !a->pi)
+        return fail(SIMPLES_EINVAL, "Y, Y0, pg, beta, sigma, lambda and pi are required");
+    if (a->iter < 0 || a->num_mc < 0) return fail(SIMPLES_EINVAL, "iter and num_mc must be >= 0");
+    if (a->n_total != 0 && a->n_total < a->n) return fail(SIMPLES_EINVAL, "n_total < n");
+    CKR(ensure_device());
+
+    simples_ctx* c = new simples_ctx();
+    std::unique_ptr<simples_ctx> guard(c);
+    c->kind = 0;
+    if (a->stream) {
+        c->stream = (cudaStream_t)a->stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->cutoff = a->cutoff;
+    c->penl = a->penl;
+    c->sigma0 = a->sigma0;
+    c->pi_alpha = a->pi_alpha;
+    c->lower = a->lower;
+    c->upper = a->upper;
+    c->est_z = a->est_z;
+    c->max_lambda = a->max_lambda;
+    c->est_lam = a->est_lam;
+    c->impt_it = a->impt_it;
+    c->num_mc = a->num_mc;
+    c->seed = a->seed;
+    c->compat = a->ref_compat_flags;
+    c->allreduce = a->allreduce;
+    c->allreduce_user = a->allreduce_user;
+    c->z_null = (a->z == nullptr);
+
+    const bool shared = sigma_is_shared(a->sigma, a->G, a->M0);
+    CKR(setup_common(c, a->G, a->n, a->M0, a->K0, a->MB, a->n_total, a->cell_offset, a->Y, a->Y0, a->pg, a->beta, a->sigma,
+                     a->lambda, a->pi, a->celltype, a->cutoff, shared));
+    DevState& s = c->s;
+    Dims& d = s.d;
+    const int M0 = d.M0, K0 = d.K0, ldG = d.ldG;
+
+    // statistics buffers
+    s.splitK = mstats_pick_splitk(ldG);
+    s.stats_count = size_t(ldG) * d.NVP + ldG + size_t(M0) * K0 * K0 + size_t(M0) * K0 + 2 * M0 + 1;
+    CKR(c->dalloc(&s.stats, s.stats_count));
+    CKR(c->dalloc(&s.part_ms, size_t(s.splitK) * ldG * (d.NVP + 1)));
+    s.nsplit_ss = std::max(1, (2 * NUM_SMS_B200) / M0);
+    CKR(c->dalloc(&s.part_ss, size_t(s.nsplit_ss) * M0 * (K0 * K0 + K0)));
+    s.ncta_gene = mstep_gene_ctas(d.G);
+    CKR(c->dalloc(&s.part_gene, size_t(s.ncta_gene)));
+    CKR(c->dalloc(&s.priorB, 2));
+    c->iter_cap = std::max(a->iter, 1);
+    CKR(c->dalloc(&s.loglik, size_t(c->iter_cap)));
+    if (!shared) {
+        const int ncg = K0 * M0 + 2 * M0;
+        CKR(c->dalloc(&s.Vg, size_t(c->n_alloc) * ncg));
+        s.statsg_count = size_t(ldG) * ncg + size_t(ldG) * M0 + size_t(M0) * K0 * K0 + size_t(M0) * K0 + 2 * M0 + 1;
+        CKR(c->dalloc(&s.statsg, s.statsg_count));
+        c->nsplit_g = 8;
+        CKR(c->dalloc(&c->part_g, size_t(c->nsplit_g) * ldG * ncg));
+    }
+
+    // ---- prologue (R/EM_impute.R:82-102) ----
+    if (std::isfinite(a->lower) || std::isfinite(a->upper)) launch_clip(s.Y, d.n, d.G, ldG, a->lower, a->upper, c->stream);
+    {
+        const int nsplit = 32;
+        double* part = nullptr;
+        CKR(c->dalloc(&part, size_t(nsplit) * ldG));
+        launch_rowsum(s.Y, part, d.n, ldG, nsplit, c->stream);
+        launch_reduce_parts(part, s.gmean, ldG, nsplit, c->stream);
+        CKR(allreduce(c, s.gmean, ldG));
+        launch_scale(s.gmean, ldG, 1.0 / double(d.n_total), c->stream);     // gene_mean <- rowMeans(Y)
+        launch_fill(s.gsd, ldG, 1.0, c->stream);                            // gene_sd <- 1
+        launch_center(s.Y, s.gmean, s.gsd, d.n, ldG, 0, 0, c->stream);      // Y <- Y - rowMeans(Y)
+    }
+    if (a->z) CKR(upload_z(c, a->z));
+    if (a->mu) {
+        std::vector<double> hm = to_rowmajor(a->mu, d.G, M0, ldG, 0.0);
+        CK(cudaMemcpyAsync(s.mu, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    } else if (M0 > 1 && a->z) {
+        // mu <- Y %*% z / n   (R/EM_impute.R:95, Q3)
+        const int nsplit = 16;
+        double* part = nullptr;
+        CKR(c->dalloc(&part, size_t(nsplit) * ldG * M0));
+        launch_ygemm_simple(s.Y, s.z, part, d.n, ldG, M0, M0, 0, nsplit, c->stream);
+        launch_reduce_parts(part, s.mu, size_t(ldG) * M0, nsplit, c->stream);
+        CKR(allreduce(c, s.mu, size_t(ldG) * M0));
+        if (c->compat & SIMPLES_COMPAT_MU_DIV_N) {
+            launch_scale(s.mu, size_t(ldG) * M0, 1.0 / double(d.n_total), c->stream);
+        } else {
+            return fail(SIMPLES_EINVAL, "ref_compat_flags without SIMPLES_COMPAT_MU_DIV_N requires an explicit mu");
+        }
+    }   // else mu = 0 (already zeroed)
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    *out = guard.release();
+    return SIMPLES_OK;
+}
+
+int simples_em_set_profile(simples_ctx* c, int enable) {
+    if (!c) return fail(SIMPLES_EINVAL, "null ctx");
+    c->profile = enable != 0;
+    return SIMPLES_OK;
+}
+
+int simples_em_run(simples_ctx* c, int iters) {
+    if (!c || c->kind != 0) return fail(SIMPLES_EINVAL, "not an EM context");
+    if (iters < 0) return fail(SIMPLES_EINVAL, "iters < 0");
+    CKR(ensure_device());
+    if (c->it + iters > c->iter_cap) {   // grow the loglik array
+        double* nl = nullptr;
+        const int cap = c->it + iters;
+        CKR(c->dalloc(&nl, size_t(cap)));
+        CK(cudaMemcpyAsync(nl, c->s.loglik, size_t(c->it) * 8, cudaMemcpyDeviceToDevice, c->stream));
+        c->s.loglik = nl;
+        c->iter_cap = cap;
+    }
+    for (auto e : c->iter_ev) cudaEventDestroy(e);
+    c->iter_ev.clear();
+    c->iter_ms.clear();
+    for (int k = 0; k < KC_COUNT; ++k) {
+        c->prof_launches[k] = 0;
+        c->prof_ms[k] = 0;
+    }
+    cudaEvent_t e0;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventRecord(e0, c->stream));
+    c->iter_ev.push_back(e0);
+    for (int i = 0; i < iters; ++i) {
+        CKR(em_iteration(c));
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(e, c->stream));
+        c->iter_ev.push_back(e);
+    }
+    return SIMPLES_OK;
+}
+
+int simples_em_sync(simples_ctx* c) {
+    if (!c) return fail(SIMPLES_EINVAL, "null ctx");
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    if (c->iter_ev.size() > 1 && c->iter_ms.empty()) {
+        for (size_t i = 1; i < c->iter_ev.size(); ++i) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, c->iter_ev[i - 1], c->iter_ev[i]));
+            c->iter_ms.push_back(ms);
+        }
+    }
+    c->prof_collect();
+    return SIMPLES_OK;
+}
+
+int simples_em_iter_ms(simples_ctx* c, double* ms, int cap) {
+    if (!c) return fail(SIMPLES_EINVAL, "null ctx");
+    CKR(simples_em_sync(c));
+    const int k = std::min<int>(cap, int(c->iter_ms.size()));
+    for (int i = 0; i < k; ++i) ms[i] = c->iter_ms[i];
+    return int(c->iter_ms.size());
+}
+
+int simples_em_profile(simples_ctx* c, int64_t* launches, double* total_ms, int cap) {
+    if (!c) return fail(SIMPLES_EINVAL, "null ctx");
+    CKR(simples_em_sync(c));
+    for (int k = 0; k < std::min<int>(cap, KC_COUNT); ++k) {
+        launches[k] = c->prof_launches[k];
+        total_ms[k] = c->prof_ms[k];
+    }
+    return KC_COUNT;
+}
+
+int64_t simples_em_nnz0(simples_ctx* c) { return c ? c->nnz0 : -1; }
+
+int simples_em_fetch(simples_ctx* c, simples_em_out* o) {
+    if (!c || !o || c->kind != 0) return fail(SIMPLES_EINVAL, "not an EM context");
+    CKR(simples_em_sync(c));
+    DevState& s = c->s;
+    const Dims& d = s.d;
+    const int M0 = d.M0, K0 = d.K0;
+    if (o->loglik && c->it > 0) CK(cudaMemcpy(o->loglik, s.loglik, size_t(c->it) * 8, cudaMemcpyDeviceToHost));
+    if (o->pi) CK(cudaMemcpy(o->pi, s.pi, size_t(M0) * 8, cudaMemcpyDeviceToHost));
+    if (o->mu) CKR(fetch_genemajor(c, s.mu, M0, o->mu));
+    if (o->sigma) CKR(fetch_genemajor(c, s.sigma, M0, o->sigma));
+    if (o->beta) CKR(fetch_genemajor(c, s.beta, K0, o->beta));
+    if (o->lambda) {
+        std::vector<double> t(size_t(M0) * K0);
+        CK(cudaMemcpy(t.data(), s.lam, t.size() * 8, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < K0; ++k)
+            for (int m = 0; m < M0; ++m) o->lambda[size_t(k) * M0 + m] = t[size_t(m) * K0 + k];
+    }
+    if (o->z) CKR(fetch_transposed(c, s.z, d.n, M0, M0, o->z));
+    if (o->Ef)
+        for (int m = 0; m < M0; ++m)
+            CKR(fetch_transposed(c, s.W + size_t(m) * d.n * K0, d.n, K0, K0, o->Ef + size_t(m) * d.n * K0));
+    if (o->Varf) CK(cudaMemcpy(o->Varf, s.cc.Mm, size_t(M0) * K0 * K0 * 8, cudaMemcpyDeviceToHost));   // symmetric
+    if (o->Y)
+        CKR(fetch_big(c, o->Y, [&](double* dst, size_t c0, size_t nc) {
+            launch_uncenter(s.Y + c0 * d.ldG, dst, s.gmean, s.gsd, int(nc), d.G, d.ldG, c->stream);   // :335
+        }));
+    if (o->geneM) CK(cudaMemcpy(o->geneM, s.gmean, size_t(d.G) * 8, cudaMemcpyDeviceToHost));
+    if (o->geneSd) CK(cudaMemcpy(o->geneSd, s.gsd, size_t(d.G) * 8, cudaMemcpyDeviceToHost));
+    if (o->priorB) CK(cudaMemcpy(o->priorB, s.priorB, 8, cudaMemcpyDeviceToHost));
+    return SIMPLES_OK;
+}
+
+int simples_em_impute(const simples_em_args* a, simples_em_out* o) {
+    simples_ctx* c = nullptr;
+    CKR(simples_em_create(a, &c));
+    int r = simples_em_run(c, a->iter);
+    if (r == SIMPLES_OK && o) r = simples_em_fetch(c, o);
+    if (r == SIMPLES_OK) r = simples_em_sync(c);
+    simples_ctx_destroy(c);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
+    if (!a || !o) return fail(SIMPLES_EINVAL, "null argument");
+    CKR(check_common(a->G, a->n, a->M0, a->K0, a->MB));
+    if (!a->dat || !a->Y || !a->beta || !a->lambda || !a->sigma || !a->mu || !a->pi || !a->pg)
+        return fail(SIMPLES_EINVAL, "dat, Y, beta, lambda, sigma, mu, pi and pg are required");
+    if (a->mcmc < 1 || a->burnin < 0) return fail(SIMPLES_EINVAL, "mcmc must be >= 1 and burnin >= 0");
+    if (a->want_consensus && a->allreduce) return fail(SIMPLES_EINVAL, "consensus_cluster is single-rank only");
+    CKR(ensure_device());
+
+    std::unique_ptr<simples_ctx> guard(new simples_ctx());
+    simples_ctx* c = guard.get();
+    c->kind = 1;
+    if (a->stream) {
+        c->stream = (cudaStream_t)a->stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->cutoff = a->cutoff;
+    c->seed = a->seed;
+    c->compat = a->ref_compat_flags;
+    c->allreduce = a->allreduce;
+    c->allreduce_user = a->allreduce_user;
+    c->mcmc = a->mcmc;
+    c->burnin = a->burnin;
+    const bool shared = sigma_is_shared(a->sigma, a->G, a->M0);
+    CKR(setup_common(c, a->G, a->n, a->M0, a->K0, a->MB, a->n_total, a->cell_offset, a->Y, a->dat, a->pg, a->beta, a->sigma,
+                     a->lambda, a->pi, a->celltype, a->cutoff, shared));
+    DevState& s = c->s;
+    const Dims& d = s.d;
+    const int M0 = d.M0, K0 = d.K0, ldG = d.ldG, n = d.n, G = d.G;
+    const size_t na = c->n_alloc;
+    {
+        std::vector<double> hm = to_rowmajor(a->mu, G, M0, ldG, 0.0);
+        std::vector<double> pm(ldG, 0.0), ps(ldG, 1.0);
+        if (a->pos_mean) std::copy(a->pos_mean, a->pos_mean + G, pm.begin());
+        if (a->pos_sd) std::copy(a->pos_sd, a->pos_sd + G, ps.begin());
+        CK(cudaMemcpyAsync(s.mu, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.gmean, pm.data(), size_t(ldG) * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.gsd, ps.data(), size_t(ldG) * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    launch_center(s.Y, s.gmean, s.gsd, n, ldG, 0, 1, c->stream);   // Y <- (Y - pos_mean) / pos_sd  (:50)
+    CKR(c->dalloc(&c->rec1, na * ldG));
+    CKR(c->dalloc(&c->rec2, na * ldG));
+    CKR(c->dalloc(&c->rEF, size_t(n) * K0));
+    CKR(c->dalloc(&c->rF2, size_t(n) * K0));
+    CKR(c->dalloc(&c->rVF, size_t(n) * K0));
+    const int nit = a->mcmc + a->burnin;
+    CKR(c->dalloc(&c->tot_mi, size_t(nit) * (2 * M0 + 1)));
+    if (a->want_consensus && o->consensus_cluster) CKR(c->dalloc(&c->cons, size_t(n) * n));
+    const double pi_const = (c->compat & SIMPLES_COMPAT_PI) ? 3.14159265359 : M_PI;
+
+    CKR(run_prep(c));   // parameters are fixed: cluster constants computed once, not per sweep
+    for (int it = 1; it <= nit; ++it) {                                       // :67
+        const bool rec = it > a->burnin;
+        c->sweep = unsigned(it - 1);
+        CKR(e_pass(c, true, false, true, true, rec, false, pi_const));        // :69-104, :107, :112
+        launch_finalize_cell(s.part_cell, s.ncta_cell, M0, c->tot_mi + size_t(it - 1) * (2 * M0 + 1), c->stream);   // :89
+        if (rec && c->cons) launch_consensus(s.z, c->cons, n, M0, c->stream);   // :96
+        CKR(run_sweep(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));   // :109-136, :140-141
+        if (rec) launch_mi_record_factors(d, s.W, s.z, s.cc.Mm, c->rEF, c->rF2, c->rVF, c->stream);   // :143-147
+    }
+    CK(cudaGetLastError());
+    CKR(allreduce(c, c->tot_mi, size_t(nit) * (2 * M0 + 1)));
+    CK(cudaStreamSynchronize(c->stream));
+
+    // ---- outputs (R/do_impute.R:156-159) ----
+    if (o->loglik) {
+        std::vector<double> t(size_t(nit) * (2 * M0 + 1));
+        CK(cudaMemcpy(t.data(), c->tot_mi, t.size() * 8, cudaMemcpyDeviceToHost));
+        double sacc = 0.0;
+        for (int it = a->burnin; it < nit; ++it) sacc += t[size_t(it) * (2 * M0 + 1) + 2 * M0];
+        *o->loglik = sacc / a->mcmc;
+    }
+    if (o->impt)
+        CKR(fetch_big(c, o->impt, [&](double* dst, size_t c0, size_t nc) {
+            launch_mi_finalize(s.Y + c0 * ldG, s.mask + c0 * (ldG / 32), c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean,
+                               s.gsd, dst, nullptr, int(nc), G, ldG, a->mcmc, c->stream);
+        }));
+    if (o->impt_var)
+        CKR(fetch_big(c, o->impt_var, [&](double* dst, size_t c0, size_t nc) {
+            launch_mi_finalize(s.Y + c0 * ldG, s.mask + c0 * (ldG / 32), c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean,
+                               s.gsd, nullptr, dst, int(nc), G, ldG, a->mcmc, c->stream);
+        }));
+    if (o->EF || o->varF) {
+        std::vector<double> ef(size_t(n) * K0), f2(size_t(n) * K0), vf(size_t(n) * K0);
+        CK(cudaMemcpy(ef.data(), c->rEF, ef.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(f2.data(), c->rF2, f2.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(vf.data(), c->rVF, vf.size() * 8, cudaMemcpyDeviceToHost));
+        const double mc = a->mcmc;
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < K0; ++k) {
+                const size_t e = size_t(i) * K0 + k, h = size_t(k) * n + i;
+                const double m1 = ef[e] / mc;
+                if (o->EF) o->EF[h] = m1;
+                if (o->varF) o->varF[h] = f2[e] / mc - m1 * m1 + vf[e] / mc;
+            }
+    }
+    if (o->consensus_cluster && c->cons) {
+        launch_scale(c->cons, size_t(n) * n, 1.0 / a->mcmc, c->stream);
+        CK(cudaMemcpyAsync(o->consensus_cluster, c->cons, size_t(n) * n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+// Prologue / epilogue / bookkeeping kernels: mask build (Y0 <= cutoff, R/EM_impute.R:173), clip and
+// gene means (R/EM_impute.R:82-90), centring, layout transposes, do_impute accumulators
+// (R/do_impute.R:139-148,156-159) and the optional n x n consensus matrix (R/do_impute.R:96).
+#include "ptx.cuh"
+#include "state.h"
+
+namespace sb {
+namespace {
+
+__global__ void k_build_mask(const double* Y0, uint32_t* mask, int ncell, int G, int ldG, double cutoff,
+                             unsigned long long* nnz) {
+    const int nwords = ldG / 32;
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)ncell * nwords;
+    unsigned long long cnt = 0;
+    for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nw;
+         w += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int cell = int(w / nwords), word = int(w - (long long)cell * nwords);
+        const int g = word * 32 + lane;
+        const bool bit = (g < G) && (Y0[size_t(cell) * G + g] <= cutoff);
+        const unsigned b = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) {
+            mask[size_t(cell) * nwords + word] = b;
+            cnt += __popc(b);
+        }
+    }
+    if (lane == 0 && cnt) atomicAdd(nnz, cnt);
+}
+
+__global__ void k_clip(double* Y, int n, int G, int ldG, double lower, double upper) {
+    const size_t total = size_t(n) * ldG;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        if (int(i % ldG) < G) {
+            double v = Y[i];
+            v = v > upper ? upper : v;
+            v = v < lower ? lower : v;
+            Y[i] = v;
+        }
+    }
+}
+
+__global__ void k_rowsum(const double* Y, double* part, int n, int ldG, int cps) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sp = blockIdx.y;
+    if (g >= ldG) return;
+    const int cbeg = sp * cps, cend = min(n, cbeg + cps);
+    double s = 0.0;
+    for (int i = cbeg; i < cend; ++i) s += Y[size_t(i) * ldG + g];
+    part[size_t(sp) * ldG + g] = s;
+}
+
+__global__ void k_center(double* Y, const double* gmean, const double* gsd, int n, int ldG) {
+    const size_t total = size_t(n) * ldG;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int g = int(i % ldG);
+        Y[i] = (Y[i] - gmean[g]) / gsd[g];
+    }
+}
+
+__global__ void k_transpose(const double* in, double* out, int rows, int cols, int ld_in, int ld_out) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = by + r, j = bx + threadIdx.x;
+        if (i < rows && j < cols) tile[r][threadIdx.x] = in[size_t(i) * ld_in + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = bx + r, i = by + threadIdx.x;
+        if (i < rows && j < cols) out[size_t(j) * ld_out + i] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void k_fill(double* p, size_t count, double v) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
+}
+__global__ void k_scale(double* p, size_t count, double s) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) p[i] *= s;
+}
+
+__global__ void k_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG) {
+    const size_t total = size_t(n) * G;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t c = i / G;
+        const int g = int(i - c * G);
+        out[i] = Y[c * ldG + g] * gsd[g] + gmean[g];
+    }
+}
+
+__global__ void k_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2,
+                              const double* gmean, const double* gsd, double* impt, double* impt_var, int n, int G, int ldG,
+                              int mcmc) {
+    const size_t total = size_t(n) * G;
+    const int nwords = ldG / 32;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t c = i / G;
+        const int g = int(i - c * G);
+        const size_t o = c * ldG + g;
+        const bool zero = (mask[c * nwords + (g >> 5)] >> (g & 31)) & 1u;
+        double m1, v;
+        if (zero) {
+            m1 = rec1[o] / mcmc;
+            v = rec2[o] / mcmc - m1 * m1;
+        } else {
+            m1 = Y[o];     // constant over sweeps: mean = Y, variance = 0
+            v = 0.0;
+        }
+        if (impt) impt[i] = m1 * gsd[g] + gmean[g];
+        if (impt_var) impt_var[i] = v;
+    }
+}
+
+__global__ void k_mi_record_factors(Dims d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
+                                    double* rVF) {
+    const int K0 = d.K0, M0 = d.M0, n = d.n;
+    const size_t total = size_t(n) * K0;
+    for (size_t e = blockIdx.x * size_t(blockDim.x) + threadIdx.x; e < total; e += size_t(gridDim.x) * blockDim.x) {
+        const size_t i = e / K0;
+        const int k = int(e - i * K0);
+        double ef = 0.0, f2 = 0.0, vf = 0.0;
+        for (int m = 0; m < M0; ++m) {
+            const double zz = z[i * M0 + m];
+            const double w = W[(size_t(m) * n + i) * K0 + k];
+            ef = fma(zz, w, ef);
+            f2 = fma(zz * w, w, f2);
+            vf = fma(zz, Mm[(size_t(m) * K0 + k) * K0 + k], vf);
+        }
+        rEF[e] += ef;
+        rF2[e] += f2;
+        rVF[e] += vf;
+    }
+}
+
+__global__ void k_consensus(const double* z, double* cons, int n, int M0) {
+    const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+    if (i >= n || j >= n) return;
+    double s = 0.0;
+    for (int m = 0; m < M0; ++m) s = fma(z[size_t(i) * M0 + m], z[size_t(j) * M0 + m], s);
+    cons[size_t(j) * n + i] += s;   // symmetric; column-major n x n
+}
+
+inline int gs_grid(size_t total) {
+    size_t g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return int(g);
+}
+
+}  // namespace
+
+void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int G, int ldG, double cutoff,
+                       unsigned long long* nnz, cudaStream_t st) {
+    k_build_mask<<<gs_grid(size_t(ncell) * ldG), 256, 0, st>>>(Y0chunk, mask, ncell, G, ldG, cutoff, nnz);
+}
+void launch_clip(double* Y, int n, int G, int ldG, double lower, double upper, cudaStream_t st) {
+    k_clip<<<gs_grid(size_t(n) * ldG), 256, 0, st>>>(Y, n, G, ldG, lower, upper);
+}
+void launch_rowsum(const double* Y, double* part, int n, int ldG, int nsplit, cudaStream_t st) {
+    const int cps = (n + nsplit - 1) / nsplit;
+    dim3 grid((ldG + 127) / 128, nsplit);
+    k_rowsum<<<grid, 128, 0, st>>>(Y, part, n, ldG, cps);
+}
+void launch_center(double* Y, const double* gmean, const double* gsd, int n, int ldG, double, int, cudaStream_t st) {
+    k_center<<<gs_grid(size_t(n) * ldG), 256, 0, st>>>(Y, gmean, gsd, n, ldG);
+}
+void launch_transpose(const double* in, double* out, int rows, int cols, int ld_in, int ld_out, cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    k_transpose<<<grid, block, 0, st>>>(in, out, rows, cols, ld_in, ld_out);
+}
+void launch_fill(double* p, size_t count, double v, cudaStream_t st) { k_fill<<<gs_grid(count), 256, 0, st>>>(p, count, v); }
+void launch_scale(double* p, size_t count, double s, cudaStream_t st) { k_scale<<<gs_grid(count), 256, 0, st>>>(p, count, s); }
+void launch_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG,
+                     cudaStream_t st) {
+    k_uncenter<<<gs_grid(size_t(n) * G), 256, 0, st>>>(Y, out, gmean, gsd, n, G, ldG);
+}
+void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2, const double* gmean,
+                        const double* gsd, double* impt, double* impt_var, int n, int G, int ldG, int mcmc, cudaStream_t st) {
+    k_mi_finalize<<<gs_grid(size_t(n) * G), 256, 0, st>>>(Y, mask, rec1, rec2, gmean, gsd, impt, impt_var, n, G, ldG, mcmc);
+}
+void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
+                              double* rVF, cudaStream_t st) {
+    k_mi_record_factors<<<gs_grid(size_t(d.n) * d.K0), 256, 0, st>>>(d, W, z, Mm, rEF, rF2, rVF);
+}
+void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t st) {
+    dim3 grid((n + 15) / 16, (n + 15) / 16), block(16, 16);
+    k_consensus<<<grid, block, 0, st>>>(z, cons, n, M0);
+}
+
+}  // namespace sb

@@ -1,0 +1,413 @@
+// M-step from (all-reduced) sufficient statistics -- R/EM_impute.R:234-318 without the augmented
+// designs:
+//   k_gene_solve : per gene lasso for the loadings (replaces glmnet, :256-261), sg (:263-267),
+//                  priorB_g (:268), sigma clip (:273-274).  One thread per gene.
+//   k_lmp        : priorB / loglik bookkeeping (Q5), lambda step (replaces solnp, :278-304), pi (:318).
+//   k_mu         : Woodbury mu update without the G x G bigM (:307-315).  One CTA per cluster.
+#include "linalg.cuh"
+#include "ptx.cuh"
+#include "state.h"
+
+namespace sb {
+namespace {
+
+constexpr int GW = 8;   // warps (= genes) per CTA in k_gene_solve
+
+struct StatView {   // pointers into the stats buffer
+    const double *C, *R2, *U2, *S, *a, *nz, *c, *tot;
+    int ldc;        // row stride of C
+};
+
+__device__ __host__ inline StatView stat_view(const double* st, const Dims& d, int general) {
+    StatView v;
+    const size_t nS = size_t(d.M0) * d.K0 * d.K0, nA = size_t(d.M0) * d.K0;
+    v.C = st;
+    if (!general) {
+        v.ldc = d.NVP;
+        v.R2 = st + size_t(d.ldG) * d.NVP;
+        v.U2 = nullptr;
+        v.S = v.R2 + d.ldG;
+    } else {
+        v.ldc = d.K0 * d.M0 + 2 * d.M0;
+        v.R2 = nullptr;
+        v.U2 = st + size_t(d.ldG) * v.ldc;
+        v.S = v.U2 + size_t(d.ldG) * d.M0;
+    }
+    v.a = v.S + nS;
+    v.nz = v.a + nA;
+    v.c = v.nz + d.M0;
+    v.tot = v.c + d.M0;
+    return v;
+}
+
+// Exact active-set polish of a coordinate-descent iterate (one warp, lane k owns coordinate k):
+// solve A_SS x = rhs_S - kappa sign_S and verify the KKT conditions.  On success b is overwritten.
+__device__ bool lasso_polish(const double* A, int K, double rhs, double kappa, double& b, double* L, double* xs, int* idx,
+                             int lane) {
+    const bool kl = lane < K;
+    const unsigned act = __ballot_sync(0xffffffffu, kl && b != 0.0);
+    const int ns = __popc(act);
+    if (ns == 0) return __ballot_sync(0xffffffffu, kl && fabs(rhs) > kappa * (1.0 + 1e-12)) == 0u;
+    const int pos = __popc(act & ((1u << lane) - 1u));
+    const bool mine = (act >> lane) & 1u;
+    if (mine) {
+        idx[pos] = lane;
+        xs[pos] = rhs - kappa * (b > 0.0 ? 1.0 : -1.0);
+    }
+    __syncwarp();
+    for (int e = lane; e < ns * ns; e += 32) {
+        const int i = e / ns, j = e - i * ns;
+        L[e] = A[idx[i] * K + idx[j]];
+    }
+    __syncwarp();
+    warp_cholesky(L, ns, lane);
+    bool bad = false;
+    for (int i = 0; i < ns; ++i) bad |= !(L[i * ns + i] > 0.0);
+    if (bad) return false;
+    warp_chol_solve(L, xs, ns, lane);
+    const double xm = mine ? xs[pos] : 0.0;
+    if (__ballot_sync(0xffffffffu, mine && ((xm > 0.0) != (b > 0.0) || xm == 0.0))) return false;
+    double gk = rhs;
+    if (kl && !mine)
+        for (int i = 0; i < ns; ++i) gk -= A[lane * K + idx[i]] * xs[i];
+    if (__ballot_sync(0xffffffffu, kl && !mine && fabs(gk) > kappa * (1.0 + 1e-10) + 1e-300)) return false;
+    if (mine) b = xm;
+    return true;
+}
+
+// min 0.5 b'Ab - rhs'b + kappa |b|_1 : cyclic coordinate descent from 0 (glmnet's start) + exact polish.
+__device__ double lasso_solve(const double* A, int K, double rhs, double kappa, double* L, double* xs, int* idx, int lane) {
+    double b = 0.0, r = rhs;
+    const bool kl = lane < K;
+    for (int sweep = 0; sweep < 20000; ++sweep) {
+        double maxd = 0.0, maxb = 1.0;
+        for (int k = 0; k < K; ++k) {
+            const double akk = A[k * K + k];
+            const double rk = __shfl_sync(0xffffffffu, r, k), bk = __shfl_sync(0xffffffffu, b, k);
+            const double t = rk + akk * bk;
+            const double at = fabs(t) - kappa;
+            const double bn = at > 0.0 ? copysign(at, t) / akk : 0.0;
+            const double dlt = bn - bk;
+            if (dlt != 0.0) {
+                if (kl) r -= dlt * A[lane * K + k];
+                if (lane == k) b = bn;
+            }
+            maxd = fmax(maxd, fabs(dlt));
+            maxb = fmax(maxb, fabs(bn));
+        }
+        const bool done = maxd <= 1e-15 * maxb;
+        if (sweep >= 3 && ((sweep & 3) == 3 || done)) {
+            if (lasso_polish(A, K, rhs, kappa, b, L, xs, idx, lane)) return b;
+            if (done) return b;
+        }
+    }
+    return b;
+}
+
+__global__ void __launch_bounds__(GW * 32) k_gene_solve(MstepArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const Dims& d = a.d;
+    const int K0 = d.K0, M0 = d.M0;
+    const StatView sv = stat_view(a.stats, d, a.general);
+    const int KK = K0 * K0;
+    double* sAsum = sm;                       // [K0][K0]  sum_m (S_m + nz_m M_m)
+    double* sa = sAsum + KK;                  // [M0][K0]
+    double* sred = sa + M0 * K0;              // [GW]
+    double* sL = sred + GW;                   // [GW][K0*K0]
+    double* sAl = sL + GW * KK;               // [GW][K0*K0]   (general path)
+    double* sxs = sAl + (a.general ? GW * KK : 0);   // [GW][K0]
+    int* sidx = reinterpret_cast<int*>(sxs + GW * K0);   // [GW][K0]
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        double s = 0.0;
+        for (int m = 0; m < M0; ++m) s += sv.S[size_t(m) * KK + e] + sv.nz[m] * a.Mm[size_t(m) * KK + e];
+        sAsum[e] = s;
+    }
+    for (int e = threadIdx.x; e < M0 * K0; e += blockDim.x) sa[e] = sv.a[e];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool kl = lane < K0, ml = lane < M0;
+    const int g = blockIdx.x * GW + warp;
+    double prior = 0.0;
+    if (g < d.G) {
+        const double ntot = double(d.n_total);
+        const double N = double(M0) * ntot + K0;
+        const double* Cg = sv.C + size_t(g) * sv.ldc;
+        const double mu = ml ? a.mu[size_t(g) * M0 + lane] : 0.0;       // lane m
+        const double sgm = ml ? a.sigma[size_t(g) * M0 + lane] : 1.0;   // lane m
+        const double nzm = ml ? sv.nz[lane] : 0.0, cm = ml ? sv.c[lane] : 0.0;
+        double rhs = 0.0, bt = 0.0, d2, sumY, sumY2, var, kappa;
+        const double* A;
+        double* L = sL + warp * KK;
+        if (!a.general) {
+            const double sg0 = __shfl_sync(0xffffffffu, sgm, 0);
+            double s = kl ? Cg[lane] : 0.0;
+            for (int m = 0; m < M0; ++m) {
+                const double mum = __shfl_sync(0xffffffffu, mu, m);
+                if (kl) s -= mum * sa[m * K0 + lane];
+            }
+            bt = rhs = s;
+            const double U = ml ? Cg[K0 + lane] : 0.0, Uh = ml ? Cg[K0 + M0 + lane] : 0.0;
+            d2 = sv.R2[g] + warp_sum(-2.0 * mu * U + mu * mu * nzm);
+            sumY = warp_sum(Uh - mu * cm) / sqrt(sg0);
+            sumY2 = d2 / sg0;
+            var = (sumY2 - sumY * sumY / N) / (N - 1.0);
+            kappa = a.penl * var * sg0;     // objective scaled by sigma_g
+            A = sAsum;
+        } else {
+            double* Al = sAl + warp * KK;
+            for (int e = lane; e < KK; e += 32) {
+                double s = 0.0;
+                for (int m = 0; m < M0; ++m)
+                    s += (sv.S[size_t(m) * KK + e] + sv.nz[m] * a.Mm[size_t(m) * KK + e]) / a.sigma[size_t(g) * M0 + m];
+                Al[e] = s;
+            }
+            __syncwarp();
+            double s = 0.0, u = 0.0;
+            for (int m = 0; m < M0; ++m) {
+                const double mum = __shfl_sync(0xffffffffu, mu, m), sg_m = __shfl_sync(0xffffffffu, sgm, m);
+                if (kl) {
+                    const double bm = Cg[m * K0 + lane] - mum * sa[m * K0 + lane];
+                    s += bm / sg_m;
+                    u += bm;
+                }
+            }
+            rhs = s;
+            bt = u;
+            const double U = ml ? Cg[K0 * M0 + lane] : 0.0, Uh = ml ? Cg[K0 * M0 + M0 + lane] : 0.0;
+            const double D2 = ml ? sv.U2[size_t(g) * M0 + lane] - 2.0 * mu * U + mu * mu * nzm : 0.0;
+            d2 = warp_sum(D2);
+            sumY2 = warp_sum(D2 / sgm);
+            sumY = warp_sum((Uh - mu * cm) / sqrt(sgm));
+            var = (sumY2 - sumY * sumY / N) / (N - 1.0);
+            kappa = a.penl * var;
+            A = Al;
+        }
+        const double b = lasso_solve(A, K0, rhs, kappa, L, sxs + warp * K0, sidx + warp * K0, lane);
+        // sg = (sum_m D2 - 2 nb.(sum_m bm) + nb' (sum_m C_m) nb + 1) / (n + 3)
+        double ab = 0.0;
+        for (int k = 0; k < K0; ++k) {
+            const double bk = __shfl_sync(0xffffffffu, b, k);
+            if (kl) ab = fma(sAsum[lane * K0 + k], bk, ab);
+        }
+        const double quad = warp_sum(kl ? b * ab : 0.0);
+        const double lin = warp_sum(kl ? b * bt : 0.0);
+        const double l1 = warp_sum(kl ? fabs(b) : 0.0);
+        const double sg = (d2 - 2.0 * lin + quad + 1.0) / (ntot + 3.0);
+        prior = a.penl * var / sg * l1;
+        if (kl) a.beta[size_t(g) * K0 + lane] = b;
+        const double sgc = fmin(fmax(sg, 1e-4), 9.0);
+        if (ml) a.sigma[size_t(g) * M0 + lane] = sgc;
+    }
+    if (lane == 0) sred[warp] = prior;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < GW; ++i) s += sred[i];
+        a.part_gene[blockIdx.x] = s;
+    }
+}
+
+// Damped Newton for  min sum(E/x + c log x)  s.t. sum x = T  (mirrors oracle lambda_solve_k).
+__device__ void lambda_solve_k(const double* E, const double* c, double* x, int mt, double T) {
+    double g[MAXM], hm[MAXM], dx[MAXM], xn[MAXM];
+    double f = 0.0;
+    for (int m = 0; m < mt; ++m) f += E[m] / x[m] + c[m] * log(x[m]);
+    for (int it = 0; it < 500; ++it) {
+        double sg = 0.0, sh = 0.0;
+        for (int m = 0; m < mt; ++m) {
+            const double xi = x[m];
+            g[m] = -E[m] / (xi * xi) + c[m] / xi;
+            double h = fabs(2.0 * E[m] / (xi * xi * xi) - c[m] / (xi * xi));
+            if (h < 1e-300) h = 1e-300;
+            hm[m] = h;
+            sg += g[m] / h;
+            sh += 1.0 / h;
+        }
+        const double nu = -sg / sh;
+        double gd = 0.0, amax = 1.0, dmax = 0.0;
+        for (int m = 0; m < mt; ++m) {
+            dx[m] = -(g[m] + nu) / hm[m];
+            gd += g[m] * dx[m];
+            if (dx[m] < 0.0) {
+                const double al = -0.9 * x[m] / dx[m];
+                if (al < amax) amax = al;
+            }
+            if (fabs(dx[m]) > dmax) dmax = fabs(dx[m]);
+        }
+        if (dmax <= 1e-15 * T) break;
+        double al = amax, fn = f;
+        bool ok = false;
+        for (int bt = 0; bt < 60; ++bt) {
+            fn = 0.0;
+            for (int m = 0; m < mt; ++m) {
+                xn[m] = x[m] + al * dx[m];
+                fn += E[m] / xn[m] + c[m] * log(xn[m]);
+            }
+            if (fn <= f + 1e-4 * al * gd + 1e-14 * fabs(f)) {
+                ok = true;
+                break;
+            }
+            al *= 0.5;
+        }
+        if (!ok) break;
+        for (int m = 0; m < mt; ++m) x[m] = xn[m];
+        f = fn;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_lmp(MstepArgs a) {
+    const Dims& d = a.d;
+    const int K0 = d.K0, M0 = d.M0;
+    const StatView sv = stat_view(a.stats, d, a.general);
+    __shared__ int colnz[MAXK];
+    __shared__ int ind[MAXM];
+    __shared__ int mt_s;
+    if (threadIdx.x < MAXK) colnz[threadIdx.x] = 0;
+    __syncthreads();
+    // any(beta[,k] != 0) on the NEW beta (R/EM_impute.R:293)
+    for (int e = threadIdx.x; e < d.G * K0; e += blockDim.x)
+        if (a.beta[e] != 0.0) colnz[e % K0] = 1;
+    if (threadIdx.x == 0) {
+        // loglik[it] = tot - priorB(previous iteration)  (Q5), then priorB <- sum of this M-step
+        double pb = 0.0;
+        for (int i = 0; i < a.ncta_gene; ++i) pb += a.part_gene[i];
+        const double prev = a.priorB[0];
+        *a.loglik_slot = sv.tot[0] - (a.compat_priorb_prev ? prev : 0.0);
+        a.priorB[1] = prev;
+        a.priorB[0] = pb;
+        int mt = 0;
+        for (int m = 0; m < M0; ++m)
+            if (sv.nz[m] > K0 + 1 && sv.nz[m] > 3.0) ind[mt++] = m;      // :279
+        mt_s = mt;
+        for (int m = 0; m < M0; ++m)                                      // :318
+            a.pi[m] = (sv.nz[m] + a.pi_alpha - 1.0) / (double(d.n_total) + a.pi_alpha * M0 - M0);
+    }
+    __syncthreads();
+    if (!a.do_lambda) return;
+    const int mt = mt_s;
+    if (mt > 1) {
+        if (threadIdx.x < K0) {
+            const int k = threadIdx.x;
+            // lambda[-ind_m, ] <- 1/M0  (:288)
+            for (int m = 0; m < M0; ++m) {
+                bool in = false;
+                for (int q = 0; q < mt; ++q) in |= (ind[q] == m);
+                if (!in) a.lam[m * K0 + k] = 1.0 / M0;
+            }
+            if (!colnz[k]) {
+                for (int m = 0; m < M0; ++m) a.lam[m * K0 + k] = 1.0 / M0;   // :293-294
+            } else {
+                double E[MAXM], c[MAXM], x[MAXM];
+                double s = 0.0;
+                for (int q = 0; q < mt; ++q) {
+                    const int m = ind[q];
+                    E[q] = sv.S[(size_t(m) * K0 + k) * K0 + k] + a.Mm[(size_t(m) * K0 + k) * K0 + k] * sv.nz[m];  // :282-285
+                    c[q] = sv.nz[m] - 2.0;
+                    x[q] = (E[q] + 1.0) / (sv.nz[m] + 1.0);                 // :289
+                    s += x[q];
+                }
+                const double T = double(mt) / M0;
+                for (int q = 0; q < mt; ++q) x[q] = x[q] / s * mt / M0;     // :290
+                lambda_solve_k(E, c, x, mt, T);
+                for (int q = 0; q < mt; ++q) a.lam[ind[q] * K0 + k] = x[q];
+            }
+        }
+    } else {
+        for (int e = threadIdx.x; e < M0 * K0; e += blockDim.x) a.lam[e] = 1.0 / M0;   // :302
+    }
+}
+
+constexpr int MG = 64;
+
+__global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const Dims& d = a.d;
+    const int K0 = d.K0, M0 = d.M0, ldG = d.ldG;
+    const StatView sv = stat_view(a.stats, d, a.general);
+    const int m = blockIdx.x;
+    const int ucol = a.general ? K0 * M0 + m : K0 + m;
+    const double nzm = sv.nz[m];
+    double* sB = sm;               // [MG][K0]
+    double* sw = sB + MG * K0;     // 1/s
+    double* sv_ = sw + MG;         // v/s
+    double* sCm = sv_ + MG;        // [K0][K0]
+    double* srhs = sCm + K0 * K0;  // [K0]
+    const int NE = K0 * K0 + K0;
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int g0 = 0; g0 < ldG; g0 += MG) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < MG * K0; idx += blockDim.x) sB[idx] = a.beta[size_t(g0) * K0 + idx];
+        if (threadIdx.x < MG) {
+            const int g = g0 + threadIdx.x;
+            const double s = nzm + a.sigma[size_t(g) * M0 + m] / a.sigma0;     // :308
+            sw[threadIdx.x] = 1.0 / s;
+            sv_[threadIdx.x] = sv.C[size_t(g) * sv.ldc + ucol] / s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int e = threadIdx.x + q * 256;
+            if (e >= NE) continue;
+            double s = acc[q];
+            if (e < K0 * K0) {
+                const int j = e / K0, k = e - j * K0;
+                for (int r = 0; r < MG; ++r) s = fma(sB[r * K0 + j] * sw[r], sB[r * K0 + k], s);   // b2' B
+            } else {
+                const int k = e - K0 * K0;
+                for (int r = 0; r < MG; ++r) s = fma(sB[r * K0 + k], sv_[r], s);                   // b2' v
+            }
+            acc[q] = s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int e = threadIdx.x + q * 256;
+        if (e >= NE) continue;
+        if (e < K0 * K0) {
+            const int j = e / K0, k = e - j * K0;
+            sCm[e] = acc[q] + ((j == k) ? a.sigma0 / a.lam[m * K0 + k] : 0.0);   // :311
+        } else {
+            srhs[e - K0 * K0] = acc[q];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        warp_cholesky(sCm, K0, threadIdx.x);
+        warp_chol_solve(sCm, srhs, K0, threadIdx.x);
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
+        const double s = nzm + a.sigma[size_t(g) * M0 + m] / a.sigma0;
+        double t = 0.0;
+        for (int k = 0; k < K0; ++k) t += a.beta[size_t(g) * K0 + k] * srhs[k];
+        a.mu[size_t(g) * M0 + m] = (sv.C[size_t(g) * sv.ldc + ucol] - t) / s;      // v/s - b2 x
+    }
+}
+
+}  // namespace
+
+int mstep_gene_ctas(int G) { return (G + GW - 1) / GW; }
+
+void launch_mstep(const MstepArgs& a, cudaStream_t st) {
+    const int K0 = a.d.K0, M0 = a.d.M0;
+    {
+        const size_t KK = size_t(K0) * K0;
+        const size_t smem = sizeof(double) * (KK + size_t(M0) * K0 + GW + GW * KK * (a.general ? 2 : 1) + GW * K0) +
+                            sizeof(int) * GW * K0;
+        static size_t attr = 0;
+        if (smem > 48 * 1024 && smem > attr) {
+            cudaFuncSetAttribute(k_gene_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            attr = smem;
+        }
+        k_gene_solve<<<a.ncta_gene, GW * 32, smem, st>>>(a);
+    }
+    k_lmp<<<1, 256, 0, st>>>(a);
+    {
+        const size_t smem = sizeof(double) * (size_t(MG) * K0 + 2 * MG + K0 * K0 + K0);
+        k_mu<<<M0, 256, smem, st>>>(a);
+    }
+}
+
+}  // namespace sb

@@ -1,0 +1,89 @@
+// Counter-based variate tape (Philox4x32-10) and the inverse-CDF samplers that
+// replace the reference's sequential R RNG calls (rmultinom / rmvnorm / rbinom /
+// rnorm / msm::rtnorm at R/EM_impute.R:164-193, R/do_impute.R:107-131).
+// Keyed by (seed; sweep, GLOBAL cell index, gene) so results do not depend on
+// the number of GPUs.  Mirrored bit-for-bit by the test oracle.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sb {
+
+struct Philox4 {
+    uint32_t x0, x1, x2, x3;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// ((x >> 12) + 0.5) * 2^-52  in (0,1)
+__device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
+    const uint64_t x = (static_cast<uint64_t>(hi) << 32) | lo;
+    return (static_cast<double>(x >> 12) + 0.5) * 2.220446049250313e-16;
+}
+
+// per-entry uniforms: tag 0, counter (gene, cell_lo, sweep, cell_hi << 8)
+__device__ __forceinline__ void entry_uniforms(uint64_t seed, uint32_t sweep, uint64_t cell, uint32_t gene, double& ua,
+                                               double& ub) {
+    const Philox4 p = philox4x32_10(gene, static_cast<uint32_t>(cell), sweep, static_cast<uint32_t>(cell >> 32) << 8,
+                                    static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    ua = u52(p.x0, p.x1);
+    ub = u52(p.x2, p.x3);
+}
+
+// per-cell uniforms: tag 1, block j -> uniforms 2j, 2j+1
+__device__ __forceinline__ void cell_uniform_pair(uint64_t seed, uint32_t sweep, uint64_t cell, uint32_t j, double& u0,
+                                                  double& u1) {
+    const Philox4 p = philox4x32_10(j, static_cast<uint32_t>(cell), sweep,
+                                    (static_cast<uint32_t>(cell >> 32) << 8) | 1u, static_cast<uint32_t>(seed),
+                                    static_cast<uint32_t>(seed >> 32));
+    u0 = u52(p.x0, p.x1);
+    u1 = u52(p.x2, p.x3);
+}
+
+// z <= r with Phi(z) = u * Phi(r); log-space Newton (erfcx form) for r < -30.
+__device__ __forceinline__ double trunc_z(double u, double r) {
+    double z;
+    if (r >= -30.0) {
+        z = normcdfinv(u * normcdf(r));
+    } else {
+        const double S2 = 1.4142135623730951, S2PI = 2.5066282746310002;
+        const double lu = log(u);
+        const double t = lu + log(0.5 * erfcx(-r / S2)) - 0.5 * r * r;
+        z = -sqrt(r * r - 2.0 * lu);
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            const double e = 0.5 * erfcx(-z / S2);
+            z = z - (log(e) - 0.5 * z * z - t) * e * S2PI;
+        }
+    }
+    return fmin(z, r);
+}
+
+// One zero entry: R/EM_impute.R:175-198.  ms/sds already include gene_sd, gene_mean.
+__device__ __forceinline__ double sample_entry(double ms, double sds, double p, double cutoff, double ua, double ub) {
+    const double r = (cutoff - ms) / sds;
+    const double prob = normcdf(r);                              // pnorm(cutoff, ms, sds)
+    const double prob_drop = (1.0 - p) / (prob * p + (1.0 - p));
+    double zz;
+    if (ua < prob_drop) zz = normcdfinv(ub);                     // dropout: N(ms, sds)
+    else zz = trunc_z(ub, r);                                    // expressed but <= cutoff: TN(upper = cutoff)
+    return ms + sds * zz;
+}
+
+}  // namespace sb

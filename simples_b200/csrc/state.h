@@ -1,0 +1,180 @@
+// Device-resident state of one EM_impute / do_impute context and the launch
+// interface of every kernel.  Layouts (all FP64 unless noted):
+//   Y      [n][ldG]        cell-major, genes contiguous (== R's column-major G x n with padded ld)
+//   mask   [n][ldG/32]     u32 bitmask, bit g%32 of word g/32 set <=> Y0[g,i] <= cutoff
+//   beta   [ldG][K0]   sigma/mu [ldG][M0]   pg [ldG][MB]   gmean/gsd [ldG]   (gene-major rows)
+//   lam    [M0][K0]   pi [M0]   z [n][M0]
+//   Q      [NS][ldG][QS]   projection operand  [B/sigma_s | mu_m/sigma_cs(m) | 0-pad]
+//   isg    [NS][ldG]       1/sigma_s
+//   Qs     [ldG][FS]       sweep operand       [B*sd | mu*sd | mean | 0-pad]
+//   P      [NS][n][NQP]    Y^T Q          S2 [NS][n]   sum_g Y^2/sigma_s
+//   V      [n][VS]         M-step operand [Wbar (K0) | z (M0) | sqrt z (M0) | 0-pad],  zsum [n]
+//   Fh     [n][FS]         sweep operand  [f_i (K0) | onehot(m_i) (M0) | 1 | 0-pad]
+//   W      [M0][n][K0]     factor posterior means (Ef)
+// ldG = G rounded up to 64; padded genes have Y = 0, mask = 0, beta = mu = 0, sigma = 1.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sb {
+
+constexpr int GPAD = 64;     // ldG granularity
+constexpr int MAXK = 32;     // K0 <= 32
+constexpr int MAXM = 32;     // M0 <= 32
+constexpr int NUM_SMS_B200 = 148;
+
+enum KernelClass {
+    KC_PROJ = 0,      // estep_project   (DMMA)
+    KC_CELL,          // cell_post       (responsibilities, factor means, MC cell draws)
+    KC_SWEEP,         // impute_sweep    (DMMA + per-entry sampling)
+    KC_MSTATS,        // mstep_stats     (DMMA split-K)
+    KC_SSTATS,        // per-cluster K0xK0 second moments
+    KC_REDUCE,        // deterministic split-K / partial reductions
+    KC_PREP,          // cluster_prep
+    KC_GENE,          // mstep_gene_solve (lasso, sigma, priorB)
+    KC_LMP,           // lambda / mu / pi
+    KC_MISC,          // prologue, mask build, transposes, records
+    KC_COMM,          // all-reduce callback (time on stream)
+    KC_COUNT
+};
+
+struct Dims {
+    int G, ldG, n, M0, K0, MB;
+    int NS;            // distinct sigma columns in use: 1 (cluster-shared) or M0
+    int NQ, NQP, QS;   // projection cols: NQ = K0 + M0 (per sigma column), padded to 8; row stride QS = NQP + 4
+    int NF, NFP, FS;   // sweep GEMM depth: NF = K0 + M0 + 1 padded to 4 (NFP); row stride FS = NFP + 4 (== 4 mod 8)
+    int NV, NVP, VS;   // M-step cols: NV = K0 + 2 M0, padded to 8; row stride VS = NVP + 4
+    long long n_total, cell_offset;
+};
+
+struct ClusterConsts {   // device pointers, produced by cluster_prep
+    double* Mm;     // [M0][K0][K0]  (B' Sigma_m^-1 B + Lambda_m^-1)^-1
+    double* Mh;     // [M0][K0][K0]  symmetric square root of Mm
+    double* dt;     // [M0]
+    double* off;    // [M0][K0]   mu_m' (B / sigma_m)
+    double* offq;   // [M0][K0]   mu_m' (B / sigma_q)   q = M0-1 (stale beta2, Q1) -- used for the quadratic form in MC passes
+    double* cmu;    // [M0]       sum_g mu_gm^2 / sigma_gm
+    double* logpi;  // [M0]
+};
+
+struct DevState {
+    Dims d;
+    double *Y, *beta, *sigma, *mu, *pg, *gmean, *gsd, *lam, *pi, *z;
+    uint32_t* mask;
+    int32_t* celltype0;
+    double *Q, *isg, *Qs, *P, *S2, *V, *zsum, *Fh, *W;
+    int32_t* im;
+    ClusterConsts cc;
+    double* Mm_snap;   // [M0][K0][K0] copy of Mm at the last E-pass (returned as Varf)
+    // statistics: stats = [C (ldG x NVP) | R2 (ldG) | S (M0 K0 K0) | a (M0 K0) | nz (M0) | c (M0) | tot (1)]
+    double* stats;
+    size_t stats_count;
+    double *part_ms;   // mstats split-K partials [splitK][ldG][NVP+1]
+    double *part_cell; // cell_post partials [ncta][2*M0+1]
+    double *part_ss;   // sstats partials [nsplit][M0][K0*K0+K0]
+    int splitK, ncta_cell, nsplit_ss;
+    // general (per-cluster sigma) path, allocated lazily
+    double *Vg;        // [n][K0*M0 + 2*M0] = [z_m W_m | z | sqrt z]
+    double *statsg;    // [T (M0 ldG K0) | U | Uh | U2 (ldG M0 each) | S | a | nz | c | tot]
+    size_t statsg_count;
+    double *loglik;    // [iter_cap]
+    double *priorB;    // [2]: current, previous
+    double *part_gene; // per-CTA priorB partials
+    int ncta_gene;
+};
+
+// ---- launchers (each in its own .cu) ------------------------------------------------------------
+struct ProjArgs {
+    const double* Y; const double* Q; const double* isg; double* P; double* S2;
+    int n, ldG, NQP, QS;
+};
+void launch_proj(const ProjArgs& a, cudaStream_t st);
+
+struct CellArgs {
+    Dims d;
+    const double *P, *S2;
+    ClusterConsts cc;
+    double* z;            // in/out
+    double *V, *zsum, *W, *Fh, *Vg;
+    int32_t* im;
+    double* part;         // [ncta][2*M0+1]: nz, c, tot
+    int ncta;
+    int update_z, stale_q, write_W, write_Vg, sample, draw_membership;
+    double ll_const;      // G * log(2 PI)
+    unsigned long long seed;
+    unsigned sweep;
+};
+void launch_cell(const CellArgs& a, cudaStream_t st);
+
+struct SweepArgs {
+    Dims d;
+    double* Y; const uint32_t* mask; const double *Qs, *Fh, *sigma, *pg, *gmean, *gsd;
+    const int32_t *im, *celltype0;
+    double cutoff, lower, upper;
+    int clip;
+    unsigned long long seed; unsigned sweep;
+    double *rec1, *rec2;   // optional do_impute accumulators (same layout as Y), nullptr otherwise
+};
+void launch_sweep(const SweepArgs& a, cudaStream_t st);
+
+struct MstatsArgs {
+    const double *Y, *V, *zsum; double* part;   // part [splitK][ldG][NVP+1]
+    int n, ldG, NVP, VS, splitK;
+};
+void launch_mstats(const MstatsArgs& a, cudaStream_t st);
+int mstats_pick_splitk(int ldG);
+
+// generic slow GEMM for the general-sigma path and the prologue: C[g][c] = sum_i f(Y[i][g]) * V[i][c]
+void launch_ygemm_simple(const double* Y, const double* V, double* part, int n, int ldG, int ncol, int vstride,
+                         int square, int nsplit, cudaStream_t st);
+void launch_reduce_parts(const double* part, double* out, size_t count, int nparts, cudaStream_t st);
+
+struct SstatsArgs { Dims d; const double *W, *z; double* part; int nsplit; };
+void launch_sstats(const SstatsArgs& a, cudaStream_t st);
+
+struct FinalizeArgs {
+    Dims d; const double *part_ms, *part_cell, *part_ss; int splitK, ncta_cell, nsplit_ss; double* stats;
+    size_t head; int skip_head;   // general-sigma path: the first `head` entries are produced elsewhere
+};
+void launch_finalize_stats(const FinalizeArgs& a, cudaStream_t st);
+// sums only the cell_post partials: out = [nz (M0) | c (M0) | tot]
+void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out, cudaStream_t st);
+
+struct PrepArgs {
+    Dims d; const double *beta, *sigma, *mu, *lam, *pi, *gmean, *gsd;
+    double *Q, *isg, *Qs; ClusterConsts cc; int stale_q;
+};
+void launch_prep(const PrepArgs& a, cudaStream_t st);
+
+struct MstepArgs {
+    Dims d;
+    const double* stats;      // shared-sigma layout (or statsg when general)
+    int general;
+    double *beta, *sigma, *mu, *lam, *pi;
+    const double* Mm;         // pre-M-step cluster matrices
+    double *loglik_slot;      // loglik[it-1]
+    double *priorB;           // [0]=current (written), [1]=previous (read, then updated)
+    double *part_gene; int ncta_gene;
+    double penl, sigma0, pi_alpha;
+    int do_lambda, compat_priorb_prev;
+};
+void launch_mstep(const MstepArgs& a, cudaStream_t st);
+int mstep_gene_ctas(int G);
+
+// misc
+void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int G, int ldG, double cutoff, unsigned long long* nnz,
+                       cudaStream_t st);
+void launch_clip(double* Y, int n, int G, int ldG, double lower, double upper, cudaStream_t st);
+void launch_rowsum(const double* Y, double* part, int n, int ldG, int nsplit, cudaStream_t st);
+void launch_center(double* Y, const double* gmean, const double* gsd, int n, int ldG, double scale_n, int mode, cudaStream_t st);
+void launch_transpose(const double* in, double* out, int rows, int cols, int ld_in, int ld_out, cudaStream_t st);
+void launch_fill(double* p, size_t count, double v, cudaStream_t st);
+void launch_scale(double* p, size_t count, double s, cudaStream_t st);
+void launch_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG, cudaStream_t st);
+void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2, const double* gmean,
+                        const double* gsd, double* impt, double* impt_var, int n, int G, int ldG, int mcmc, cudaStream_t st);
+void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
+                              double* rVF, cudaStream_t st);
+void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t st);
+
+}  // namespace sb
