@@ -176,6 +176,8 @@ SIMPLES_API const char *simples_kernel_name(int k);
 SIMPLES_API int simples_kernel_count(void);
 /* Number of entries with Y0 <= cutoff in this context's shard. */
 SIMPLES_API int64_t simples_em_nnz0(simples_ctx *ctx);
+/* CUDA kernels enqueued by the last simples_em_run on this context. */
+SIMPLES_API int64_t simples_em_kernel_launches(simples_ctx *ctx);
 SIMPLES_API void simples_ctx_destroy(simples_ctx *ctx);
 
 #ifdef __cplusplus

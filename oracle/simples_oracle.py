@@ -124,7 +124,8 @@ def trunc_z(u, r):
     solved in log space by 4 Newton steps on log Phi (erfcx form)."""
     u = np.asarray(u, dtype=np.float64)
     r = np.asarray(r, dtype=np.float64)
-    u, r = np.broadcast_arrays(u, r)
+    u, r = np.broadcast_arrays(np.atleast_1d(u), np.atleast_1d(r))
+    scalar = (np.ndim(u) == 1 and u.shape == (1,))
     z = special.ndtri(u * special.ndtr(r))
     deep = r < TRUNC_LOG_BRANCH
     if np.any(deep):
@@ -138,7 +139,8 @@ def trunc_z(u, r):
             zd = zd - (np.log(e) - 0.5 * zd * zd - t) * e * _SQRT2PI
         z = z.copy()
         z[deep] = zd
-    return np.minimum(z, r)
+    out = np.minimum(z, r)
+    return out
 
 
 def sym_sqrt(M):

@@ -7,9 +7,9 @@ Importing this package never imports the test oracle and never falls back to
 CPU arithmetic.
 """
 from ._lib import (COMPAT_DEFAULT, COMPAT_MU_DIV_N, COMPAT_PI, COMPAT_PRIORB_PREV, COMPAT_STALE_DT, LIB_PATH,
-                   SimplesError, load)
+                   SimplesError, init, load)
 from .api import EM_impute, EMContext, do_impute
 from .dist import CellShard, partition
 
-__all__ = ["EM_impute", "do_impute", "EMContext", "CellShard", "partition", "SimplesError", "load", "LIB_PATH",
+__all__ = ["EM_impute", "do_impute", "EMContext", "CellShard", "partition", "SimplesError", "load", "init", "LIB_PATH",
            "COMPAT_DEFAULT", "COMPAT_STALE_DT", "COMPAT_PI", "COMPAT_MU_DIV_N", "COMPAT_PRIORB_PREV"]

@@ -75,7 +75,8 @@ EXPORTS = [
     "simples_abi_version", "simples_init", "simples_shutdown", "simples_last_error",
     "simples_em_impute", "simples_do_impute", "simples_em_create", "simples_em_run", "simples_em_fetch",
     "simples_em_sync", "simples_em_iter_ms", "simples_em_set_profile", "simples_em_profile",
-    "simples_kernel_name", "simples_kernel_count", "simples_em_nnz0", "simples_ctx_destroy",
+    "simples_kernel_name", "simples_kernel_count", "simples_em_nnz0", "simples_em_kernel_launches",
+    "simples_ctx_destroy",
 ]
 
 _lib = None
@@ -108,6 +109,8 @@ def load():
     lib.simples_kernel_count.restype = C.c_int
     lib.simples_em_nnz0.argtypes = [C.c_void_p]
     lib.simples_em_nnz0.restype = C.c_int64
+    lib.simples_em_kernel_launches.argtypes = [C.c_void_p]
+    lib.simples_em_kernel_launches.restype = C.c_int64
     lib.simples_ctx_destroy.argtypes = [C.c_void_p]
     lib.simples_ctx_destroy.restype = None
     _lib = lib
@@ -118,3 +121,9 @@ def check(rc):
     if rc < 0:
         raise SimplesError(rc, load().simples_last_error().decode("utf-8", "replace"))
     return rc
+
+
+def init(device: int = 0):
+    """Bind this process to one GPU (one process per GPU)."""
+    devs = (C.c_int * 1)(int(device))
+    check(load().simples_init(1, devs))

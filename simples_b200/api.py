@@ -182,6 +182,10 @@ class EMContext:
     def nnz0(self):
         return int(self._lib.simples_em_nnz0(self._h))
 
+    @property
+    def kernel_launches(self):
+        return int(self._lib.simples_em_kernel_launches(self._h))
+
     def fetch(self, big=True):
         o, bufs = _em_out(self.G, self.n, self.M0, self.K0, self.iters_done)
         if not big:

@@ -91,6 +91,7 @@ struct simples_ctx {
     std::vector<double> iter_ms;
     bool profile = false;
     std::vector<EvRec> evs;
+    long long kernel_launches = 0;   // kernels enqueued since the last simples_em_run began
     long long prof_launches[KC_COUNT] = {0};
     double prof_ms[KC_COUNT] = {0};
 
@@ -144,7 +145,10 @@ namespace {
 
 struct P {   // RAII profile scope
     simples_ctx* c;
-    P(simples_ctx* c_, int cls) : c(c_) { c->prof_begin(cls); }
+    P(simples_ctx* c_, int cls, int nk = 1) : c(c_) {
+        c->kernel_launches += nk;
+        c->prof_begin(cls);
+    }
     ~P() { c->prof_end(); }
 };
 
@@ -173,7 +177,7 @@ int ensure_device() {
 
 int allreduce(simples_ctx* c, double* buf, size_t count) {
     if (!c->allreduce) return SIMPLES_OK;
-    P p(c, KC_COMM);
+    P p(c, KC_COMM, 0);
     if (c->allreduce(c->allreduce_user, buf, count, (void*)c->stream) != 0)
         return fail(SIMPLES_ECOMM, "all-reduce callback failed");
     return SIMPLES_OK;
@@ -370,7 +374,7 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
 
 int run_prep(simples_ctx* c) {
     DevState& s = c->s;
-    P p(c, KC_PREP);
+    P p(c, KC_PREP, 2);
     PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.cc, 0};
     launch_prep(pa, c->stream);
     CK(cudaGetLastError());
@@ -457,7 +461,7 @@ int em_iteration(simples_ctx* c) {
         const int ncg = d.K0 * d.M0 + 2 * d.M0;
         const size_t nC = size_t(d.ldG) * ncg, nU2 = size_t(d.ldG) * d.M0;
         {
-            P p(c, KC_MSTATS);
+            P p(c, KC_MSTATS, 4);
             launch_ygemm_simple(s.Y, s.Vg, c->part_g, d.n, d.ldG, ncg, ncg, 0, c->nsplit_g, c->stream);
             launch_reduce_parts(c->part_g, s.statsg, nC, c->nsplit_g, c->stream);
             launch_ygemm_simple(s.Y, s.Vg + size_t(d.K0) * d.M0, c->part_g, d.n, d.ldG, d.M0, ncg, 1, c->nsplit_g, c->stream);
@@ -482,7 +486,7 @@ int em_iteration(simples_ctx* c) {
 
     // ---- M-step ----
     {
-        P p(c, KC_GENE);
+        P p(c, KC_GENE, 3);
         MstepArgs ma{};
         ma.d = d;
         ma.stats = stats;
@@ -699,6 +703,7 @@ int simples_em_run(simples_ctx* c, int iters) {
     for (auto e : c->iter_ev) cudaEventDestroy(e);
     c->iter_ev.clear();
     c->iter_ms.clear();
+    c->kernel_launches = 0;
     for (int k = 0; k < KC_COUNT; ++k) {
         c->prof_launches[k] = 0;
         c->prof_ms[k] = 0;
@@ -751,6 +756,7 @@ int simples_em_profile(simples_ctx* c, int64_t* launches, double* total_ms, int 
 }
 
 int64_t simples_em_nnz0(simples_ctx* c) { return c ? c->nnz0 : -1; }
+int64_t simples_em_kernel_launches(simples_ctx* c) { return c ? c->kernel_launches : -1; }
 
 int simples_em_fetch(simples_ctx* c, simples_em_out* o) {
     if (!c || !o || c->kind != 0) return fail(SIMPLES_EINVAL, "not an EM context");

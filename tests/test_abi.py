@@ -1,0 +1,82 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/*.h
+declares, validates arguments, and FAILS LOUDLY (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "simples_b200.h")) as f:
+        src = f.read()
+    return sorted(set(re.findall(r"SIMPLES_API[^;(]*?\b(simples_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    syms = declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(built_lib, s), f"{s} declared in include/simples_b200.h but not exported"
+    from simples_b200 import _lib
+    assert sorted(_lib.EXPORTS) == syms
+    assert built_lib.simples_abi_version() == 1
+
+
+def test_kernel_names(built_lib):
+    n = built_lib.simples_kernel_count()
+    names = [built_lib.simples_kernel_name(i).decode() for i in range(n)]
+    assert "estep_project" in names and "impute_sweep" in names and "mstep_stats" in names and len(set(names)) == n
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of the POD structs: field order and sizes follow the header."""
+    from simples_b200 import _lib
+    assert C.sizeof(_lib.EmOut) == 13 * 8 and C.sizeof(_lib.MiOut) == 6 * 8
+    assert _lib.EmArgs.G.offset == 0 and _lib.EmArgs.Y.offset == 24 and _lib.EmArgs.cutoff.offset == 48
+    assert _lib.EmArgs.seed.offset % 8 == 0 and C.sizeof(_lib.EmArgs) % 8 == 0
+    assert _lib.MiArgs.dat.offset == 24
+
+
+def test_argument_validation_without_gpu(built_lib):
+    import simples_b200 as sb
+    G, n, K0, M0 = 4, 3, 2, 1
+    ok = dict(Y=np.ones((G, n)), Y0=np.ones((G, n)), pg=np.ones((G, 1)), beta=np.ones((G, K0)), sigma=np.ones((G, M0)),
+              lam=np.ones((M0, K0)), pi=[1.0])
+    with pytest.raises(sb.SimplesError) as e:       # K0 out of range -> EINVAL before any device work
+        sb.EM_impute(ok["Y"], ok["Y0"], ok["pg"], M0, 40, 0.1, 1, np.ones((G, 40)), ok["sigma"], np.ones((M0, 40)), ok["pi"], None)
+    assert e.value.code == -1
+    with pytest.raises(ValueError):                  # host-side shape check
+        sb.EM_impute(ok["Y"], ok["Y0"][:, :2], ok["pg"], M0, K0, 0.1, 1, ok["beta"], ok["sigma"], ok["lam"], ok["pi"], None)
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device the product path must raise, not compute."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    import simples_b200 as sb
+    G, n, K0, M0 = 4, 3, 2, 1
+    with pytest.raises(sb.SimplesError) as e:
+        sb.EM_impute(np.ones((G, n)), np.ones((G, n)), np.ones((G, 1)), M0, K0, 0.1, 1, np.ones((G, K0)), np.ones((G, M0)),
+                     np.ones((M0, K0)), [1.0], None)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(sb.SimplesError):
+        sb.do_impute(np.ones((G, n)), np.ones((G, n)), np.ones((G, K0)), np.ones((M0, K0)), np.ones((G, M0)),
+                     np.zeros((G, M0)), [1.0])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "simples_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dp, f)) as fh:
+                    src = fh.read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f

@@ -1,0 +1,199 @@
+"""GPU parity tests (run on a B200 with -m gpu): every call goes through the C ABI
+(simples_b200.EM_impute / do_impute -> libsimples_b200.so) and is compared with the CPU oracle on the
+same seeded inputs and the same Philox variate tape.  Tolerances are north_star's: <= 1e-8 relative
+on parameters / log-likelihood, <= 1e-6 relative on imputed entries, identical cluster assignments."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from util import assert_em_close, em_args, make_case, rel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def sb(built_lib):
+    import simples_b200
+    simples_b200.init(0)
+    return simples_b200
+
+
+CASES = [
+    # n,   G,   K, MC, K0, M0, iters, impt_it, nonshared
+    (200, 150, 3, 3, 4, 3, 1, 5, False),     # one deterministic iteration
+    (200, 150, 3, 3, 4, 3, 5, 9, False),     # deterministic EM (impt_it >= iter never samples, R/EM_impute.R:161)
+    (200, 150, 3, 3, 4, 3, 4, 1, False),     # Monte-Carlo EM
+    (200, 150, 3, 3, 4, 3, 3, 1, True),      # user-supplied per-cluster sigma (general path at it = 1)
+    (333, 257, 3, 2, 3, 2, 4, 2, False),     # ragged: G % 64 != 0, n % 128 != 0
+    (130, 64, 1, 1, 2, 1, 3, 1, False),      # M0 = 1 (no membership draw, R/EM_impute.R:165-166)
+    (900, 520, 6, 5, 12, 7, 3, 1, False),    # K0 + M0 > 16
+    (64, 40, 1, 2, 1, 2, 2, 1, False),       # K0 = 1, tiny
+    (1500, 1000, 6, 3, 10, 3, 3, 1, False),  # config C1 shape (vignette simulation, K0 = 10, M0 = 3)
+]
+
+
+@pytest.mark.parametrize("n,G,K,MC,K0,M0,iters,impt_it,nonshared", CASES)
+def test_em_impute_matches_oracle(sb, n, G, K, MC, K0, M0, iters, impt_it, nonshared):
+    st = make_case(n, G, K, MC, K0, M0, seed=3, nonshared=nonshared)
+    kw = dict(celltype=st["celltype"], impt_it=impt_it, est_z=1, est_lam=1, seed=7)
+    ref = O.em_impute_fast(*em_args(st, M0, K0, iters), **kw)
+    got = sb.EM_impute(*em_args(st, M0, K0, iters), **kw)
+    assert_em_close(got, ref, M0)
+
+
+def test_em_matches_literal_reference_formulation(sb):
+    """Against the literal restatement (augmented design + dense bigM), not the sufficient statistics."""
+    K0, M0 = 4, 3
+    st = make_case(120, 100, 3, 3, K0, M0, seed=12)
+    kw = dict(celltype=st["celltype"], impt_it=2, est_z=1, est_lam=1, seed=5)
+    ref = O.em_impute_ref(*em_args(st, M0, K0, 4), **kw)
+    got = sb.EM_impute(*em_args(st, M0, K0, 4), **kw)
+    assert_em_close(got, ref, M0)
+
+
+def test_em_reference_defaults_and_options(sb):
+    """est_z = 2 / est_lam = 2 defaults (R/EM_impute.R:76), z = NULL, explicit mu, max_lambda = F,
+    finite clip bounds, celltype with MB != M0 (SIMPLE_B style pg, R/SIMPLE_B.R:318-321)."""
+    K0, M0 = 5, 3
+    st = make_case(300, 200, 3, 3, K0, M0, seed=4, MB=4)
+    a = em_args(st, M0, K0, 4)
+    for kw in (dict(celltype=st["celltype"], impt_it=2, seed=1),                                   # defaults
+               dict(celltype=st["celltype"], impt_it=1, max_lambda=False, seed=2, penl=0.3, sigma0=10, pi_alpha=2),
+               dict(celltype=st["celltype"], impt_it=1, est_z=1, lower=-0.5, upper=4.0, num_mc=2, seed=3),
+               dict(celltype=None, impt_it=1, est_z=3, est_lam=3, seed=4)):
+        if kw["celltype"] is None:
+            st2 = dict(st, pg=st["pg"][:, :1])
+            a2 = em_args(st2, M0, K0, 4)
+        else:
+            a2 = a
+        ref = O.em_impute_fast(*a2, **kw)
+        got = sb.EM_impute(*a2, **kw)
+        assert_em_close(got, ref, M0)
+    # z = NULL => mu = 0 and z computed at it = 1 even though est_z = 2 (R/EM_impute.R:93-99,148)
+    a3 = a[:11] + (None,)
+    kw = dict(celltype=st["celltype"], impt_it=1, seed=5)
+    assert_em_close(sb.EM_impute(*a3, **kw), O.em_impute_fast(*a3, **kw), M0)
+    mu0 = np.random.default_rng(0).standard_normal((st["Y"].shape[0], M0)) * 0.1
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, mu=mu0, seed=6)
+    assert_em_close(sb.EM_impute(*a, **kw), O.em_impute_fast(*a, **kw), M0)
+
+
+def test_compat_flags(sb):
+    K0, M0 = 3, 3
+    st = make_case(150, 100, 3, 3, K0, M0, seed=6)
+    for flags in (O.COMPAT_DEFAULT & ~O.COMPAT_STALE_DT, O.COMPAT_DEFAULT & ~O.COMPAT_PI,
+                  O.COMPAT_DEFAULT & ~O.COMPAT_PRIORB_PREV):
+        kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=1)
+        ref = O.em_impute_fast(*em_args(st, M0, K0, 4), compat=flags, **kw)
+        got = sb.EM_impute(*em_args(st, M0, K0, 4), ref_compat=flags, **kw)
+        assert_em_close(got, ref, M0)
+
+
+def test_resident_context_equals_one_shot(sb):
+    K0, M0 = 4, 3
+    st = make_case(260, 190, 3, 3, K0, M0, seed=9)
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=11)
+    one = sb.EM_impute(*em_args(st, M0, K0, 5), **kw)
+    with sb.EMContext(st["Y"], st["Y0"], st["pg"], M0, K0, 0.1, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"],
+                      iter=2, **kw) as ctx:
+        ctx.run(2)
+        ctx.run(3)                    # grows the loglik array, continues the tape
+        two = ctx.fetch()
+        assert ctx.nnz0 == int((st["Y0"] <= 0.1).sum())
+        assert ctx.kernel_launches > 0 and len(ctx.iter_ms()) == 3
+    for k in ("loglik", "beta", "sigma", "mu", "lambda", "pi", "z", "Y"):
+        assert np.array_equal(one[k], two[k]), k            # bit-identical: deterministic reductions
+
+
+def test_run_to_run_determinism(sb):
+    K0, M0 = 6, 4
+    st = make_case(700, 300, 4, 4, K0, M0, seed=10)
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=3)
+    a = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
+    b = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
+    for k in ("loglik", "beta", "sigma", "mu", "lambda", "z", "Y"):
+        assert np.array_equal(a[k], b[k]), k
+    c = sb.EM_impute(*em_args(st, M0, K0, 3), **dict(kw, seed=4))
+    assert not np.array_equal(a["Y"], c["Y"])
+
+
+def test_do_impute_matches_oracle(sb):
+    K0, M0 = 5, 3
+    st = make_case(240, 180, 3, 3, K0, M0, seed=13, MB=2)
+    em = O.em_impute_fast(*em_args(st, M0, K0, 3), celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=2)
+    G = st["Y"].shape[0]
+    sd = np.random.default_rng(1).uniform(0.7, 1.4, G)
+    for pos_sd, pg in ((em["geneSd"], st["pg"]), (sd, 0.5)):
+        kw = dict(mcmc=5, burnin=2, pg=pg, cutoff=0.1, seed=21)
+        args = (st["Y0"], em["Y"], em["beta"], em["lambda"], em["sigma"], em["mu"], em["pi"], em["geneM"], pos_sd,
+                st["celltype"])
+        ref = O.do_impute_ref(*args, **kw)
+        got = sb.do_impute(*args, **kw)
+        assert abs(got["loglik"] - ref["loglik"]) <= 1e-8 * abs(ref["loglik"])
+        assert rel(got["impt"], ref["impt"]) <= 1e-6
+        assert np.abs(got["impt_var"] - ref["impt_var"]).max() <= 1e-6 * max(1.0, np.abs(ref["impt_var"]).max())
+        assert rel(got["EF"], ref["EF"]) <= 1e-7 and rel(got["varF"], ref["varF"]) <= 1e-7
+        assert rel(got["consensus_cluster"], ref["consensus_cluster"]) <= 1e-8
+    nocons = sb.do_impute(*args, consensus=False, **kw)
+    assert nocons["consensus_cluster"] is None and rel(nocons["impt"], ref["impt"]) <= 1e-6
+
+
+def test_golden_fixture(sb):
+    g = np.load(os.path.join(GOLD, "em_small.npz"))
+    K0, M0 = int(g["K0"]), int(g["M0"])
+    got = sb.EM_impute(g["Y"], g["Y0"], g["pg"], M0, K0, 0.1, int(g["iter"]), g["beta"], g["sigma"], g["lam"], g["pi"],
+                       g["z"], celltype=g["celltype"], impt_it=1, est_z=1, est_lam=1, seed=int(g["seed"]))
+    for k in ("loglik", "pi", "mu", "sigma", "beta", "lambda", "z"):
+        assert rel(got[k], g["out_" + k]) <= 1e-8, k
+    assert rel(got["Y"], g["out_Y"]) <= 1e-6
+    assert rel(np.stack(got["Ef"]), g["out_Ef"]) <= 1e-7 and rel(np.stack(got["Varf"]), g["out_Varf"]) <= 1e-8
+    mi = sb.do_impute(g["Y0"], g["out_Y"], g["out_beta"], g["out_lambda"], g["out_sigma"], g["out_mu"], g["out_pi"],
+                      g["out_geneM"], np.ones(g["Y"].shape[0]), g["celltype"], mcmc=4, burnin=2, pg=g["pg"],
+                      seed=int(g["seed"]) + 1)
+    assert rel(mi["impt"], g["mi_impt"]) <= 1e-6 and abs(mi["loglik"] - float(g["mi_loglik"])) <= 1e-8 * abs(float(g["mi_loglik"]))
+
+
+def test_error_paths(sb):
+    K0, M0 = 3, 2
+    st = make_case(64, 40, 1, 2, K0, M0, seed=1)
+    bad_ct = st["celltype"].copy()
+    bad_ct[0] = 9
+    with pytest.raises(sb.SimplesError) as e:
+        sb.EM_impute(*em_args(st, M0, K0, 1), celltype=bad_ct)
+    assert e.value.code == -1 and "celltype" in str(e.value)
+
+
+def test_full_size_properties(sb):
+    """BASELINE.json configs[2] (100k cells x 2k genes, K0 = M0 = 10): size-independent properties --
+    observed entries untouched, imputed entries of non-recorded dropouts finite, z rows sum to 1,
+    sigma within the clip, finite log-likelihood, and a 4k-cell slice of the first deterministic
+    iteration agreeing with the oracle run on that slice (cells are conditionally independent)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from simples_b200 import synth
+    n, G, K0, M0 = 100_000, 2000, 10, 10
+    gp = synth.gene_params(G, 10, 10, seed=1)
+    Y2, Z = synth.simulate_shard(gp, n, shard=0, seed=1)
+    st = synth.init_state(gp, Y2, Z, K0, M0, seed=1)
+    kw = dict(celltype=st["celltype"], est_z=1, est_lam=1, impt_it=1, num_mc=3, seed=99)
+    with sb.EMContext(st["Y"], st["Y0"], st["pg"], M0, K0, 0.1, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"],
+                      iter=3, **kw) as ctx:
+        ctx.run(3)
+        out = ctx.fetch()
+    assert np.all(np.isfinite(out["loglik"])) and np.all(np.isfinite(out["beta"]))
+    obs = st["Y0"] > 0.1
+    assert np.allclose(out["Y"][obs], st["Y0"][obs], rtol=0, atol=1e-9)
+    assert np.all(np.isfinite(out["Y"]))
+    assert np.allclose(out["z"].sum(axis=1), 1.0, atol=1e-12)
+    assert out["sigma"].min() >= 1e-4 and out["sigma"].max() <= 9.0 and np.all(out["sigma"] == out["sigma"][:, :1])
+    assert abs(out["pi"].sum() - 1.0) < 1e-12 and np.allclose(out["lambda"].sum(axis=0), 1.0, atol=1e-9)
+    # E-pass on a slice == oracle E-pass on that slice with the returned (pre-M-step ... post) parameters:
+    # re-run one deterministic iteration on 4k cells starting from the fitted parameters.
+    sl = slice(0, 4000)
+    a = (np.asfortranarray(out["Y"][:, sl]), np.asfortranarray(st["Y0"][:, sl]), st["pg"], M0, K0, 0.1, 1, out["beta"],
+         out["sigma"], out["lambda"], out["pi"], out["z"][sl])
+    kw1 = dict(celltype=st["celltype"][sl], est_z=1, est_lam=1, impt_it=5, mu=out["mu"])
+    assert_em_close(sb.EM_impute(*a, **kw1), O.em_impute_fast(*a, **kw1), M0)

@@ -1,0 +1,198 @@
+"""CPU tests of the oracle (test infrastructure).  The reference ships no tests or golden vectors
+(SURVEY.md section 4), so the oracle is pinned by: published Philox KATs, closed-form identities
+(dense MVN vs Woodbury), KKT residuals of the lasso / lambda solvers, literal (augmented design,
+R/EM_impute.R:238-270) vs sufficient-statistic M-step, distributional checks of the samplers, and
+committed oracle-generated fixtures (tests/golden, regression only -- PARITY UNPINNED)."""
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy import special, stats
+
+import oracle as O
+from util import assert_em_close, em_args, make_case, rel
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32(*ctr, *key)
+        assert tuple(int(v) for v in got) == want
+
+
+def test_uniforms_open_interval_and_streams():
+    ua, ub = O.entry_uniforms(7, 3, np.arange(1000), np.arange(1000) % 17)
+    cu = O.cell_uniforms(7, 3, np.arange(1000), 11)
+    for u in (ua, ub, cu):
+        assert np.all(u > 0) and np.all(u < 1)
+    assert abs(ua.mean() - 0.5) < 0.05 and abs(cu.mean() - 0.5) < 0.02
+    # different sweep / seed / tag => different stream
+    ua2, _ = O.entry_uniforms(7, 4, np.arange(1000), np.arange(1000) % 17)
+    assert not np.allclose(ua, ua2)
+    # 64-bit cell indices
+    big = np.array([2**33 + 5, 5], dtype=np.uint64)
+    a, _ = O.entry_uniforms(1, 0, big, [3, 3])
+    assert a[0] != a[1]
+
+
+def test_trunc_z_distribution_and_tail():
+    rng = np.random.default_rng(0)
+    for r in (-3.0, -0.5, 0.7, 2.5):
+        u = rng.random(20000)
+        z = O.trunc_z(u, r)
+        assert np.all(z <= r)
+        ks = stats.kstest(z, lambda x: special.ndtr(x) / special.ndtr(r))
+        assert ks.pvalue > 1e-3
+    # deep tail (log-space branch) is continuous with the direct branch and exact
+    u = np.array([0.1, 0.5, 0.9])
+    for r in (-29.999, -30.001, -45.0, -200.0):
+        z = O.trunc_z(u, r)
+        lhs = special.log_ndtr(z)
+        rhs = np.log(u) + special.log_ndtr(r)
+        assert np.allclose(lhs, rhs, rtol=1e-12, atol=0)
+    assert abs(float(O.trunc_z(0.3, -29.999999)[0] - O.trunc_z(0.3, -30.000001)[0]) - 2e-6) < 1e-7   # continuous across the branch switch
+
+
+def test_woodbury_density_matches_dense_mvn():
+    rng = np.random.default_rng(1)
+    G, n, K0, M0 = 40, 25, 4, 3
+    beta = rng.standard_normal((G, K0))
+    sigma = rng.uniform(0.5, 2, (G, M0))
+    lam = rng.uniform(0.2, 1.5, (M0, K0))
+    mu = rng.standard_normal((G, M0))
+    pi = np.array([0.2, 0.3, 0.5])
+    Y = rng.standard_normal((G, n))
+    ll, lik, sc, Ms, _, _ = O.epass(Y, beta, sigma, lam, mu, pi, pi_const=math.pi)
+    for m in range(M0):
+        cov = beta @ np.diag(lam[m]) @ beta.T + np.diag(sigma[:, m])
+        want = stats.multivariate_normal(mu[:, m], cov).logpdf(Y.T) + math.log(pi[m])
+        assert np.allclose(ll[:, m], want, rtol=1e-9, atol=1e-9)
+    Wm = O.factor_means(Y, beta, sigma, mu, Ms)
+    for m in range(M0):   # Wm == x2 M_m
+        x2 = (Y - mu[:, m][:, None]).T @ (beta / sigma[:, m][:, None])
+        assert np.allclose(Wm[m], x2 @ Ms[m], rtol=1e-10, atol=1e-12)
+
+
+def test_lasso_kkt():
+    rng = np.random.default_rng(2)
+    K = 9
+    X = rng.standard_normal((60, K))
+    A = X.T @ X
+    for kap in (0.0, 1.0, 8.0, 30.0, 1e4):
+        rhs = rng.standard_normal((7, K)) * 10
+        b = O.lasso_solve_batch(A, rhs, np.full(7, kap))
+        grad = rhs - b @ A
+        act = b != 0
+        assert np.all(np.abs(grad[~act]) <= kap * (1 + 1e-9) + 1e-12)
+        assert np.allclose(grad[act], kap * np.sign(b[act]), rtol=1e-9, atol=1e-9)
+    Ag = np.stack([A * s for s in (0.5, 1.0, 2.0)])
+    rhs = rng.standard_normal((3, K)) * 10
+    b = O.lasso_solve_batch(Ag, rhs, np.full(3, 3.0))
+    for g in range(3):
+        assert np.allclose(b[g], O.lasso_solve(Ag[g], rhs[g], 3.0), atol=1e-12)
+
+
+def test_lambda_solver_kkt_both_regimes():
+    rng = np.random.default_rng(3)
+    for scale in (0.3, 1.0, 3.0):     # shrink / neutral / expand (non-convex) regimes
+        mt = 5
+        c = rng.uniform(20, 200, mt)
+        E = c * rng.uniform(0.05, 0.4, mt) * scale
+        T = mt / 7.0
+        x0 = (E + 1) / (c + 3)
+        x0 = x0 / x0.sum() * T
+        x = O.lambda_solve_k(E, c, x0, T)
+        assert abs(x.sum() - T) < 1e-12 and np.all(x > 0)
+        g = -E / x**2 + c / x
+        assert np.ptp(g) <= 1e-8 * np.abs(g).max() + 1e-10          # stationarity: equal multipliers
+        f = lambda v: np.sum(E / v + c * np.log(v))
+        for _ in range(20):                                          # local minimality on the constraint plane
+            d = rng.standard_normal(mt)
+            d -= d.mean()
+            xx = x + 1e-4 * d / np.linalg.norm(d) * x.min()
+            assert f(xx) >= f(x) - 1e-12 * abs(f(x))
+
+
+@pytest.mark.parametrize("nonshared", [False, True])
+def test_literal_vs_sufficient_statistics(nonshared):
+    K0, M0 = 4, 3
+    st = make_case(90, 130, 3, 3, K0, M0, seed=5, nonshared=nonshared)
+    kw = dict(celltype=st["celltype"], impt_it=2, est_z=1, est_lam=1, seed=9)
+    a = O.em_impute_ref(*em_args(st, M0, K0, 4), **kw)
+    b = O.em_impute_fast(*em_args(st, M0, K0, 4), **kw)
+    assert_em_close(b, a, M0, tol_param=1e-9, tol_y=1e-9)
+    n = st["Y"].shape[1]
+    c = O.em_impute_fast(*em_args(st, M0, K0, 4), shards=[0, 31, 64, n], **kw)   # 3-rank emulation
+    assert_em_close(c, a, M0, tol_param=1e-9, tol_y=1e-9)
+
+
+def test_quirk_flags_change_results():
+    K0, M0 = 3, 3
+    st = make_case(80, 100, 3, 3, K0, M0, seed=6)
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=1)
+    base = O.em_impute_fast(*em_args(st, M0, K0, 3), **kw)
+    nostale = O.em_impute_fast(*em_args(st, M0, K0, 3), compat=O.COMPAT_DEFAULT & ~O.COMPAT_STALE_DT, **kw)
+    nopi = O.em_impute_fast(*em_args(st, M0, K0, 3), compat=O.COMPAT_DEFAULT & ~O.COMPAT_PI, **kw)
+    nopb = O.em_impute_fast(*em_args(st, M0, K0, 3), compat=O.COMPAT_DEFAULT & ~O.COMPAT_PRIORB_PREV, **kw)
+    assert not np.array_equal(base["loglik"], nopi["loglik"])     # 3.14159265359 vs pi: ~1e-13 relative
+    assert np.allclose(base["loglik"][0], nopb["loglik"][0]) and not np.allclose(base["loglik"][1:], nopb["loglik"][1:], rtol=1e-13, atol=0)
+    assert base["loglik"].shape == nostale["loglik"].shape   # Q1 only matters once lambda rows differ
+    assert np.all(np.isfinite(nostale["beta"]))
+
+
+def test_sampler_matches_closed_form_mean():
+    """MC average of sample_sweep over many tape sweeps -> the conditional expectation
+    prob_drop*ms + (1-prob_drop)*(ms - sds*phi(r)/Phi(r)) (north_star; R/SIMPLE.R:59)."""
+    rng = np.random.default_rng(4)
+    G, n, K0, M0 = 6, 4, 2, 1
+    beta = rng.standard_normal((G, K0)) * 0.3
+    sigma = rng.uniform(0.5, 1.5, (G, M0))
+    mu = rng.standard_normal((G, M0)) * 0.5
+    pg = np.full((G, 1), 0.6)
+    mask = np.ones((G, n), dtype=bool)
+    Wm = [rng.standard_normal((n, K0)) * 0.2]
+    Ms = [np.zeros((K0, K0))]            # no factor noise -> ms is deterministic
+    z = np.ones((n, 1))
+    gm = rng.standard_normal(G) * 0.2
+    gs = np.ones(G)
+    acc = np.zeros((G, n))
+    S = 4000
+    for s in range(S):
+        Yc = np.zeros((G, n))
+        O.sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, np.zeros(n, dtype=int), gm, gs, 0.1, 42, s,
+                       draw_membership=False)
+        acc += Yc + gm[:, None]
+    ms = mu[:, [0]] + beta @ Wm[0].T + gm[:, None]
+    want = O.expected_impute(ms, np.sqrt(sigma[:, [0]]) * np.ones((1, n)), 0.6, 0.1)
+    assert np.abs(acc / S - want).max() < 6 * np.sqrt(sigma.max() / S)
+
+
+def test_do_impute_oracle_runs_and_shapes():
+    K0, M0 = 3, 2
+    st = make_case(60, 90, 2, 2, K0, M0, seed=8)
+    em = O.em_impute_fast(*em_args(st, M0, K0, 3), celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=2)
+    r = O.do_impute_ref(st["Y0"], em["Y"], em["beta"], em["lambda"], em["sigma"], em["mu"], em["pi"], em["geneM"],
+                        em["geneSd"], st["celltype"], mcmc=5, burnin=2, pg=st["pg"], seed=3)
+    G, n = st["Y"].shape
+    assert r["impt"].shape == (G, n) and r["EF"].shape == (n, K0) and r["consensus_cluster"].shape == (n, n)
+    obs = st["Y0"] > 0.1
+    assert np.allclose(r["impt"][obs], st["Y0"][obs], rtol=1e-12)       # observed entries are never touched
+    assert np.all(r["impt_var"][~obs] >= -1e-12) and np.all(np.abs(r["impt_var"][obs]) < 1e-9)
+    assert np.allclose(np.diag(r["consensus_cluster"]), [np.mean(1.0)] * n, atol=1.0)
+
+
+def test_golden_fixture_regression():
+    """Committed oracle-generated fixture (tests/golden/make_golden.py).  Regression pin only."""
+    g = np.load(os.path.join(GOLD, "em_small.npz"))
+    K0, M0 = int(g["K0"]), int(g["M0"])
+    out = O.em_impute_fast(g["Y"], g["Y0"], g["pg"], M0, K0, 0.1, int(g["iter"]), g["beta"], g["sigma"], g["lam"],
+                           g["pi"], g["z"], celltype=g["celltype"], impt_it=1, est_z=1, est_lam=1, seed=int(g["seed"]))
+    for k in ("loglik", "pi", "mu", "sigma", "beta", "lambda", "z", "Y"):
+        assert rel(out[k], g["out_" + k]) <= 1e-9, k
