@@ -248,6 +248,10 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.Q, size_t(c->NS_max) * ldG * d.QS));
     CKR(c->dalloc(&s.isg, size_t(c->NS_max) * ldG));
     CKR(c->dalloc(&s.Qs, size_t(ldG) * d.FS));
+    CKR(c->dalloc(&s.sdsA, size_t(ldG) * M0));
+    CKR(c->dalloc(&s.isdA, size_t(ldG) * M0));
+    CKR(c->dalloc(&s.igs, size_t(ldG)));
+    s.n_alloc = c->n_alloc;
     CKR(c->dalloc(&s.P, size_t(c->NS_max) * na * d.NQP));
     CKR(c->dalloc(&s.S2, size_t(c->NS_max) * na));
     CKR(c->dalloc(&s.V, na * d.VS));
@@ -282,7 +286,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     for (size_t c0 = 0; c0 < size_t(n); c0 += cells_per_chunk) {
         const size_t nc = std::min(cells_per_chunk, size_t(n) - c0);
         CK(cudaMemcpyAsync(c->stage, Y0 + c0 * G, nc * G * 8, cudaMemcpyHostToDevice, c->stream));
-        launch_build_mask(c->stage, s.mask + c0 * nwords, int(nc), G, ldG, cutoff, c->d_nnz, c->stream);
+        launch_build_mask(c->stage, s.mask, int(nc), int(c0), c->n_alloc, G, ldG, cutoff, c->d_nnz, c->stream);
     }
     {
         std::vector<double> hb = to_rowmajor(beta, G, K0, ldG, 0.0);
@@ -375,7 +379,7 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
 int run_prep(simples_ctx* c) {
     DevState& s = c->s;
     P p(c, KC_PREP, 2);
-    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.cc, 0};
+    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.igs, s.cc, 0};
     launch_prep(pa, c->stream);
     CK(cudaGetLastError());
     return SIMPLES_OK;
@@ -390,10 +394,12 @@ int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2) {
     sa.mask = s.mask;
     sa.Qs = s.Qs;
     sa.Fh = s.Fh;
-    sa.sigma = s.sigma;
+    sa.sdsA = s.sdsA;
+    sa.isdA = s.isdA;
     sa.pg = s.pg;
     sa.gmean = s.gmean;
-    sa.gsd = s.gsd;
+    sa.igs = s.igs;
+    sa.n_alloc = s.n_alloc;
     sa.im = s.im;
     sa.celltype0 = s.celltype0;
     sa.cutoff = c->cutoff;
@@ -878,13 +884,13 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     }
     if (o->impt)
         CKR(fetch_big(c, o->impt, [&](double* dst, size_t c0, size_t nc) {
-            launch_mi_finalize(s.Y + c0 * ldG, s.mask + c0 * (ldG / 32), c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean,
-                               s.gsd, dst, nullptr, int(nc), G, ldG, a->mcmc, c->stream);
+            launch_mi_finalize(s.Y + c0 * ldG, s.mask, c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean, s.gsd, dst, nullptr,
+                               int(nc), int(c0), c->n_alloc, G, ldG, a->mcmc, c->stream);
         }));
     if (o->impt_var)
         CKR(fetch_big(c, o->impt_var, [&](double* dst, size_t c0, size_t nc) {
-            launch_mi_finalize(s.Y + c0 * ldG, s.mask + c0 * (ldG / 32), c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean,
-                               s.gsd, nullptr, dst, int(nc), G, ldG, a->mcmc, c->stream);
+            launch_mi_finalize(s.Y + c0 * ldG, s.mask, c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean, s.gsd, nullptr, dst,
+                               int(nc), int(c0), c->n_alloc, G, ldG, a->mcmc, c->stream);
         }));
     if (o->EF || o->varF) {
         std::vector<double> ef(size_t(n) * K0), f2(size_t(n) * K0), vf(size_t(n) * K0);

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(CW * 32) k_cell(CellArgs a) {
         if (a.sample) {
             double ua, ub;
             cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + i), unsigned(1 + lane) >> 1, ua, ub);
-            const double eps = kl ? normcdfinv(((1 + lane) & 1) ? ub : ua) : 0.0;
+            const double eps = kl ? qnorm(((1 + lane) & 1) ? ub : ua) : 0.0;
             const double* Mh = a.cc.Mh + size_t(im) * K0 * K0;
             double f = wsel;
             for (int j = 0; j < K0; ++j) {

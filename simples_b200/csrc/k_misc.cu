@@ -7,8 +7,8 @@
 namespace sb {
 namespace {
 
-__global__ void k_build_mask(const double* Y0, uint32_t* mask, int ncell, int G, int ldG, double cutoff,
-                             unsigned long long* nnz) {
+__global__ void k_build_mask(const double* Y0, uint32_t* mask, int ncell, int cell0, int n_alloc, int G, int ldG,
+                             double cutoff, unsigned long long* nnz) {
     const int nwords = ldG / 32;
     const int lane = threadIdx.x & 31;
     const long long nw = (long long)ncell * nwords;
@@ -20,7 +20,7 @@ __global__ void k_build_mask(const double* Y0, uint32_t* mask, int ncell, int G,
         const bool bit = (g < G) && (Y0[size_t(cell) * G + g] <= cutoff);
         const unsigned b = __ballot_sync(0xffffffffu, bit);
         if (lane == 0) {
-            mask[size_t(cell) * nwords + word] = b;
+            mask[size_t(word) * n_alloc + cell0 + cell] = b;
             cnt += __popc(b);
         }
     }
@@ -88,15 +88,14 @@ __global__ void k_uncenter(const double* Y, double* out, const double* gmean, co
 }
 
 __global__ void k_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2,
-                              const double* gmean, const double* gsd, double* impt, double* impt_var, int n, int G, int ldG,
-                              int mcmc) {
+                              const double* gmean, const double* gsd, double* impt, double* impt_var, int n, int cell0,
+                              int n_alloc, int G, int ldG, int mcmc) {
     const size_t total = size_t(n) * G;
-    const int nwords = ldG / 32;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const size_t c = i / G;
         const int g = int(i - c * G);
         const size_t o = c * ldG + g;
-        const bool zero = (mask[c * nwords + (g >> 5)] >> (g & 31)) & 1u;
+        const bool zero = (mask[size_t(g >> 5) * n_alloc + cell0 + c] >> (g & 31)) & 1u;
         double m1, v;
         if (zero) {
             m1 = rec1[o] / mcmc;
@@ -148,9 +147,9 @@ inline int gs_grid(size_t total) {
 
 }  // namespace
 
-void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int G, int ldG, double cutoff,
-                       unsigned long long* nnz, cudaStream_t st) {
-    k_build_mask<<<gs_grid(size_t(ncell) * ldG), 256, 0, st>>>(Y0chunk, mask, ncell, G, ldG, cutoff, nnz);
+void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int cell0, int n_alloc, int G, int ldG,
+                       double cutoff, unsigned long long* nnz, cudaStream_t st) {
+    k_build_mask<<<gs_grid(size_t(ncell) * ldG), 256, 0, st>>>(Y0chunk, mask, ncell, cell0, n_alloc, G, ldG, cutoff, nnz);
 }
 void launch_clip(double* Y, int n, int G, int ldG, double lower, double upper, cudaStream_t st) {
     k_clip<<<gs_grid(size_t(n) * ldG), 256, 0, st>>>(Y, n, G, ldG, lower, upper);
@@ -174,8 +173,10 @@ void launch_uncenter(const double* Y, double* out, const double* gmean, const do
     k_uncenter<<<gs_grid(size_t(n) * G), 256, 0, st>>>(Y, out, gmean, gsd, n, G, ldG);
 }
 void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2, const double* gmean,
-                        const double* gsd, double* impt, double* impt_var, int n, int G, int ldG, int mcmc, cudaStream_t st) {
-    k_mi_finalize<<<gs_grid(size_t(n) * G), 256, 0, st>>>(Y, mask, rec1, rec2, gmean, gsd, impt, impt_var, n, G, ldG, mcmc);
+                        const double* gsd, double* impt, double* impt_var, int n, int cell0, int n_alloc, int G, int ldG,
+                        int mcmc, cudaStream_t st) {
+    k_mi_finalize<<<gs_grid(size_t(n) * G), 256, 0, st>>>(Y, mask, rec1, rec2, gmean, gsd, impt, impt_var, n, cell0, n_alloc, G,
+                                                          ldG, mcmc);
 }
 void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
                               double* rVF, cudaStream_t st) {

@@ -23,6 +23,12 @@ __global__ void k_build_ops(PrepArgs a) {
         for (int m = 0; m < M0; ++m) q[K0 + m] = a.mu[size_t(g) * M0 + m] * inv;
         for (int c = K0 + M0; c < d.QS; ++c) q[c] = 0.0;
     }
+    for (int m = 0; m < M0; ++m) {
+        const double sdv = sqrt(a.sigma[size_t(g) * M0 + m]) * sd;
+        a.sdsA[size_t(g) * M0 + m] = sdv;
+        a.isdA[size_t(g) * M0 + m] = 1.0 / sdv;
+    }
+    a.igs[g] = 1.0 / sd;
     double* qs = a.Qs + size_t(g) * d.FS;
     for (int k = 0; k < K0; ++k) qs[k] = a.beta[size_t(g) * K0 + k] * sd;
     for (int m = 0; m < M0; ++m) qs[K0 + m] = a.mu[size_t(g) * M0 + m] * sd;

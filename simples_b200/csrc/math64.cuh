@@ -1,0 +1,132 @@
+// FP64 special functions tuned for the sampling kernels: coefficient tables live in __constant__
+// memory (so DFMA takes them through LDC/LDCU instead of two UMOV per 64-bit immediate) and the
+// divisions are a float-seeded Newton reciprocal.  Accuracy ~1e-15 relative (checked against SciPy in
+// tests/test_oracle.py::test_device_math_restatement), i.e. the same mathematical functions the
+// oracle evaluates with scipy.special.ndtr / ndtri.
+//   pnorm : Cody (1969) rational Chebyshev erfc, the algorithm of R's pnorm_both (stats::pnorm,
+//           called at R/EM_impute.R:179)
+//   qnorm : Wichura (1988) AS241 PPND16, the algorithm of R's qnorm5 (used by rnorm's inversion,
+//           R/EM_impute.R:186)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sb {
+
+static __constant__ double kQA[8] = {3.3871328727963666080,    1.3314166789178437745e+2, 1.9715909503065514427e+3,
+                                     1.3731693765509461125e+4, 4.5921953931549871457e+4, 6.7265770927008700853e+4,
+                                     3.3430575583588128105e+4, 2.5090809287301226727e+3};
+static __constant__ double kQB[8] = {1.0,                      4.2313330701600911252e+1, 6.8718700749205790830e+2,
+                                     5.3941960214247511077e+3, 2.1213794301586595867e+4, 3.9307895800092710610e+4,
+                                     2.8729085735721942674e+4, 5.2264952788528545610e+3};
+static __constant__ double kQC[8] = {1.42343711074968357734,    4.63033784615654529590,    5.76949722146069140550,
+                                     3.64784832476320460504,    1.27045825245236838258,    2.41780725177450611770e-1,
+                                     2.27238449892691845833e-2, 7.74545014278341407640e-4};
+static __constant__ double kQD[8] = {1.0,                       2.05319162663775882187,    1.67638483018380384940,
+                                     6.89767334985100004550e-1, 1.48103976427480074590e-1, 1.51986665636164571966e-2,
+                                     5.47593808499534494600e-4, 1.05075007164441684324e-9};
+static __constant__ double kQE[8] = {6.65790464350110377720,    5.46378491116411436990,    1.78482653991729133580,
+                                     2.96560571828504891230e-1, 2.65321895265761230930e-2, 1.24266094738807843860e-3,
+                                     2.71155556874348757815e-5, 2.01033439929228813265e-7};
+static __constant__ double kQF[8] = {1.0,                       5.99832206555887937690e-1, 1.36929880922735805310e-1,
+                                     1.48753612908506148525e-2, 7.86869131145613259100e-4, 1.84631831751005468180e-5,
+                                     1.42151175831644588870e-7, 2.04426310338993978564e-15};
+
+static __constant__ double kPA[5] = {2.2352520354606839287, 161.02823106855587881, 1067.6894854603709582,
+                                     18154.981253343561249, 0.065682337918207449113};
+static __constant__ double kPB[4] = {47.20258190468824187, 976.09855173777669322, 10260.932208618978205,
+                                     45507.789335026729956};
+static __constant__ double kPC[9] = {0.39894151208813466764, 8.8831497943883759412, 93.506656132177855979,
+                                     597.27027639480026226,  2494.5375852903726711, 6848.1904505362823326,
+                                     11602.651437647350124,  9842.7148383839780218, 1.0765576773720192317e-8};
+static __constant__ double kPD[8] = {22.266688044328115691, 235.38790178262499861, 1519.377599407554805,
+                                     6485.558298266760755,  18615.571640885098091, 34900.952721145977266,
+                                     38912.003286093271411, 19685.429676859990727};
+static __constant__ double kPP[6] = {0.21589853405795699,    0.1274011611602473639, 0.022235277870649807,
+                                     0.001421619193227893466, 2.9112874951168792e-5, 0.02307344176494017303};
+static __constant__ double kPQ[5] = {1.28426009614491121, 0.468238212480865118, 0.0659881378689285515,
+                                     0.00378239633202758244, 7.29751555083966205e-5};
+
+// 1/y for y within float range; two Newton steps from a float seed (~1 ulp).
+__device__ __forceinline__ double fast_rcp(double y) {
+    double r = static_cast<double>(__frcp_rn(static_cast<float>(y)));
+    double e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// exp(-y^2/2) with the rounding error of y*y compensated
+__device__ __forceinline__ double exp_mhalfsq(double y) {
+    const double h = -0.5 * y * y;
+    const double l = fma(-0.5 * y, y, -h);
+    const double e = exp(h);
+    return fma(e, l, e);
+}
+
+// Phi(x), full relative accuracy in the lower tail
+__device__ __forceinline__ double pnorm(double x) {
+    const double y = fabs(x);
+    if (y <= 0.67448975) {
+        const double xs = x * x;
+        double xn = kPA[4] * xs, xd = xs;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            xn = (xn + kPA[i]) * xs;
+            xd = (xd + kPB[i]) * xs;
+        }
+        return fma(x * (xn + kPA[3]), fast_rcp(xd + kPB[3]), 0.5);
+    }
+    double lo;
+    if (y <= 5.656854249492380195206754896838) {   // sqrt(32)
+        double xn = kPC[8] * y, xd = y;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            xn = (xn + kPC[i]) * y;
+            xd = (xd + kPD[i]) * y;
+        }
+        lo = exp_mhalfsq(y) * ((xn + kPC[7]) * fast_rcp(xd + kPD[7]));
+    } else {
+        const double xs = 1.0 / (x * x);
+        double xn = kPP[5] * xs, xd = xs;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xn = (xn + kPP[i]) * xs;
+            xd = (xd + kPQ[i]) * xs;
+        }
+        double t = xs * (xn + kPP[4]) / (xd + kPQ[4]);
+        t = (0.398942280401432677939946059934 - t) / y;
+        lo = exp_mhalfsq(y) * t;
+    }
+    return x < 0.0 ? lo : 1.0 - lo;
+}
+
+template <int N>
+__device__ __forceinline__ double horner8(const double* c, double x) {
+    double r = c[N - 1];
+#pragma unroll
+    for (int i = N - 2; i >= 0; --i) r = fma(r, x, c[i]);
+    return r;
+}
+
+// Phi^-1(p), 0 < p < 1
+__device__ __forceinline__ double qnorm(double p) {
+    const double q = p - 0.5;
+    if (fabs(q) <= 0.425) {
+        const double r = 0.180625 - q * q;
+        return q * horner8<8>(kQA, r) * fast_rcp(horner8<8>(kQB, r));
+    }
+    const double pp = q < 0.0 ? p : 1.0 - p;
+    double r = sqrt(-log(pp));
+    double v;
+    if (r <= 5.0) {
+        r -= 1.6;
+        v = horner8<8>(kQC, r) * fast_rcp(horner8<8>(kQD, r));
+    } else {
+        r -= 5.0;
+        v = horner8<8>(kQE, r) * fast_rcp(horner8<8>(kQF, r));
+    }
+    return q < 0.0 ? -v : v;
+}
+
+}  // namespace sb

@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "math64.cuh"
+
 namespace sb {
 
 struct Philox4 {
@@ -32,9 +34,10 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 }
 
 // ((x >> 12) + 0.5) * 2^-52  in (0,1)
+// (== [1 + m 2^-52] - 1 + 2^-53 with m = x >> 12 the top 52 bits; every step is exact)
 __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
-    const uint64_t x = (static_cast<uint64_t>(hi) << 32) | lo;
-    return (static_cast<double>(x >> 12) + 0.5) * 2.220446049250313e-16;
+    const double one_m = __hiloint2double(0x3FF00000 | (hi >> 12), (hi << 20) | (lo >> 12));
+    return (one_m - 1.0) + 1.1102230246251565e-16;
 }
 
 // per-entry uniforms: tag 0, counter (gene, cell_lo, sweep, cell_hi << 8)
@@ -56,34 +59,38 @@ __device__ __forceinline__ void cell_uniform_pair(uint64_t seed, uint32_t sweep,
     u1 = u52(p.x2, p.x3);
 }
 
-// z <= r with Phi(z) = u * Phi(r); log-space Newton (erfcx form) for r < -30.
-__device__ __forceinline__ double trunc_z(double u, double r) {
-    double z;
-    if (r >= -30.0) {
-        z = normcdfinv(u * normcdf(r));
-    } else {
-        const double S2 = 1.4142135623730951, S2PI = 2.5066282746310002;
-        const double lu = log(u);
-        const double t = lu + log(0.5 * erfcx(-r / S2)) - 0.5 * r * r;
-        z = -sqrt(r * r - 2.0 * lu);
+// deep lower tail (r < -30): solve log Phi(z) = log u + log Phi(r) by Newton (erfcx form); never inlined
+static __device__ __noinline__ double trunc_z_deep(double u, double r) {
+    const double S2 = 1.4142135623730951, S2PI = 2.5066282746310002;
+    const double lu = log(u);
+    const double t = lu + log(0.5 * erfcx(-r / S2)) - 0.5 * r * r;
+    double z = -sqrt(r * r - 2.0 * lu);
 #pragma unroll 1
-        for (int it = 0; it < 4; ++it) {
-            const double e = 0.5 * erfcx(-z / S2);
-            z = z - (log(e) - 0.5 * z * z - t) * e * S2PI;
-        }
+    for (int it = 0; it < 4; ++it) {
+        const double e = 0.5 * erfcx(-z / S2);
+        z = z - (log(e) - 0.5 * z * z - t) * e * S2PI;
     }
     return fmin(z, r);
 }
 
-// One zero entry: R/EM_impute.R:175-198.  ms/sds already include gene_sd, gene_mean.
-__device__ __forceinline__ double sample_entry(double ms, double sds, double p, double cutoff, double ua, double ub) {
-    const double r = (cutoff - ms) / sds;
-    const double prob = normcdf(r);                              // pnorm(cutoff, ms, sds)
-    const double prob_drop = (1.0 - p) / (prob * p + (1.0 - p));
+// One zero entry: R/EM_impute.R:175-198.  ms/sds include gene_sd and gene_mean; isd = 1/sds.
+//   prob = pnorm(cutoff, ms, sds); prob_drop = (1-p)/(prob p + 1-p); I_drop ~ Bern(prob_drop)   (:179-181)
+//   dropout: N(ms, sds) (:186);  else TN(ms, sds; upper = cutoff) (:191-192), both by inverse CDF.
+// The Bernoulli test ua < prob_drop is evaluated as ua (prob p + 1-p) < 1-p (no division).
+__device__ __forceinline__ double sample_entry(double ms, double sds, double isd, double p, double cutoff, double ua,
+                                               double ub) {
+    const double r = (cutoff - ms) * isd;
+    const double prob = pnorm(r);
+    const double q1 = 1.0 - p;
+    const bool drop = ua * fma(prob, p, q1) < q1;
     double zz;
-    if (ua < prob_drop) zz = normcdfinv(ub);                     // dropout: N(ms, sds)
-    else zz = trunc_z(ub, r);                                    // expressed but <= cutoff: TN(upper = cutoff)
-    return ms + sds * zz;
+    if (!drop && r < -30.0) {
+        zz = trunc_z_deep(ub, r);
+    } else {
+        zz = qnorm(drop ? ub : ub * prob);
+        if (!drop) zz = fmin(zz, r);
+    }
+    return fma(sds, zz, ms);
 }
 
 }  // namespace sb

@@ -1,12 +1,13 @@
 // Device-resident state of one EM_impute / do_impute context and the launch
 // interface of every kernel.  Layouts (all FP64 unless noted):
 //   Y      [n][ldG]        cell-major, genes contiguous (== R's column-major G x n with padded ld)
-//   mask   [n][ldG/32]     u32 bitmask, bit g%32 of word g/32 set <=> Y0[g,i] <= cutoff
+//   mask   [ldG/32][n_alloc] u32 bitmask (chunk-major), bit g%32 of word [g/32][i] set <=> Y0[g,i] <= cutoff
 //   beta   [ldG][K0]   sigma/mu [ldG][M0]   pg [ldG][MB]   gmean/gsd [ldG]   (gene-major rows)
 //   lam    [M0][K0]   pi [M0]   z [n][M0]
 //   Q      [NS][ldG][QS]   projection operand  [B/sigma_s | mu_m/sigma_cs(m) | 0-pad]
 //   isg    [NS][ldG]       1/sigma_s
 //   Qs     [ldG][FS]       sweep operand       [B*sd | mu*sd | mean | 0-pad]
+//   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  igs [ldG] = 1/sd
 //   P      [NS][n][NQP]    Y^T Q          S2 [NS][n]   sum_g Y^2/sigma_s
 //   V      [n][VS]         M-step operand [Wbar (K0) | z (M0) | sqrt z (M0) | 0-pad],  zsum [n]
 //   Fh     [n][FS]         sweep operand  [f_i (K0) | onehot(m_i) (M0) | 1 | 0-pad]
@@ -62,7 +63,8 @@ struct DevState {
     double *Y, *beta, *sigma, *mu, *pg, *gmean, *gsd, *lam, *pi, *z;
     uint32_t* mask;
     int32_t* celltype0;
-    double *Q, *isg, *Qs, *P, *S2, *V, *zsum, *Fh, *W;
+    double *Q, *isg, *Qs, *sdsA, *isdA, *igs, *P, *S2, *V, *zsum, *Fh, *W;
+    int n_alloc;
     int32_t* im;
     ClusterConsts cc;
     double* Mm_snap;   // [M0][K0][K0] copy of Mm at the last E-pass (returned as Varf)
@@ -108,7 +110,8 @@ void launch_cell(const CellArgs& a, cudaStream_t st);
 
 struct SweepArgs {
     Dims d;
-    double* Y; const uint32_t* mask; const double *Qs, *Fh, *sigma, *pg, *gmean, *gsd;
+    double* Y; const uint32_t* mask; const double *Qs, *Fh, *sdsA, *isdA, *pg, *gmean, *igs;
+    int n_alloc;
     const int32_t *im, *celltype0;
     double cutoff, lower, upper;
     int clip;
@@ -142,7 +145,7 @@ void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out
 
 struct PrepArgs {
     Dims d; const double *beta, *sigma, *mu, *lam, *pi, *gmean, *gsd;
-    double *Q, *isg, *Qs; ClusterConsts cc; int stale_q;
+    double *Q, *isg, *Qs, *sdsA, *isdA, *igs; ClusterConsts cc; int stale_q;
 };
 void launch_prep(const PrepArgs& a, cudaStream_t st);
 
@@ -162,8 +165,8 @@ void launch_mstep(const MstepArgs& a, cudaStream_t st);
 int mstep_gene_ctas(int G);
 
 // misc
-void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int G, int ldG, double cutoff, unsigned long long* nnz,
-                       cudaStream_t st);
+void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int cell0, int n_alloc, int G, int ldG, double cutoff,
+                       unsigned long long* nnz, cudaStream_t st);
 void launch_clip(double* Y, int n, int G, int ldG, double lower, double upper, cudaStream_t st);
 void launch_rowsum(const double* Y, double* part, int n, int ldG, int nsplit, cudaStream_t st);
 void launch_center(double* Y, const double* gmean, const double* gsd, int n, int ldG, double scale_n, int mode, cudaStream_t st);
@@ -172,7 +175,8 @@ void launch_fill(double* p, size_t count, double v, cudaStream_t st);
 void launch_scale(double* p, size_t count, double s, cudaStream_t st);
 void launch_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG, cudaStream_t st);
 void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2, const double* gmean,
-                        const double* gsd, double* impt, double* impt_var, int n, int G, int ldG, int mcmc, cudaStream_t st);
+                        const double* gsd, double* impt, double* impt_var, int n, int cell0, int n_alloc, int G, int ldG, int mcmc,
+                        cudaStream_t st);
 void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
                               double* rVF, cudaStream_t st);
 void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t st);
