@@ -14,6 +14,7 @@
 
 #include "../../include/simples_b200.h"
 #include "state.h"
+#include "tmap.h"
 
 using namespace sb;
 
@@ -76,6 +77,7 @@ struct simples_ctx {
     int n_alloc = 0;
     int NS_max = 1;
     long long nnz0 = 0;
+    CUtensorMap tmapY;                // Y as [n_alloc][ldG], box {16 genes, 128 cells}, SWIZZLE_128B
     double* cellsum_main = nullptr;   // [2 M0 + 1] of the main E-pass of the current iteration
     double* stage = nullptr;          // staging buffer for chunked H2D / D2H
     size_t stage_elems = 0;
@@ -235,6 +237,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
 
     CKR(c->dalloc(&s.Y, na * ldG));
     CKR(c->dalloc(&s.mask, na * nwords));
+    CK(make_tmap_2d(&c->tmapY, s.Y, ldG, c->n_alloc, 16, 128));
     CKR(c->dalloc(&s.celltype0, na));
     CKR(c->dalloc(&s.beta, size_t(ldG) * K0));
     CKR(c->dalloc(&s.sigma, size_t(ldG) * M0));
@@ -261,12 +264,13 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.im, na));
     CKR(c->dalloc(&s.cc.Mm, size_t(M0) * K0 * K0));
     CKR(c->dalloc(&s.cc.Mh, size_t(M0) * K0 * K0));
+    CKR(c->dalloc(&s.cc.MmP, size_t(M0) * (4 * ((K0 + 3) / 4)) * (8 * ((K0 + 7) / 8) + 4)));
     CKR(c->dalloc(&s.cc.dt, size_t(M0)));
     CKR(c->dalloc(&s.cc.off, size_t(M0) * K0));
     CKR(c->dalloc(&s.cc.offq, size_t(M0) * K0));
     CKR(c->dalloc(&s.cc.cmu, size_t(M0)));
     CKR(c->dalloc(&s.cc.logpi, size_t(M0)));
-    s.ncta_cell = std::min((n + 7) / 8, NUM_SMS_B200 * 4);
+    s.ncta_cell = std::min((n + 63) / 64, NUM_SMS_B200 * 4);
     CKR(c->dalloc(&s.part_cell, size_t(s.ncta_cell) * (2 * M0 + 1)));
     CKR(c->dalloc(&c->cellsum_main, size_t(2 * M0 + 1)));
     CKR(c->dalloc(&c->d_nnz, 1));
@@ -343,7 +347,7 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
         P p(c, KC_PROJ);
         ProjArgs pa{s.Y, s.Q + size_t(sc) * d.ldG * d.QS, s.isg + size_t(sc) * d.ldG, s.P + size_t(sc) * d.n * d.NQP,
                     s.S2 + size_t(sc) * d.n, d.n, d.ldG, d.NQP, d.QS};
-        launch_proj(pa, c->stream);
+        launch_proj(pa, c->tmapY, c->stream);
     }
     {
         P p(c, KC_CELL);

@@ -1,8 +1,12 @@
 // cell_post: per-cell epilogue of an E-pass.  From the projections P = Y^T Q and S2 it forms the
-// Woodbury Mahalanobis distance, log-likelihoods, responsibilities z, log-lik total, factor posterior
-// means W_m = x2_m M_m (R/EM_impute.R:126-157), the M-step operand row V_i, and -- when an MC sweep
-// follows -- the cell-level draws of that sweep (membership + factor vector, R/EM_impute.R:163-171).
-// One warp per cell; lane k owns factor k, lane m owns cluster m.  Deterministic per-CTA partials.
+// Woodbury Mahalanobis distance, log-likelihoods, responsibilities z, the log-lik total, the factor
+// posterior means W_m = x2_m M_m (R/EM_impute.R:126-157), the M-step operand row V_i, and -- when an
+// MC sweep follows -- the cell-level draws of that sweep (membership + factor vector,
+// R/EM_impute.R:163-171).
+//
+// A warp owns 8 cells (one DMMA m-tile): T_m = X2_m M_m is a tiny FP64 DMMA product per cluster
+// (K0 x K0, padded to 4 x 8 granules), so the K0^2 M0 work per cell runs on the tensor path instead
+// of shuffle loops.  Deterministic per-CTA partial sums (nz, sum sqrt z, tot).
 #include "ptx.cuh"
 #include "rng.cuh"
 #include "state.h"
@@ -12,20 +16,48 @@ namespace {
 
 constexpr int CW = 8;   // warps per CTA
 
-__global__ void __launch_bounds__(CW * 32) k_cell(CellArgs a) {
+struct CellSmem {
+    double *Mp, *off, *offq, *cmu, *dt, *lp, *red;
+    double *Pa, *Pb, *ll, *zz, *ws, *eps;   // per-warp
+    int* im;
+};
+
+__global__ void __launch_bounds__(CW * 32) k_cell(CellArgs a, int mm_in_smem) {
     extern __shared__ __align__(16) double sm[];
     const int M0 = a.d.M0, K0 = a.d.K0, NS = a.d.NS, n = a.d.n, NQP = a.d.NQP;
-    double* sMm = sm;                        // [M0][K0][K0]
-    double* sOff = sMm + M0 * K0 * K0;       // [M0][K0]
-    double* sOffq = sOff + M0 * K0;          // [M0][K0]
-    double* sCmu = sOffq + M0 * K0;          // [M0]
-    double* sDt = sCmu + M0;                 // [M0]
-    double* sLp = sDt + M0;                  // [M0]
-    double* sRed = sLp + M0;                 // [CW][2*M0+1]
-    for (int i = threadIdx.x; i < M0 * K0 * K0; i += blockDim.x) sMm[i] = a.cc.Mm[i];
-    for (int i = threadIdx.x; i < M0 * K0; i += blockDim.x) {
-        sOff[i] = a.cc.off[i];
-        sOffq[i] = a.cc.offq[i];
+    const int KS = (K0 + 3) / 4, NT = (K0 + 7) / 8, KR = 4 * KS, KPS = 8 * NT + 4;   // padded M_m: [KR][KPS]
+    const int MMSZ = KR * KPS;
+    // ---- shared memory carve-up ----
+    double* p = sm;
+    const double* sMp;
+    if (mm_in_smem) {
+        for (int i = threadIdx.x; i < M0 * MMSZ; i += blockDim.x) p[i] = a.cc.MmP[i];
+        sMp = p;
+        p += M0 * MMSZ;
+    } else {
+        sMp = a.cc.MmP;
+    }
+    double* sOff = p;      p += M0 * KR;     // [M0][KR] (zero padded)
+    double* sOffq = p;     p += M0 * KR;
+    double* sCmu = p;      p += M0;
+    double* sDt = p;       p += M0;
+    double* sLp = p;       p += M0;
+    double* sRed = p;      p += CW * (2 * M0 + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int PWS = NQP + 4;
+    double* Pa = p + warp * (2 * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR);   // [8][PWS]  x2 source for the quadratic form
+    double* Pb = Pa + 8 * PWS;                                               // [8][PWS]  x2 source for W, mu column
+    double* llw = Pb + 8 * PWS;                                              // [8][M0]
+    double* zw = llw + 8 * M0;                                               // [8][M0]
+    double* wsw = zw + 8 * M0;                                               // [8][KPS]  W of the sampled cluster
+    double* epw = wsw + 8 * KPS;                                             // [8][KR]   factor normals
+    p += CW * (2 * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR);
+    int* imw = reinterpret_cast<int*>(p) + warp * 8;
+
+    for (int i = threadIdx.x; i < M0 * KR; i += blockDim.x) {
+        const int m = i / KR, k = i - m * KR;
+        sOff[i] = k < K0 ? a.cc.off[m * K0 + k] : 0.0;
+        sOffq[i] = k < K0 ? a.cc.offq[m * K0 + k] : 0.0;
     }
     for (int i = threadIdx.x; i < M0; i += blockDim.x) {
         sCmu[i] = a.cc.cmu[i];
@@ -34,116 +66,227 @@ __global__ void __launch_bounds__(CW * 32) k_cell(CellArgs a) {
     }
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool kl = lane < K0, ml = lane < M0;
+    const bool ml = lane < M0;
     double nz_acc = 0.0, c_acc = 0.0, tot_acc = 0.0;
     const size_t pstride = size_t(n) * NQP;
+    const int ngroups = (n + 7) / 8;
+    const int VGS = K0 * M0 + 2 * M0;
 
-    for (int i = blockIdx.x * CW + warp; i < n; i += gridDim.x * CW) {
-        const double* prow = a.P + size_t(i) * NQP;
-        double llv = -INFINITY;
+    for (int grp = blockIdx.x * CW + warp; grp < ngroups; grp += gridDim.x * CW) {
+        const int cell0 = grp * 8;
+        const int cell = cell0 + g;             // this lane's row
+        const bool rv = cell < n;
+        // ---- stage the P rows of the 8 cells (shared-sigma path: one tile serves everything) ----
+        if (NS == 1) {
+            for (int idx = lane; idx < 8 * NQP; idx += 32) {
+                const int r = idx / NQP, c = idx - r * NQP;
+                Pa[r * PWS + c] = (cell0 + r < n) ? a.P[size_t(cell0 + r) * NQP + c] : 0.0;
+            }
+        }
+        const double* PbT = (NS == 1) ? Pa : Pb;
+        __syncwarp();
+
         // ---- pass 1: log-likelihoods ----
         for (int m = 0; m < M0; ++m) {
             const int cs = (NS == 1) ? 0 : m;
             const int qs = a.stale_q ? NS - 1 : cs;
-            const double* off = a.stale_q ? sOffq : sOff;
-            const double x2 = kl ? prow[qs * pstride + lane] - off[m * K0 + lane] : 0.0;
-            double t = 0.0;
-            const double* Mm = sMm + m * K0 * K0;
-            for (int j = 0; j < K0; ++j) {
-                const double xj = __shfl_sync(0xffffffffu, x2, j);
-                if (kl) t = fma(xj, Mm[j * K0 + lane], t);
+            if (NS > 1) {
+                __syncwarp();
+                for (int idx = lane; idx < 8 * NQP; idx += 32) {
+                    const int r = idx / NQP, c = idx - r * NQP;
+                    const bool v = cell0 + r < n;
+                    Pa[r * PWS + c] = v ? a.P[qs * pstride + size_t(cell0 + r) * NQP + c] : 0.0;
+                    Pb[r * PWS + c] = v ? a.P[cs * pstride + size_t(cell0 + r) * NQP + c] : 0.0;
+                }
+                __syncwarp();
             }
-            const double qd = warp_sum(kl ? t * x2 : 0.0);
-            const double quad = a.S2[size_t(cs) * n + i] - 2.0 * prow[cs * pstride + K0 + m] + sCmu[m];
-            const double dt = a.stale_q ? sDt[M0 - 1] : sDt[m];
-            const double ll = (-(quad - qd) - dt - a.ll_const) / 2.0 + sLp[m];
-            if (lane == m) llv = ll;
-        }
-        const double mx = warp_max(llv);
-        const double lik = ml ? exp(llv - mx) : 0.0;
-        const double lsum = warp_sum(lik);
-        double zz;
-        if (a.update_z) {
-            zz = ml ? lik / lsum : 0.0;
-            if (ml) a.z[size_t(i) * M0 + lane] = zz;
-        } else {
-            zz = ml ? a.z[size_t(i) * M0 + lane] : 0.0;
-        }
-        const double zsq = sqrt(zz);
-        nz_acc += zz;
-        c_acc += zsq;
-        tot_acc += log(lsum) + mx;
-
-        // ---- membership draw for the coming sweep ----
-        int im = 0;
-        if (a.sample && a.draw_membership) {
-            double u0, u1;
-            cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + i), 0u, u0, u1);
-            double cum = 0.0;
-            for (int m = 0; m < M0; ++m) {
-                cum += __shfl_sync(0xffffffffu, zz, m);
-                im += (u0 >= cum) ? 1 : 0;
+            const double* off = (a.stale_q ? sOffq : sOff) + m * KR;
+            const double* Mp = sMp + m * MMSZ;
+            double qd = 0.0;
+            for (int nt = 0; nt < NT; ++nt) {
+                double c0 = 0.0, c1 = 0.0;
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int k = 4 * ks + t;
+                    const double av = (k < K0) ? Pa[g * PWS + k] - off[k] : 0.0;
+                    dmma(c0, c1, av, Mp[k * KPS + nt * 8 + g]);
+                }
+                const int k0 = nt * 8 + 2 * t;
+                const double x0 = (k0 < K0) ? Pa[g * PWS + k0] - off[k0] : 0.0;
+                const double x1 = (k0 + 1 < K0) ? Pa[g * PWS + k0 + 1] - off[k0 + 1] : 0.0;
+                qd = fma(c0, x0, fma(c1, x1, qd));
             }
-            im = min(im, M0 - 1);
+            qd += __shfl_xor_sync(0xffffffffu, qd, 1);
+            qd += __shfl_xor_sync(0xffffffffu, qd, 2);
+            if (t == 0) {
+                const double s2 = rv ? a.S2[size_t(cs) * n + cell] : 0.0;
+                const double quad = s2 - 2.0 * PbT[g * PWS + K0 + m] + sCmu[m];
+                const double dt = a.stale_q ? sDt[M0 - 1] : sDt[m];
+                llw[g * M0 + m] = (-(quad - qd) - dt - a.ll_const) / 2.0 + sLp[m];
+            }
+        }
+        __syncwarp();
+
+        // ---- responsibilities: lane (g, t) covers clusters t, t+4, ... of cell g ----
+        double mx = -INFINITY;
+        for (int m = t; m < M0; m += 4) mx = fmax(mx, llw[g * M0 + m]);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        double ls = 0.0;
+        for (int m = t; m < M0; m += 4) {
+            const double e = exp(llw[g * M0 + m] - mx);
+            zw[g * M0 + m] = e;
+            ls += e;
+        }
+        // sum over the 4 lanes of the row in ascending-cluster order is not required for parity (1e-16)
+        ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+        ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+        for (int m = t; m < M0; m += 4) {
+            double z;
+            if (a.update_z) {
+                z = zw[g * M0 + m] / ls;
+                if (rv) a.z[size_t(cell) * M0 + m] = z;
+            } else {
+                z = rv ? a.z[size_t(cell) * M0 + m] : 0.0;
+            }
+            zw[g * M0 + m] = rv ? z : 0.0;
+        }
+        if (t == 0 && rv) tot_acc += log(ls) + mx;
+        __syncwarp();
+        if (ml) {
+            double s = 0.0, c = 0.0;
+            for (int r = 0; r < 8; ++r) {
+                const double z = zw[r * M0 + lane];
+                s += z;
+                c += sqrt(z);
+            }
+            nz_acc += s;
+            c_acc += c;
         }
 
-        // ---- pass 2: factor posterior means ----
-        double wbar = 0.0, wsel = 0.0;
+        // ---- membership draw for the coming sweep (lanes 0..7: one cell each) ----
+        if (a.sample) {
+            if (lane < 8) {
+                int im = 0;
+                if (a.draw_membership) {
+                    double u0, u1;
+                    cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + cell0 + lane), 0u, u0, u1);
+                    double cum = 0.0;
+                    for (int m = 0; m < M0; ++m) {
+                        cum += zw[lane * M0 + m];
+                        im += (u0 >= cum) ? 1 : 0;
+                    }
+                    im = min(im, M0 - 1);
+                }
+                imw[lane] = im;
+                if (cell0 + lane < n) a.im[cell0 + lane] = im;
+            }
+            __syncwarp();
+        }
+        const int im_g = a.sample ? imw[g] : -1;
+
+        // ---- pass 2: factor posterior means W_m = x2_m M_m, Wbar = sum_m z_m W_m ----
+        double wb[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) wb[nt][0] = wb[nt][1] = 0.0;
         for (int m = 0; m < M0; ++m) {
             const int cs = (NS == 1) ? 0 : m;
-            const double xc = kl ? prow[cs * pstride + lane] - sOff[m * K0 + lane] : 0.0;
-            double w = 0.0;
-            const double* Mm = sMm + m * K0 * K0;
-            for (int j = 0; j < K0; ++j) {
-                const double xj = __shfl_sync(0xffffffffu, xc, j);
-                if (kl) w = fma(xj, Mm[j * K0 + lane], w);
+            if (NS > 1) {
+                __syncwarp();
+                for (int idx = lane; idx < 8 * NQP; idx += 32) {
+                    const int r = idx / NQP, c = idx - r * NQP;
+                    Pb[r * PWS + c] = (cell0 + r < n) ? a.P[cs * pstride + size_t(cell0 + r) * NQP + c] : 0.0;
+                }
+                __syncwarp();
             }
-            const double zm = __shfl_sync(0xffffffffu, zz, m);
-            wbar = fma(zm, w, wbar);
-            if (m == im) wsel = w;
-            if (kl) {
-                if (a.write_W) a.W[(size_t(m) * n + i) * K0 + lane] = w;
-                if (a.write_Vg) a.Vg[size_t(i) * (K0 * M0 + 2 * M0) + m * K0 + lane] = zm * w;
+            const double* off = sOff + m * KR;
+            const double* Mp = sMp + m * MMSZ;
+            const double zm = zw[g * M0 + m];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (nt < NT) {
+                    double c0 = 0.0, c1 = 0.0;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int k = 4 * ks + t;
+                        const double av = (k < K0) ? PbT[g * PWS + k] - off[k] : 0.0;
+                        dmma(c0, c1, av, Mp[k * KPS + nt * 8 + g]);
+                    }
+                    wb[nt][0] = fma(zm, c0, wb[nt][0]);
+                    wb[nt][1] = fma(zm, c1, wb[nt][1]);
+                    const int k0 = nt * 8 + 2 * t;
+                    if (m == im_g) {
+                        wsw[g * KPS + k0] = c0;
+                        wsw[g * KPS + k0 + 1] = c1;
+                    }
+                    if (rv) {
+                        if (a.write_W) {
+                            double* wr = a.W + (size_t(m) * n + cell) * K0;
+                            if (k0 < K0) wr[k0] = c0;
+                            if (k0 + 1 < K0) wr[k0 + 1] = c1;
+                        }
+                        if (a.write_Vg) {
+                            double* vg = a.Vg + size_t(cell) * VGS + m * K0;
+                            if (k0 < K0) vg[k0] = zm * c0;
+                            if (k0 + 1 < K0) vg[k0 + 1] = zm * c1;
+                        }
+                    }
+                }
             }
         }
         // ---- M-step operand row ----
-        double* vrow = a.V + size_t(i) * a.d.VS;
-        if (kl) vrow[lane] = wbar;
-        if (ml) {
-            vrow[K0 + lane] = zz;
-            vrow[K0 + M0 + lane] = zsq;
-            if (a.write_Vg) {
-                double* vg = a.Vg + size_t(i) * (K0 * M0 + 2 * M0) + K0 * M0;
-                vg[lane] = zz;
-                vg[M0 + lane] = zsq;
+        if (rv) {
+            double* vrow = a.V + size_t(cell) * a.d.VS;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int k0 = nt * 8 + 2 * t;
+                if (nt < NT) {
+                    if (k0 < K0) vrow[k0] = wb[nt][0];
+                    if (k0 + 1 < K0) vrow[k0 + 1] = wb[nt][1];
+                }
             }
+            double zs = 0.0;
+            for (int m = t; m < M0; m += 4) {
+                const double z = zw[g * M0 + m];
+                vrow[K0 + m] = z;
+                vrow[K0 + M0 + m] = sqrt(z);
+                if (a.write_Vg) {
+                    double* vg = a.Vg + size_t(cell) * VGS + K0 * M0;
+                    vg[m] = z;
+                    vg[M0 + m] = sqrt(z);
+                }
+            }
+            for (int m = 0; m < M0; ++m) zs += zw[g * M0 + m];
+            if (t == 0) a.zsum[cell] = zs;
         }
-        const double zs = warp_sum(zz);
-        if (lane == 0) a.zsum[i] = zs;
 
         // ---- factor draw: f = W_im[i,] + eps Mh_im  (symmetric sqrt, as mixtools::rmvnorm) ----
         if (a.sample) {
-            double ua, ub;
-            cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + i), unsigned(1 + lane) >> 1, ua, ub);
-            const double eps = kl ? qnorm(((1 + lane) & 1) ? ub : ua) : 0.0;
-            const double* Mh = a.cc.Mh + size_t(im) * K0 * K0;
-            double f = wsel;
-            for (int j = 0; j < K0; ++j) {
-                const double ej = __shfl_sync(0xffffffffu, eps, j);
-                if (kl) f = fma(ej, Mh[j * K0 + lane], f);
+            __syncwarp();
+            for (int id = lane; id < 8 * K0; id += 32) {
+                const int r = id / K0, k = id - r * K0;
+                double ua, ub;
+                cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + cell0 + r), unsigned(1 + k) >> 1, ua, ub);
+                epw[r * KR + k] = qnorm(((1 + k) & 1) ? ub : ua);
             }
-            double* frow = a.Fh + size_t(i) * a.d.FS;
-            if (kl) frow[lane] = f;
-            if (ml) frow[K0 + lane] = (lane == im) ? 1.0 : 0.0;
-            if (lane == 0) {
-                frow[K0 + M0] = 1.0;
-                a.im[i] = im;
+            __syncwarp();
+            for (int id = lane; id < 8 * K0; id += 32) {
+                const int r = id / K0, k = id - r * K0;
+                if (cell0 + r < n) {
+                    const double* Mh = a.cc.Mh + size_t(imw[r]) * K0 * K0;
+                    double f = wsw[r * KPS + k];
+                    for (int j = 0; j < K0; ++j) f = fma(epw[r * KR + j], Mh[j * K0 + k], f);
+                    a.Fh[size_t(cell0 + r) * a.d.FS + k] = f;
+                }
+            }
+            for (int id = lane; id < 8 * (M0 + 1); id += 32) {
+                const int r = id / (M0 + 1), m = id - r * (M0 + 1);
+                if (cell0 + r < n) a.Fh[size_t(cell0 + r) * a.d.FS + K0 + m] = (m == M0 || m == imw[r]) ? 1.0 : 0.0;
             }
         }
+        __syncwarp();
     }
 
     // ---- deterministic CTA reduction of (nz, c, tot) ----
+    tot_acc = warp_sum(tot_acc);
     const int R = 2 * M0 + 1;
     if (ml) {
         sRed[warp * R + lane] = nz_acc;
@@ -170,13 +313,19 @@ __global__ void k_finalize_cell(const double* part, int ncta, int R, double* out
 
 void launch_cell(const CellArgs& a, cudaStream_t st) {
     const int M0 = a.d.M0, K0 = a.d.K0;
-    const size_t smem = sizeof(double) * (size_t(M0) * K0 * K0 + 2 * M0 * K0 + 3 * M0 + CW * (2 * M0 + 1));
+    const int KS = (K0 + 3) / 4, NT = (K0 + 7) / 8, KR = 4 * KS, KPS = 8 * NT + 4, PWS = a.d.NQP + 4;
+    const size_t fixed = sizeof(double) * (size_t(2) * M0 * KR + 3 * M0 + CW * (2 * M0 + 1) +
+                                           size_t(CW) * (2 * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR)) +
+                         sizeof(int) * CW * 8;
+    const size_t mm = sizeof(double) * size_t(M0) * KR * KPS;
+    const int mm_in_smem = (fixed + mm <= 160 * 1024) ? 1 : 0;
+    const size_t smem = fixed + (mm_in_smem ? mm : 0);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         cudaFuncSetAttribute(k_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr = smem;
     }
-    k_cell<<<a.ncta, CW * 32, smem, st>>>(a);
+    k_cell<<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem);
 }
 
 void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out, cudaStream_t st) {

@@ -133,6 +133,13 @@ __global__ void __launch_bounds__(256) k_cluster(PrepArgs a) {
             a.cc.Mm[size_t(m) * K0 * K0 + e] = sM[e];
             sA[e] = sM[e];
         }
+        {
+            const int KR = 4 * ((K0 + 3) / 4), KPS = 8 * ((K0 + 7) / 8) + 4;
+            for (int e = lane; e < KR * KPS; e += 32) {
+                const int k = e / KPS, c = e - k * KPS;
+                a.cc.MmP[size_t(m) * KR * KPS + e] = (k < K0 && c < K0) ? sM[k * K0 + c] : 0.0;
+            }
+        }
         __syncwarp();
         warp_sym_sqrt(sA, sV, sLi, K0, lane);
         for (int e = lane; e < K0 * K0; e += 32) a.cc.Mh[size_t(m) * K0 * K0 + e] = sLi[e];

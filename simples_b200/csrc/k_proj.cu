@@ -1,34 +1,40 @@
 // estep_project: P = Y^T Q (n x NQP) and S2_i = sum_g Y_gi^2 / sigma_g, the skinny FP64 GEMM of
 // the E-pass (replaces the n*M0 R closures at R/EM_impute.R:126-136 and the Wm GEMM at :155-157;
-// SURVEY.md 3.3).  FP64 DMMA (mma.sync m8n8k4) fed by a bulk-async-copy (TMA engine) mbarrier ring.
+// SURVEY.md 3.3).  FP64 DMMA (mma.sync m8n8k4) fed by tensor-map TMA through an mbarrier ring.
 //
 // CTA = 8 consumer warps (16 cells each) + 1 producer warp; tile = 128 cells x all genes, streamed
-// in 32-gene chunks: stage = Y[128][32] (row stride 36 doubles => conflict-free fragment loads),
-// Q[32][QS], isg[32].  Persistent grid over cell tiles.
+// in 32-gene chunks.  Stage = two TMA boxes [128 cells][16 genes] (SWIZZLE_128B, 16 KB per
+// cp.async.bulk.tensor) + Q[32][QS] + isg[32].  The m-tile row -> cell map rho(g) = 2(g&3) + (g>>2)
+// makes every DMMA A-fragment load hit 32 distinct banks under the 128B swizzle.
+// (A ring of 256-byte 1-D bulk copies was TMA-issue bound at ~1 TB/s: profiles/r01_notes.md.)
 #include "ptx.cuh"
 #include "state.h"
+#include "tmap.h"
 
 namespace sb {
 
 namespace {
 constexpr int TC = 128;     // cells per tile
 constexpr int GC = 32;      // genes per chunk
-constexpr int YS = 36;      // smem row stride of the Y tile (== 4 mod 16)
 constexpr int NCW = 8;      // consumer warps
 constexpr int THREADS = (NCW + 1) * 32;
+constexpr int YBOX = TC * 16;   // doubles per TMA box
 
 __host__ __device__ constexpr size_t stage_bytes(int QS) {
-    return size_t(TC) * YS * 8 + size_t(GC) * QS * 8 + GC * 8;
+    return size_t(2) * YBOX * 8 + size_t(GC) * QS * 8 + GC * 8 + 768;   // keep every stage 1024-B aligned
 }
+static_assert((2 * YBOX * 8) % 1024 == 0, "box alignment");
 
 template <int NT>
-__global__ void __launch_bounds__(THREADS, 1) k_proj(ProjArgs a, int stages, int ntiles) {
+__global__ void __launch_bounds__(THREADS, 1) k_proj(const __grid_constant__ CUtensorMap tmapY, ProjArgs a, int stages,
+                                                     int ntiles) {
     constexpr int QS = NT * 8 + 4;
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    constexpr size_t SB = (stage_bytes(QS) + 1023) / 1024 * 1024;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // TMA swizzle needs 1024-B alignment
+    unsigned char* stage0 = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(stages) * SB);
     uint64_t* empty = full + 8;
-    unsigned char* stage0 = smem + 128;
-    const size_t SB = stage_bytes(QS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -37,38 +43,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(ProjArgs a, int stages, int
             mbar_init(&empty[s], NCW);
         }
         mbar_fence_init();
+        tma_prefetch_desc(&tmapY);
     }
     __syncthreads();
 
     const int nchunks = a.ldG / GC;
 
     if (warp == NCW) {
-        // ---------------- producer ----------------
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int cell0 = tile * TC;
-            const int rows = min(TC, a.n - cell0);
-            for (int c = 0; c < nchunks; ++c) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                unsigned char* sp = stage0 + stage * SB;
-                double* Ys = reinterpret_cast<double*>(sp);
-                double* Qc = Ys + TC * YS;
-                double* Ic = Qc + GC * QS;
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[stage], uint32_t(rows) * GC * 8 + GC * QS * 8 + GC * 8);
+        // ---------------- producer (one elected lane) ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int cell0 = tile * TC;
+                for (int c = 0; c < nchunks; ++c) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sp = stage0 + stage * SB;
+                    double* Ys = reinterpret_cast<double*>(sp);
+                    double* Qc = Ys + 2 * YBOX;
+                    double* Ic = Qc + GC * QS;
+                    mbar_arrive_expect_tx(&full[stage], 2 * YBOX * 8 + GC * QS * 8 + GC * 8);
+                    tma_load_2d(Ys, &tmapY, c * GC, cell0, &full[stage]);
+                    tma_load_2d(Ys + YBOX, &tmapY, c * GC + 16, cell0, &full[stage]);
                     bulk_g2s(Qc, a.Q + size_t(c) * GC * QS, GC * QS * 8, &full[stage]);
                     bulk_g2s(Ic, a.isg + size_t(c) * GC, GC * 8, &full[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                for (int r = lane; r < rows; r += 32)
-                    bulk_g2s(Ys + r * YS, a.Y + size_t(cell0 + r) * a.ldG + size_t(c) * GC, GC * 8, &full[stage]);
-                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
         // ---------------- consumers ----------------
         const int g = lane >> 2, t = lane & 3;
+        const int rho = 2 * (g & 3) + (g >> 2);          // row -> cell permutation (bank-conflict-free under the swizzle)
+        const int r0 = warp * 16 + rho;                  // m-tile 0 row; m-tile 1 = r0 + 8
+        // swizzled offsets of (row r0, gene 4*kk + t), kk = 0..3, inside a box
+        int off[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) off[kk] = swz16(r0, 4 * kk + t);
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -84,18 +95,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(ProjArgs a, int stages, int
                 mbar_wait(&full[stage], phase);
                 const unsigned char* sp = stage0 + stage * SB;
                 const double* Ys = reinterpret_cast<const double*>(sp);
-                const double* Qc = Ys + TC * YS;
+                const double* Qc = Ys + 2 * YBOX;
                 const double* Ic = Qc + GC * QS;
-                const double* ya = Ys + (warp * 16 + g) * YS + t;
 #pragma unroll
                 for (int ks = 0; ks < GC / 4; ++ks) {
                     double b[NT];
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) b[nt] = Qc[(ks * 4 + t) * QS + nt * 8 + g];
                     const double w = Ic[ks * 4 + t];
+                    const double* yb = Ys + (ks >> 2) * YBOX + off[ks & 3];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        const double av = ya[mt * 8 * YS + ks * 4];
+                        const double av = yb[mt * 8 * 16];     // row + 8: same (row & 7) => same swizzle
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], av, b[nt]);
                         s2[mt] = fma(av * av, w, s2[mt]);
@@ -105,10 +116,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(ProjArgs a, int stages, int
                 if (lane == 0) mbar_arrive(&empty[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            // epilogue: C[g][2t,2t+1] per (mt, nt)
+            // epilogue: C[row g][2t, 2t+1] per (mt, nt); row g of m-tile mt is cell cell0 + 16 warp + 8 mt + rho
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                const int cell = cell0 + warp * 16 + mt * 8 + g;
+                const int cell = cell0 + r0 + mt * 8;
                 double s = s2[mt];
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -125,12 +136,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(ProjArgs a, int stages, int
 }
 
 template <int NT>
-void launch_nt(const ProjArgs& a, cudaStream_t st) {
+void launch_nt(const ProjArgs& a, const CUtensorMap& tm, cudaStream_t st) {
     constexpr int QS = NT * 8 + 4;
-    const size_t SB = stage_bytes(QS);
-    int stages = int((227 * 1024 - 128) / SB);
-    if (stages > 4) stages = 4;
-    const size_t smem = 128 + stages * SB;
+    const size_t SB = (stage_bytes(QS) + 1023) / 1024 * 1024;
+    int stages = int((227 * 1024 - 256 - 1024) / SB);
+    if (stages > 5) stages = 5;
+    const size_t smem = stages * SB + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_proj<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -138,20 +149,20 @@ void launch_nt(const ProjArgs& a, cudaStream_t st) {
     }
     const int ntiles = (a.n + TC - 1) / TC;
     const int grid = ntiles < NUM_SMS_B200 ? ntiles : NUM_SMS_B200;
-    k_proj<NT><<<grid, THREADS, smem, st>>>(a, stages, ntiles);
+    k_proj<NT><<<grid, THREADS, smem, st>>>(tm, a, stages, ntiles);
 }
 }  // namespace
 
-void launch_proj(const ProjArgs& a, cudaStream_t st) {
+void launch_proj(const ProjArgs& a, const CUtensorMap& tmapY, cudaStream_t st) {
     switch (a.NQP / 8) {
-        case 1: launch_nt<1>(a, st); break;
-        case 2: launch_nt<2>(a, st); break;
-        case 3: launch_nt<3>(a, st); break;
-        case 4: launch_nt<4>(a, st); break;
-        case 5: launch_nt<5>(a, st); break;
-        case 6: launch_nt<6>(a, st); break;
-        case 7: launch_nt<7>(a, st); break;
-        case 8: launch_nt<8>(a, st); break;
+        case 1: launch_nt<1>(a, tmapY, st); break;
+        case 2: launch_nt<2>(a, tmapY, st); break;
+        case 3: launch_nt<3>(a, tmapY, st); break;
+        case 4: launch_nt<4>(a, tmapY, st); break;
+        case 5: launch_nt<5>(a, tmapY, st); break;
+        case 6: launch_nt<6>(a, tmapY, st); break;
+        case 7: launch_nt<7>(a, tmapY, st); break;
+        case 8: launch_nt<8>(a, tmapY, st); break;
         default: break;   // validated by the engine (K0 + M0 <= 64)
     }
 }

@@ -74,23 +74,15 @@ __device__ inline void warp_sym_sqrt(double* A, double* V, double* R, int K, int
     for (int e = lane; e < K * K; e += 32) V[e] = ((e / K) == (e % K)) ? 1.0 : 0.0;
     __syncwarp();
     for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0, dg = 0.0;
-        for (int e = lane; e < K * K; e += 32) {
-            const int i = e / K, j = e - i * K;
-            const double v = A[e];
-            if (i == j) dg += v * v; else off += v * v;
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            off += __shfl_xor_sync(0xffffffffu, off, o);
-            dg += __shfl_xor_sync(0xffffffffu, dg, o);
-        }
-        if (off <= 1e-32 * dg) break;
+        int nrot = 0;
         for (int p = 0; p < K - 1; ++p) {
             for (int q = p + 1; q < K; ++q) {
                 const double apq = A[p * K + q];
                 const double app = A[p * K + p], aqq = A[q * K + q];
                 __syncwarp();
-                if (fabs(apq) <= 1e-300) continue;
+                // converged pair: the rotation would not change the diagonal in double precision
+                if (fabs(apq) <= 4e-16 * sqrt(fabs(app * aqq)) || fabs(apq) <= 1e-300) continue;
+                ++nrot;
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
@@ -113,6 +105,7 @@ __device__ inline void warp_sym_sqrt(double* A, double* V, double* R, int K, int
                 __syncwarp();
             }
         }
+        if (nrot == 0) break;
     }
     __syncwarp();
     for (int e = lane; e < K * K; e += 32) {

@@ -51,6 +51,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 2-D tensor-map TMA load (SASS UTMALDG): box at coordinates (c0 = inner/gene, c1 = outer/cell).
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// 2-D tensor-map TMA store (SASS UTMASTG), bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// Index (in doubles) of element (row r, column j < 16) inside a [rows][16] FP64 box written by TMA with
+// SWIZZLE_128B: the 16-byte chunk index is XORed with (r mod 8).
+__device__ __forceinline__ int swz16(int r, int j) { return r * 16 + ((((j >> 1) ^ (r & 7)) << 1) | (j & 1)); }
+
 // 1-D bulk async copy shared -> global.
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),

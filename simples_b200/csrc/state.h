@@ -15,6 +15,7 @@
 // ldG = G rounded up to 64; padded genes have Y = 0, mask = 0, beta = mu = 0, sigma = 1.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace sb {
@@ -50,6 +51,7 @@ struct Dims {
 
 struct ClusterConsts {   // device pointers, produced by cluster_prep
     double* Mm;     // [M0][K0][K0]  (B' Sigma_m^-1 B + Lambda_m^-1)^-1
+    double* MmP;    // [M0][KR][KPS] zero-padded copy of Mm for DMMA B-fragments (KR = 4 ceil(K0/4), KPS = 8 ceil(K0/8) + 4)
     double* Mh;     // [M0][K0][K0]  symmetric square root of Mm
     double* dt;     // [M0]
     double* off;    // [M0][K0]   mu_m' (B / sigma_m)
@@ -90,7 +92,7 @@ struct ProjArgs {
     const double* Y; const double* Q; const double* isg; double* P; double* S2;
     int n, ldG, NQP, QS;
 };
-void launch_proj(const ProjArgs& a, cudaStream_t st);
+void launch_proj(const ProjArgs& a, const CUtensorMap& tmapY, cudaStream_t st);   // tmapY: box {16 genes, 128 cells}
 
 struct CellArgs {
     Dims d;
