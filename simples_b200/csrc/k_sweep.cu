@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
     double* sF = sm;                                 // [SC][FS]
     double* sMs = sF + SC * FS;                      // [SW][8][MSS]
     double* sBuf = sMs + SW * 8 * MSS;               // [2][CD]
-    unsigned char* sList = reinterpret_cast<unsigned char*>(sBuf + 2 * CD);   // [SW][256]
-    int* sCell = reinterpret_cast<int*>(sList + SW * 256);                    // [SW][8][2]  (im, celltype)
+    double* sDub = sBuf + 2 * CD;                    // [SW][256]  value uniforms of the certain-dropout lists
+    unsigned char* sList = reinterpret_cast<unsigned char*>(sDub + SW * 256);   // [SW][3][256]  all / D / X entry codes
+    int* sCell = reinterpret_cast<int*>(sList + SW * 768);                      // [SW][8][2]  (im, celltype)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cell0 = blockIdx.x * SC;
@@ -85,7 +86,10 @@ __global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
     load_chunk(a, chunk_buf(sBuf, FS, M0, MB), 0, tid, blockDim.x);
 
     double* msW = sMs + warp * 8 * MSS;
-    unsigned char* list = sList + warp * 256;
+    unsigned char* list = sList + warp * 768;
+    unsigned char* dcode = list + 256;
+    unsigned char* xcode = list + 512;
+    double* dub = sDub + warp * 256;
     const int* cellinfo = sCell + warp * 16;
     const double* fa = sF + (warp * 8 + g) * FS + t;
 
@@ -123,28 +127,89 @@ __global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
         }
         __syncwarp();
 
-        // ---- 3. sample ----
+        // ---- 3a. classify every zero entry with a cheap FP32 screen of the Bernoulli test ----
+        // Phi(r) ~ 0.5 + 0.5 tanh(sqrt(2/pi)(r + 0.044715 r^3)) (|err| < 5e-4 incl. MUFU.TANH); an entry whose
+        // test statistic clears the 1.5e-3 band is a CERTAIN dropout and never needs the FP64 pnorm.
+        // Lists: Dc = certain dropout & central quantile, Dt = certain dropout & tail quantile, X = exact path.
+        int nDc = 0, nDt = 0, nX = 0;
+        const int rounds = (total + 31) >> 5;
 #pragma unroll 1
-        for (int e = lane; e < total; e += 32) {
-            const int code = list[e];
+        for (int it = 0; it < rounds; ++it) {
+            const int e = it * 32 + lane;
+            const bool valid = e < total;
+            const int code = valid ? list[e] : 0;
             const int r = code >> 5, gl = code & 31;
-            const int cell = wc0 + r, gene = chunk * SG + gl;
             const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
             const double ms = msW[r * MSS + gl];
-            double ua, ub;
-            entry_uniforms(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + cell), (uint32_t)gene, ua, ub);
-            double x = sample_entry(ms, b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct], a.cutoff, ua, ub);
+            const double p = b.pg[gl * MB + ct];
+            const Philox4 px = entry_philox(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + wc0 + r),
+                                            (uint32_t)(chunk * SG + gl));
+            const double ub = u52(px.x2, px.x3);
+            const float rf = (float)((a.cutoff - ms) * b.isd[gl * M0 + im]);
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.7978845608f * fmaf(0.044715f * rf * rf, rf, rf)));
+            const float pf = fmaf(0.5f, th, 0.5f);
+            const float uaf = (float)(px.x0 >> 8) * 5.9604644775390625e-8f;
+            const float pfl = (float)p, q1f = 1.0f - pfl;
+            const float d = fmaf(uaf, fmaf(pf, pfl, q1f), -q1f);
+            const bool isD = valid && (d < -1.5e-3f);
+            const bool cen = fabs(ub - 0.5) <= 0.425;
+            const unsigned bDc = __ballot_sync(0xffffffffu, isD && cen);
+            const unsigned bDt = __ballot_sync(0xffffffffu, isD && !cen);
+            const unsigned bX = __ballot_sync(0xffffffffu, valid && !isD);
+            const unsigned lt = (1u << lane) - 1u;
+            if (isD) {
+                const int pos = cen ? nDc + __popc(bDc & lt) : 255 - (nDt + __popc(bDt & lt));
+                dcode[pos] = (unsigned char)code;
+                dub[pos] = ub;
+            } else if (valid) {
+                xcode[nX + __popc(bX & lt)] = (unsigned char)code;
+            }
+            nDc += __popc(bDc);
+            nDt += __popc(bDt);
+            nX += __popc(bX);
+        }
+        __syncwarp();
+
+        auto finish = [&](int r, int gl, double x) {
             if (a.clip) {
                 x = fmin(x, a.upper);
                 x = fmax(x, a.lower);
             }
             const double v = (x - b.gm[gl]) * b.igs[gl];
-            const size_t o = size_t(cell) * ldG + gene;
+            const size_t o = size_t(wc0 + r) * ldG + chunk * SG + gl;
             a.Y[o] = v;
             if (a.rec1) {
                 a.rec1[o] += v;
                 a.rec2[o] += v * v;
             }
+        };
+        // ---- 3b. certain dropouts, central quantile: x = ms + sds Phi^-1(ub)   (R/EM_impute.R:186) ----
+#pragma unroll 1
+        for (int e = lane; e < nDc; e += 32) {
+            const int code = dcode[e];
+            const int r = code >> 5, gl = code & 31;
+            const double z = qnorm_central(dub[e]);
+            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], z, msW[r * MSS + gl]));
+        }
+        // ---- 3c. certain dropouts, tail quantile ----
+#pragma unroll 1
+        for (int e = lane; e < nDt; e += 32) {
+            const int code = dcode[255 - e];
+            const int r = code >> 5, gl = code & 31;
+            const double z = qnorm_tail(dub[255 - e]);
+            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], z, msW[r * MSS + gl]));
+        }
+        // ---- 3d. exact path: FP64 pnorm, exact Bernoulli test, normal or truncated-normal draw ----
+#pragma unroll 1
+        for (int e = lane; e < nX; e += 32) {
+            const int code = xcode[e];
+            const int r = code >> 5, gl = code & 31;
+            const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
+            double ua, ub;
+            entry_uniforms(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + wc0 + r), (uint32_t)(chunk * SG + gl), ua, ub);
+            finish(r, gl, sample_entry(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct],
+                                       a.cutoff, ua, ub));
         }
         __syncwarp();
     }
@@ -154,7 +219,7 @@ __global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
 
 void launch_sweep(const SweepArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(double) * (size_t(SC) * a.d.FS + size_t(SW) * 8 * MSS + 2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
-                        SW * 256 + SW * 16 * sizeof(int);
+                        SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -40,6 +40,12 @@ __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
     return (one_m - 1.0) + 1.1102230246251565e-16;
 }
 
+// per-entry Philox block: tag 0, counter (gene, cell_lo, sweep, cell_hi << 8); (x0,x1) -> ua, (x2,x3) -> ub
+__device__ __forceinline__ Philox4 entry_philox(uint64_t seed, uint32_t sweep, uint64_t cell, uint32_t gene) {
+    return philox4x32_10(gene, static_cast<uint32_t>(cell), sweep, static_cast<uint32_t>(cell >> 32) << 8,
+                         static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+}
+
 // per-entry uniforms: tag 0, counter (gene, cell_lo, sweep, cell_hi << 8)
 __device__ __forceinline__ void entry_uniforms(uint64_t seed, uint32_t sweep, uint64_t cell, uint32_t gene, double& ua,
                                                double& ub) {
@@ -76,12 +82,16 @@ static __device__ __noinline__ double trunc_z_deep(double u, double r) {
 // One zero entry: R/EM_impute.R:175-198.  ms/sds include gene_sd and gene_mean; isd = 1/sds.
 //   prob = pnorm(cutoff, ms, sds); prob_drop = (1-p)/(prob p + 1-p); I_drop ~ Bern(prob_drop)   (:179-181)
 //   dropout: N(ms, sds) (:186);  else TN(ms, sds; upper = cutoff) (:191-192), both by inverse CDF.
-// The Bernoulli test ua < prob_drop is evaluated as ua (prob p + 1-p) < 1-p (no division).
-__device__ __forceinline__ double sample_entry(double ms, double sds, double isd, double p, double cutoff, double ua,
+// The Bernoulli test ua < prob_drop is evaluated as ua (prob p + 1-p) < 1-p (no division).  When the
+// cutoff is > 8 sd below the mean, prob < 6.3e-16 and the draw is a certain dropout unless ua is within
+// 1e-9 of 1 or p > 0.999 -- those cases take the exact (cold) path, so the decision is always exact.
+static __device__ __noinline__ double sample_entry(double ms, double sds, double isd, double p, double cutoff, double ua,
                                                double ub) {
     const double r = (cutoff - ms) * isd;
-    const double prob = pnorm(r);
     const double q1 = 1.0 - p;
+    double prob;
+    if (r < -8.0 && q1 >= 1e-3 && ua <= 0.999999999) prob = 0.0;
+    else prob = pnorm(r);
     const bool drop = ua * fma(prob, p, q1) < q1;
     double zz;
     if (!drop && r < -30.0) {
