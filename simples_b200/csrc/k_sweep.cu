@@ -58,15 +58,15 @@ __device__ __forceinline__ void load_chunk(const SweepArgs& a, const ChunkBuf& b
     cp_async_commit();
 }
 
-__global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
+__global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB, ldG = a.d.ldG, n = a.d.n;
     const int KST = a.d.NFP / 4;
     const int CD = chunk_doubles(FS, M0, MB);
     double* sF = sm;                                 // [SC][FS]
     double* sMs = sF + SC * FS;                      // [SW][8][MSS]
-    double* sBuf = sMs + SW * 8 * MSS;               // [2][CD]
-    double* sDub = sBuf + 2 * CD;                    // [SW][256]  value uniforms of the certain-dropout lists
+    double* sBuf = sMs + SW * 8 * MSS;               // [CD]  (single buffer: 3 CTAs / SM hide the refill)
+    double* sDub = sBuf + CD;                    // [SW][256]  value uniforms of the certain-dropout lists
     unsigned char* sList = reinterpret_cast<unsigned char*>(sDub + SW * 256);   // [SW][3][256]  all / D / X entry codes
     int* sCell = reinterpret_cast<int*>(sList + SW * 768);                      // [SW][8][2]  (im, celltype)
 
@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
         sCell[(warp * 8 + lane) * 2 + 1] = cell < n ? a.celltype0[cell] : 0;
     }
     const int nchunks = ldG / SG;
-    load_chunk(a, chunk_buf(sBuf, FS, M0, MB), 0, tid, blockDim.x);
 
     double* msW = sMs + warp * 8 * MSS;
     unsigned char* list = sList + warp * 768;
@@ -94,10 +93,11 @@ __global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
     const double* fa = sF + (warp * 8 + g) * FS + t;
 
     for (int chunk = 0; chunk < nchunks; ++chunk) {
+        __syncthreads();                               // every warp is done with the previous chunk's parameters
+        const ChunkBuf b = chunk_buf(sBuf, FS, M0, MB);
+        load_chunk(a, b, chunk, tid, blockDim.x);
         cp_async_wait_all();
-        __syncthreads();                               // chunk's parameters visible; other buffer free
-        if (chunk + 1 < nchunks) load_chunk(a, chunk_buf(sBuf + ((chunk + 1) & 1) * CD, FS, M0, MB), chunk + 1, tid, blockDim.x);
-        const ChunkBuf b = chunk_buf(sBuf + (chunk & 1) * CD, FS, M0, MB);
+        __syncthreads();                               // chunk's parameters visible
 
         // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes)
         unsigned word = 0u;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(SW * 32, 2) k_sweep(SweepArgs a) {
 }  // namespace
 
 void launch_sweep(const SweepArgs& a, cudaStream_t st) {
-    const size_t smem = sizeof(double) * (size_t(SC) * a.d.FS + size_t(SW) * 8 * MSS + 2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
+    const size_t smem = sizeof(double) * (size_t(SC) * a.d.FS + size_t(SW) * 8 * MSS + chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
                         SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
