@@ -196,3 +196,63 @@ def test_golden_fixture_regression():
                            g["pi"], g["z"], celltype=g["celltype"], impt_it=1, est_z=1, est_lam=1, seed=int(g["seed"]))
     for k in ("loglik", "pi", "mu", "sigma", "beta", "lambda", "z", "Y"):
         assert rel(out[k], g["out_" + k]) <= 1e-9, k
+
+
+def _device_tables():
+    """Parse the __constant__ coefficient tables out of csrc/math64.cuh (pins the constants the kernels use)."""
+    import re
+    src = open(os.path.join(os.path.dirname(GOLD), "..", "simples_b200", "csrc", "math64.cuh")).read()
+    out = {}
+    for name, body in re.findall(r"static __constant__ double (k\w+)\[\d+\] = \{([^}]*)\};", src):
+        out[name] = [float(x) for x in body.replace("\n", " ").split(",")]
+    return out
+
+
+def test_device_math_restatement():
+    """NumPy restatement of csrc/math64.cuh (Cody pnorm mid formula, AS241 qnorm, Taylor exp) with the
+    device's own coefficient tables vs scipy.special -- the functions the oracle uses."""
+    T = _device_tables()
+    assert set(T) >= {"kQA", "kQB", "kQC", "kQD", "kQE", "kQF", "kPC", "kPD", "kEX"}
+
+    def horner(c, x):
+        r = np.full_like(x, c[-1])
+        for v in c[-2::-1]:
+            r = r * x + v
+        return r
+
+    # qnorm
+    p = np.concatenate([np.linspace(1e-6, 1 - 1e-6, 100001), 10.0 ** -np.linspace(6, 300, 1000)])
+    q = p - 0.5
+    z = np.empty_like(p)
+    cen = np.abs(q) <= 0.425
+    r = 0.180625 - q[cen] ** 2
+    z[cen] = q[cen] * horner(T["kQA"], r) / horner(T["kQB"], r)
+    pp = np.where(q[~cen] < 0, p[~cen], 1 - p[~cen])
+    r = np.sqrt(-np.log(pp))
+    v = np.where(r <= 5, horner(T["kQC"], r - 1.6) / horner(T["kQD"], r - 1.6), horner(T["kQE"], r - 5) / horner(T["kQF"], r - 5))
+    z[~cen] = np.where(q[~cen] < 0, -v, v)
+    zr = special.ndtri(p)
+    assert np.max(np.abs(z - zr) / np.maximum(np.abs(zr), 1e-300)) < 5e-15
+    # pnorm: the single mid-range formula the hot path uses on |x| <= 8
+    c, d = T["kPC"], T["kPD"]
+    y = np.linspace(0, 8, 80001)
+    xn = c[8] * y
+    xd = y.copy()
+    for i in range(7):
+        xn = (xn + c[i]) * y
+        xd = (xd + d[i]) * y
+    lo = np.exp(-0.5 * y * y) * (xn + c[7]) / (xd + d[7])
+    ref = special.ndtr(-y)
+    err = np.abs(lo - ref) / ref
+    assert err[y >= 0.67].max() < 2e-14 and err.max() < 6e-12        # documented in math64.cuh
+    # exp: Taylor to 1/13! on |r| <= ln2/2
+    rr = np.linspace(-0.3466, 0.3466, 2001)
+    pe = np.full_like(rr, T["kEX"][11])
+    for i in range(10, -1, -1):
+        pe = pe * rr + T["kEX"][i]
+    pe = pe * rr * rr + rr + 1.0
+    assert np.max(np.abs(pe - np.exp(rr)) / np.exp(rr)) < 5e-16
+    # FP32 screen of the Bernoulli test (k_sweep): tanh approximation error bound used for the band
+    x = np.linspace(-12, 12, 240001)
+    pf = 0.5 + 0.5 * np.tanh(0.7978845608 * (x + 0.044715 * x ** 3))
+    assert np.abs(pf - special.ndtr(x)).max() < 2e-4                  # + MUFU.TANH 2^-11 rel => < 5e-4 < band 1.5e-3
