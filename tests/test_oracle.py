@@ -241,9 +241,9 @@ def test_device_math_restatement():
     for i in range(7):
         xn = (xn + c[i]) * y
         xd = (xd + d[i]) * y
-    lo = np.exp(-0.5 * y * y) * (xn + c[7]) / (xd + d[7])
-    ref = special.ndtr(-y)
-    err = np.abs(lo - ref) / ref
+    ratio = (xn + c[7]) / (xd + d[7])                 # device: Phi(-y) = exp_mhalfsq(y) * ratio (compensated exp)
+    ref = 0.5 * special.erfcx(y / math.sqrt(2.0))      # == Phi(-y) exp(y^2/2)
+    err = np.abs(ratio - ref) / ref
     assert err[y >= 0.67].max() < 2e-14 and err.max() < 6e-12        # documented in math64.cuh
     # exp: Taylor to 1/13! on |r| <= ln2/2
     rr = np.linspace(-0.3466, 0.3466, 2001)
