@@ -1,0 +1,39 @@
+"""Multi-GPU invariance check (run under torchrun): cells sharded over N ranks + NCCL all-reduce must
+reproduce the single-GPU result (parameters to reduction-order rounding, Y / z shards equal to the
+corresponding slices), because the Philox tape is keyed by the GLOBAL cell index."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import torch, torch.distributed as dist
+import simples_b200 as sb
+from util import make_case, em_args, rel
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); sb.init(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+K0, M0 = 6, 4
+st = make_case(3001, 700, 4, 4, K0, M0, seed=31)          # same on every rank (seeded)
+G, n = st["Y"].shape
+kw = dict(impt_it=1, est_z=1, est_lam=1, seed=13, num_mc=2)
+sh = sb.CellShard(n)
+part = sb.EM_impute(sh.cols(st["Y"]), sh.cols(st["Y0"]), st["pg"], M0, K0, 0.1, 4, st["beta"], st["sigma"], st["lam"],
+                    st["pi"], sh.rows(st["z"]), celltype=sh.rows(st["celltype"]), comm=sh, **kw)
+mi = sb.do_impute(sh.cols(st["Y0"]), part["Y"], part["beta"], part["lambda"], part["sigma"], part["mu"], part["pi"],
+                  part["geneM"], part["geneSd"], sh.rows(st["celltype"]), mcmc=3, burnin=1, pg=st["pg"], seed=5, comm=sh)
+ok = True
+msgs = []
+if rank == 0:
+    full = sb.EM_impute(*em_args(st, M0, K0, 4), celltype=st["celltype"], **kw)
+    fmi = sb.do_impute(st["Y0"], full["Y"], full["beta"], full["lambda"], full["sigma"], full["mu"], full["pi"],
+                       full["geneM"], full["geneSd"], st["celltype"], mcmc=3, burnin=1, pg=st["pg"], seed=5, consensus=False)
+    for k in ("loglik", "pi", "mu", "sigma", "beta", "lambda", "geneM"):
+        e = rel(part[k], full[k]); msgs.append(f"{k}={e:.1e}"); ok &= e <= 1e-9
+    a, b = sh.bounds[0], sh.bounds[1]
+    for k, sl in (("Y", full["Y"][:, a:b]), ("z", full["z"][a:b])):
+        e = rel(part[k], sl); msgs.append(f"{k}[shard0]={e:.1e}"); ok &= e <= 1e-8
+    e = abs(mi["loglik"] - fmi["loglik"]) / abs(fmi["loglik"]); msgs.append(f"mi.loglik={e:.1e}"); ok &= e <= 1e-9
+    e = rel(mi["impt"], fmi["impt"][:, a:b]); msgs.append(f"mi.impt[shard0]={e:.1e}"); ok &= e <= 1e-8
+    print(json.dumps({"world": world, "ok": bool(ok), "allreduces_em+mi": sh.n_allreduce, "errs": msgs}), flush=True)
+dist.barrier(); dist.destroy_process_group()
+sys.exit(0 if ok else 1)
