@@ -93,12 +93,25 @@ def _em_args(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu, c
     return a, keep, (G, n, MB)
 
 
-def _em_out(G, n, M0, K0, iter):
-    bufs = dict(loglik=np.zeros(max(iter, 1)), pi=np.zeros(M0), mu=np.zeros((G, M0), order="F"),
-                sigma=np.zeros((G, M0), order="F"), beta=np.zeros((G, K0), order="F"),
-                lambda_=np.zeros((M0, K0), order="F"), z=np.zeros((n, M0), order="F"),
-                Ef=np.zeros((M0, K0, n)), Varf=np.zeros((M0, K0, K0)), Y=np.zeros((G, n), order="F"),
-                geneM=np.zeros(G), geneSd=np.zeros(G), priorB=np.zeros(1))
+def em_out_shapes(G, n, M0, K0, iter):
+    """Shapes / orders of the EM_impute output buffers (for callers that pre-allocate them, e.g. in
+    pinned host memory): name -> (shape, order)."""
+    return dict(loglik=((max(iter, 1),), "C"), pi=((M0,), "C"), mu=((G, M0), "F"), sigma=((G, M0), "F"),
+                beta=((G, K0), "F"), lambda_=((M0, K0), "F"), z=((n, M0), "F"), Ef=((M0, K0, n), "C"),
+                Varf=((M0, K0, K0), "C"), Y=((G, n), "F"), geneM=((G,), "C"), geneSd=((G,), "C"), priorB=((1,), "C"))
+
+
+def _em_out(G, n, M0, K0, iter, out=None):
+    bufs = {}
+    for k, (shape, order) in em_out_shapes(G, n, M0, K0, iter).items():
+        b = None if out is None else out.get(k)
+        if b is None:
+            b = np.empty(shape, order=order)
+        else:
+            ok = b.dtype == np.float64 and tuple(b.shape) == tuple(shape) and (b.flags.f_contiguous if order == "F" else b.flags.c_contiguous)
+            if not ok:
+                raise ValueError(f"out[{k!r}] must be float64 {shape} in {order} order")
+        bufs[k] = b
     o = EmOut()
     for k, v in bufs.items():
         setattr(o, k, _ptr(v))
@@ -116,7 +129,7 @@ def _em_result(bufs, M0, iter):
 
 def EM_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu=None, celltype=None, penl=1,
               est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1, verbose=False, num_mc=3,
-              lower=-math.inf, upper=math.inf, *, seed=0, ref_compat=COMPAT_DEFAULT, comm=None, stream=None):
+              lower=-math.inf, upper=math.inf, *, seed=0, ref_compat=COMPAT_DEFAULT, comm=None, stream=None, out=None):
     """Monte-Carlo EM imputation on B200 -- drop-in for ``EM_impute`` (R/EM_impute.R:75-339).
 
     Returns a dict with the reference's list names in the reference's order:
@@ -124,13 +137,14 @@ def EM_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu=N
     ``verbose`` is accepted and ignored (the reference's verbose block uses
     undefined globals, R/EM_impute.R:327-329).  Keyword-only extras: ``seed``
     (Philox key replacing R's global RNG), ``ref_compat`` (quirk bits),
-    ``comm`` (a simples_b200.dist.CellShard when cells are sharded over GPUs).
+    ``comm`` (a simples_b200.dist.CellShard when cells are sharded over GPUs), ``out`` (optional dict of
+    pre-allocated output arrays, see ``em_out_shapes`` -- lets a caller keep results in pinned memory).
     """
     lib = _lib.load()
     a, keep, (G, n, _) = _em_args(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu, celltype, penl,
                                   est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper, seed,
                                   ref_compat, comm, stream)
-    o, bufs = _em_out(G, n, int(M0), int(K0), int(iter))
+    o, bufs = _em_out(G, n, int(M0), int(K0), int(iter), out)
     rc = lib.simples_em_impute(C.byref(a), C.byref(o))
     if rc < 0 and "_comm" in keep and keep["_comm"].error is not None:
         raise keep["_comm"].error

@@ -4,6 +4,7 @@
 // host <-> device synchronisation: all data-dependent decisions (lambda eligibility, lasso active
 // sets, priorB bookkeeping) happen on the device.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -524,17 +525,40 @@ int em_iteration(simples_ctx* c) {
     return SIMPLES_OK;
 }
 
-// chunked D2H of a per-entry G x n result produced by `fill(chunk_dev_out, cell0, ncells)`
+// chunked D2H of a per-entry G x n result produced by `fill(chunk_dev_out, cell0, ncells)`.
+// The staging buffer is split in two halves: the fill kernel of chunk k+1 (compute stream) overlaps the
+// D2H copy of chunk k (copy stream).
 template <typename F>
 int fetch_big(simples_ctx* c, double* host_out, F fill) {
     const Dims& d = c->s.d;
-    const size_t cpc = c->stage_elems / d.G;
-    for (size_t c0 = 0; c0 < size_t(d.n); c0 += cpc) {
-        const size_t nc = std::min(cpc, size_t(d.n) - c0);
-        fill(c->stage, c0, nc);
-        CK(cudaMemcpyAsync(host_out + c0 * d.G, c->stage, nc * d.G * 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+    const size_t half_elems = c->stage_elems / 2;
+    const size_t cpc = std::max<size_t>(1, half_elems / d.G);
+    cudaStream_t cs;
+    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaEvent_t filled[2], copied[2];
+    for (int h = 0; h < 2; ++h) {
+        CK(cudaEventCreateWithFlags(&filled[h], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&copied[h], cudaEventDisableTiming));
     }
+    int k = 0;
+    for (size_t c0 = 0; c0 < size_t(d.n); c0 += cpc, ++k) {
+        const int h = k & 1;
+        const size_t nc = std::min(cpc, size_t(d.n) - c0);
+        double* buf = c->stage + size_t(h) * half_elems;
+        if (k >= 2) CK(cudaStreamWaitEvent(c->stream, copied[h], 0));      // half h is free again
+        fill(buf, c0, nc);
+        CK(cudaEventRecord(filled[h], c->stream));
+        CK(cudaStreamWaitEvent(cs, filled[h], 0));
+        CK(cudaMemcpyAsync(host_out + c0 * d.G, buf, nc * d.G * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(copied[h], cs));
+    }
+    CK(cudaStreamSynchronize(cs));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int h = 0; h < 2; ++h) {
+        cudaEventDestroy(filled[h]);
+        cudaEventDestroy(copied[h]);
+    }
+    cudaStreamDestroy(cs);
     return SIMPLES_OK;
 }
 
@@ -801,12 +825,25 @@ int simples_em_fetch(simples_ctx* c, simples_em_out* o) {
 }
 
 int simples_em_impute(const simples_em_args* a, simples_em_out* o) {
+    using clk = std::chrono::steady_clock;
+    const bool trace = getenv("SIMPLES_TRACE") != nullptr;
+    const auto t0 = clk::now();
     simples_ctx* c = nullptr;
     CKR(simples_em_create(a, &c));
+    const auto t1 = clk::now();
     int r = simples_em_run(c, a->iter);
+    if (r == SIMPLES_OK) r = simples_em_sync(c);
+    const auto t2 = clk::now();
     if (r == SIMPLES_OK && o) r = simples_em_fetch(c, o);
     if (r == SIMPLES_OK) r = simples_em_sync(c);
+    const auto t3 = clk::now();
     simples_ctx_destroy(c);
+    const auto t4 = clk::now();
+    if (trace) {
+        auto ms = [](clk::time_point x, clk::time_point y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
+        fprintf(stderr, "[simples_b200] em_impute: create(H2D+prologue) %.1f ms, run(%d it) %.1f ms, fetch(D2H) %.1f ms, destroy %.1f ms\n",
+                ms(t0, t1), a->iter, ms(t1, t2), ms(t2, t3), ms(t3, t4));
+    }
     return r;
 }
 
