@@ -80,6 +80,7 @@ struct simples_ctx {
     long long nnz0 = 0;
     CUtensorMap tmapY;                // Y as [n_alloc][ldG], box {16 genes, 128 cells}, SWIZZLE_128B
     double* cellsum_main = nullptr;   // [2 M0 + 1] of the main E-pass of the current iteration
+    double* cellsum_last = nullptr;   // [2 M0 + 1] of the last E-pass (nz, c feed the M-step)
     double* stage = nullptr;          // staging buffer for chunked H2D / D2H
     size_t stage_elems = 0;
     unsigned long long* d_nnz = nullptr;
@@ -274,6 +275,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     s.ncta_cell = std::min((n + 63) / 64, NUM_SMS_B200 * 4);
     CKR(c->dalloc(&s.part_cell, size_t(s.ncta_cell) * (2 * M0 + 1)));
     CKR(c->dalloc(&c->cellsum_main, size_t(2 * M0 + 1)));
+    CKR(c->dalloc(&c->cellsum_last, size_t(2 * M0 + 1)));
     CKR(c->dalloc(&c->d_nnz, 1));
 
     // staging buffer: whole cells, at most 32 Mi doubles (256 MB)
@@ -462,8 +464,9 @@ int em_iteration(simples_ctx* c) {
             launch_sstats(sa, c->stream);
         }
         {
-            P p(c, KC_REDUCE);
-            FinalizeArgs fa{d, s.part_ms, s.part_cell, s.part_ss, s.splitK, s.ncta_cell, s.nsplit_ss, s.stats, 0, 0};
+            P p(c, KC_REDUCE, 2);
+            launch_finalize_cell(s.part_cell, s.ncta_cell, d.M0, c->cellsum_last, c->stream);
+            FinalizeArgs fa{d, s.part_ms, c->cellsum_last, s.part_ss, s.splitK, 1, s.nsplit_ss, s.stats, 0, 0};
             launch_finalize_stats(fa, c->stream);
         }
         stats = s.stats;
@@ -484,8 +487,9 @@ int em_iteration(simples_ctx* c) {
             launch_sstats(sa, c->stream);
         }
         {
-            P p(c, KC_REDUCE);
-            FinalizeArgs fa{d, nullptr, s.part_cell, s.part_ss, 0, s.ncta_cell, s.nsplit_ss, s.statsg, nC + nU2, 1};
+            P p(c, KC_REDUCE, 2);
+            launch_finalize_cell(s.part_cell, s.ncta_cell, d.M0, c->cellsum_last, c->stream);
+            FinalizeArgs fa{d, nullptr, c->cellsum_last, s.part_ss, 0, 1, s.nsplit_ss, s.statsg, nC + nU2, 1};
             launch_finalize_stats(fa, c->stream);
         }
         stats = s.statsg;
@@ -662,7 +666,7 @@ int simples_em_create(const simples_em_args* a, simples_ctx** out) {
     s.stats_count = size_t(ldG) * d.NVP + ldG + size_t(M0) * K0 * K0 + size_t(M0) * K0 + 2 * M0 + 1;
     CKR(c->dalloc(&s.stats, s.stats_count));
     CKR(c->dalloc(&s.part_ms, size_t(s.splitK) * ldG * (d.NVP + 1)));
-    s.nsplit_ss = std::max(1, (2 * NUM_SMS_B200) / M0);
+    s.nsplit_ss = std::max(1, (4 * NUM_SMS_B200) / M0);
     CKR(c->dalloc(&s.part_ss, size_t(s.nsplit_ss) * M0 * (K0 * K0 + K0)));
     s.ncta_gene = mstep_gene_ctas(d.G);
     CKR(c->dalloc(&s.part_gene, size_t(s.ncta_gene)));

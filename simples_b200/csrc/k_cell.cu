@@ -301,12 +301,13 @@ __global__ void __launch_bounds__(CW * 32) k_cell(CellArgs a, int mm_in_smem) {
     }
 }
 
+// one warp per column: lane-strided partial sums then a fixed shuffle tree (deterministic)
 __global__ void k_finalize_cell(const double* part, int ncta, int R, double* out) {
-    for (int c = threadIdx.x; c < R; c += blockDim.x) {
-        double s = 0.0;
-        for (int b = 0; b < ncta; ++b) s += part[size_t(b) * R + c];
-        out[c] = s;
-    }
+    const int c = blockIdx.x, lane = threadIdx.x;
+    double s = 0.0;
+    for (int b = lane; b < ncta; b += 32) s += part[size_t(b) * R + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s;
 }
 
 }  // namespace
@@ -329,7 +330,7 @@ void launch_cell(const CellArgs& a, cudaStream_t st) {
 }
 
 void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out, cudaStream_t st) {
-    k_finalize_cell<<<1, 64, 0, st>>>(part_cell, ncta, 2 * M0 + 1, out);
+    k_finalize_cell<<<2 * M0 + 1, 32, 0, st>>>(part_cell, ncta, 2 * M0 + 1, out);
 }
 
 }  // namespace sb

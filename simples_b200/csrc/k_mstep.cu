@@ -208,42 +208,41 @@ __global__ void __launch_bounds__(GW * 32) k_gene_solve(MstepArgs a) {
     }
 }
 
-// Damped Newton for  min sum(E/x + c log x)  s.t. sum x = T  (mirrors oracle lambda_solve_k).
-__device__ void lambda_solve_k(const double* E, const double* c, double* x, int mt, double T) {
-    double g[MAXM], hm[MAXM], dx[MAXM], xn[MAXM];
-    double f = 0.0;
-    for (int m = 0; m < mt; ++m) f += E[m] / x[m] + c[m] * log(x[m]);
+// sum of v over lanes 0..mt-1 in ascending lane order (mirrors the oracle's sequential Python sums)
+__device__ __forceinline__ double ordered_sum(double v, int mt) {
+    double s = 0.0;
+    for (int m = 0; m < mt; ++m) s += __shfl_sync(0xffffffffu, v, m);
+    return s;
+}
+
+// Damped Newton for  min sum(E/x + c log x)  s.t. sum x = T  (mirrors oracle lambda_solve_k operation for
+// operation).  One warp per factor, lane m owns component m (mt <= 32).
+__device__ void lambda_solve_warp(double E, double c, double& x, int mt, double T, int lane) {
+    const bool act = lane < mt;
+    if (!act) { E = 1.0; c = 1.0; x = 1.0; }
+    double f = ordered_sum(act ? E / x + c * log(x) : 0.0, mt);
     for (int it = 0; it < 500; ++it) {
-        double sg = 0.0, sh = 0.0;
-        for (int m = 0; m < mt; ++m) {
-            const double xi = x[m];
-            g[m] = -E[m] / (xi * xi) + c[m] / xi;
-            double h = fabs(2.0 * E[m] / (xi * xi * xi) - c[m] / (xi * xi));
-            if (h < 1e-300) h = 1e-300;
-            hm[m] = h;
-            sg += g[m] / h;
-            sh += 1.0 / h;
-        }
+        const double g = -E / (x * x) + c / x;
+        double h = fabs(2.0 * E / (x * x * x) - c / (x * x));
+        if (h < 1e-300) h = 1e-300;
+        const double sg = ordered_sum(act ? g / h : 0.0, mt);
+        const double sh = ordered_sum(act ? 1.0 / h : 0.0, mt);
         const double nu = -sg / sh;
-        double gd = 0.0, amax = 1.0, dmax = 0.0;
-        for (int m = 0; m < mt; ++m) {
-            dx[m] = -(g[m] + nu) / hm[m];
-            gd += g[m] * dx[m];
-            if (dx[m] < 0.0) {
-                const double al = -0.9 * x[m] / dx[m];
-                if (al < amax) amax = al;
-            }
-            if (fabs(dx[m]) > dmax) dmax = fabs(dx[m]);
+        const double dx = act ? -(g + nu) / h : 0.0;
+        const double gd = ordered_sum(g * dx, mt);
+        double al = (act && dx < 0.0) ? -0.9 * x / dx : 1.0;
+        double dm = fabs(dx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            al = fmin(al, __shfl_xor_sync(0xffffffffu, al, o));
+            dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         }
-        if (dmax <= 1e-15 * T) break;
-        double al = amax, fn = f;
+        if (dm <= 1e-15 * T) break;
+        double fn = f, xn = x;
         bool ok = false;
         for (int bt = 0; bt < 60; ++bt) {
-            fn = 0.0;
-            for (int m = 0; m < mt; ++m) {
-                xn[m] = x[m] + al * dx[m];
-                fn += E[m] / xn[m] + c[m] * log(xn[m]);
-            }
+            xn = x + al * dx;
+            fn = ordered_sum(act ? E / xn + c * log(xn) : 0.0, mt);
             if (fn <= f + 1e-4 * al * gd + 1e-14 * fabs(f)) {
                 ok = true;
                 break;
@@ -251,66 +250,69 @@ __device__ void lambda_solve_k(const double* E, const double* c, double* x, int 
             al *= 0.5;
         }
         if (!ok) break;
-        for (int m = 0; m < mt; ++m) x[m] = xn[m];
+        x = xn;
         f = fn;
     }
 }
 
-__global__ void __launch_bounds__(256) k_lmp(MstepArgs a) {
+__global__ void __launch_bounds__(1024) k_lmp(MstepArgs a) {
     const Dims& d = a.d;
     const int K0 = d.K0, M0 = d.M0;
     const StatView sv = stat_view(a.stats, d, a.general);
     __shared__ int colnz[MAXK];
     __shared__ int ind[MAXM];
     __shared__ int mt_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < MAXK) colnz[threadIdx.x] = 0;
     __syncthreads();
     // any(beta[,k] != 0) on the NEW beta (R/EM_impute.R:293)
     for (int e = threadIdx.x; e < d.G * K0; e += blockDim.x)
         if (a.beta[e] != 0.0) colnz[e % K0] = 1;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
         // loglik[it] = tot - priorB(previous iteration)  (Q5), then priorB <- sum of this M-step
         double pb = 0.0;
-        for (int i = 0; i < a.ncta_gene; ++i) pb += a.part_gene[i];
-        const double prev = a.priorB[0];
-        *a.loglik_slot = sv.tot[0] - (a.compat_priorb_prev ? prev : 0.0);
-        a.priorB[1] = prev;
-        a.priorB[0] = pb;
-        int mt = 0;
-        for (int m = 0; m < M0; ++m)
-            if (sv.nz[m] > K0 + 1 && sv.nz[m] > 3.0) ind[mt++] = m;      // :279
-        mt_s = mt;
-        for (int m = 0; m < M0; ++m)                                      // :318
-            a.pi[m] = (sv.nz[m] + a.pi_alpha - 1.0) / (double(d.n_total) + a.pi_alpha * M0 - M0);
+        for (int i = lane; i < a.ncta_gene; i += 32) pb += a.part_gene[i];
+        pb = warp_sum(pb);
+        if (lane == 0) {
+            const double prev = a.priorB[0];
+            *a.loglik_slot = sv.tot[0] - (a.compat_priorb_prev ? prev : 0.0);
+            a.priorB[1] = prev;
+            a.priorB[0] = pb;
+            int mt = 0;
+            for (int m = 0; m < M0; ++m)
+                if (sv.nz[m] > K0 + 1 && sv.nz[m] > 3.0) ind[mt++] = m;      // :279
+            mt_s = mt;
+        }
+        if (lane < M0)                                                        // :318
+            a.pi[lane] = (sv.nz[lane] + a.pi_alpha - 1.0) / (double(d.n_total) + a.pi_alpha * M0 - M0);
     }
     __syncthreads();
     if (!a.do_lambda) return;
     const int mt = mt_s;
     if (mt > 1) {
-        if (threadIdx.x < K0) {
-            const int k = threadIdx.x;
+        if (warp < K0) {
+            const int k = warp;
             // lambda[-ind_m, ] <- 1/M0  (:288)
-            for (int m = 0; m < M0; ++m) {
+            if (lane < M0) {
                 bool in = false;
-                for (int q = 0; q < mt; ++q) in |= (ind[q] == m);
-                if (!in) a.lam[m * K0 + k] = 1.0 / M0;
+                for (int q = 0; q < mt; ++q) in |= (ind[q] == lane);
+                if (!in) a.lam[lane * K0 + k] = 1.0 / M0;
             }
             if (!colnz[k]) {
-                for (int m = 0; m < M0; ++m) a.lam[m * K0 + k] = 1.0 / M0;   // :293-294
+                if (lane < M0) a.lam[lane * K0 + k] = 1.0 / M0;               // :293-294
             } else {
-                double E[MAXM], c[MAXM], x[MAXM];
-                double s = 0.0;
-                for (int q = 0; q < mt; ++q) {
-                    const int m = ind[q];
-                    E[q] = sv.S[(size_t(m) * K0 + k) * K0 + k] + a.Mm[(size_t(m) * K0 + k) * K0 + k] * sv.nz[m];  // :282-285
-                    c[q] = sv.nz[m] - 2.0;
-                    x[q] = (E[q] + 1.0) / (sv.nz[m] + 1.0);                 // :289
-                    s += x[q];
+                double E = 1.0, c = 1.0, x = 1.0;
+                if (lane < mt) {
+                    const int m = ind[lane];
+                    E = sv.S[(size_t(m) * K0 + k) * K0 + k] + a.Mm[(size_t(m) * K0 + k) * K0 + k] * sv.nz[m];   // :282-285
+                    c = sv.nz[m] - 2.0;
+                    x = (E + 1.0) / (sv.nz[m] + 1.0);                         // :289
                 }
+                const double s = ordered_sum(lane < mt ? x : 0.0, mt);
                 const double T = double(mt) / M0;
-                for (int q = 0; q < mt; ++q) x[q] = x[q] / s * mt / M0;     // :290
-                lambda_solve_k(E, c, x, mt, T);
-                for (int q = 0; q < mt; ++q) a.lam[ind[q] * K0 + k] = x[q];
+                x = x / s * mt / M0;                                          // :290
+                lambda_solve_warp(E, c, x, mt, T, lane);
+                if (lane < mt) a.lam[ind[lane] * K0 + k] = x;
             }
         }
     } else {
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256) k_lmp(MstepArgs a) {
     }
 }
 
-constexpr int MG = 64;
+constexpr int MG = 256;
 
 __global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
     extern __shared__ __align__(16) double sm[];
@@ -337,12 +339,14 @@ __global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
     double acc[5] = {0, 0, 0, 0, 0};
     for (int g0 = 0; g0 < ldG; g0 += MG) {
         __syncthreads();
-        for (int idx = threadIdx.x; idx < MG * K0; idx += blockDim.x) sB[idx] = a.beta[size_t(g0) * K0 + idx];
+        for (int idx = threadIdx.x; idx < MG * K0; idx += blockDim.x)
+            sB[idx] = (g0 + idx / K0 < ldG) ? a.beta[size_t(g0) * K0 + idx] : 0.0;      // rows past ldG contribute 0
         if (threadIdx.x < MG) {
             const int g = g0 + threadIdx.x;
-            const double s = nzm + a.sigma[size_t(g) * M0 + m] / a.sigma0;     // :308
+            const bool v = g < ldG;
+            const double s = nzm + (v ? a.sigma[size_t(g) * M0 + m] : 1.0) / a.sigma0;     // :308
             sw[threadIdx.x] = 1.0 / s;
-            sv_[threadIdx.x] = sv.C[size_t(g) * sv.ldc + ucol] / s;
+            sv_[threadIdx.x] = v ? sv.C[size_t(g) * sv.ldc + ucol] / s : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -403,9 +407,14 @@ void launch_mstep(const MstepArgs& a, cudaStream_t st) {
         }
         k_gene_solve<<<a.ncta_gene, GW * 32, smem, st>>>(a);
     }
-    k_lmp<<<1, 256, 0, st>>>(a);
+    k_lmp<<<1, 1024, 0, st>>>(a);
     {
         const size_t smem = sizeof(double) * (size_t(MG) * K0 + 2 * MG + K0 * K0 + K0);
+        static size_t attr2 = 0;
+        if (smem > 48 * 1024 && smem > attr2) {
+            cudaFuncSetAttribute(k_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            attr2 = smem;
+        }
         k_mu<<<M0, 256, smem, st>>>(a);
     }
 }

@@ -36,7 +36,7 @@ __global__ void k_build_ops(PrepArgs a) {
     for (int c = K0 + M0 + 1; c < d.FS; ++c) qs[c] = 0.0;
 }
 
-constexpr int GT = 64;   // genes per smem tile
+constexpr int GT = 256;  // genes per smem tile
 
 __global__ void __launch_bounds__(256) k_cluster(PrepArgs a) {
     extern __shared__ __align__(16) double sm[];
@@ -61,11 +61,13 @@ __global__ void __launch_bounds__(256) k_cluster(PrepArgs a) {
     double acc[5] = {0, 0, 0, 0, 0};   // NE <= 1090 <= 5 * 256
     for (int g0 = 0; g0 < ldG; g0 += GT) {
         __syncthreads();
-        for (int idx = threadIdx.x; idx < GT * K0; idx += blockDim.x) sB[idx] = a.beta[size_t(g0) * K0 + idx];
+        for (int idx = threadIdx.x; idx < GT * K0; idx += blockDim.x)
+            sB[idx] = (g0 + idx / K0 < ldG) ? a.beta[size_t(g0) * K0 + idx] : 0.0;      // rows past ldG contribute 0
         if (threadIdx.x < GT) {
             const int g = g0 + threadIdx.x;
-            const double sg = a.sigma[size_t(g) * M0 + cs], sq = a.sigma[size_t(g) * M0 + qcol];
-            const double mu = a.mu[size_t(g) * M0 + m];
+            const bool v = g < ldG;
+            const double sg = v ? a.sigma[size_t(g) * M0 + cs] : 1.0, sq = v ? a.sigma[size_t(g) * M0 + qcol] : 1.0;
+            const double mu = v ? a.mu[size_t(g) * M0 + m] : 0.0;
             sw[threadIdx.x] = 1.0 / sg;
             smw[threadIdx.x] = mu / sg;
             smq[threadIdx.x] = mu / sq;

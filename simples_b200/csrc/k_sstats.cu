@@ -8,7 +8,7 @@
 namespace sb {
 namespace {
 
-constexpr int CH = 64;   // cells per smem chunk
+constexpr int CH = 256;  // cells per smem chunk
 
 __global__ void __launch_bounds__(256) k_sstats(SstatsArgs a, int cps) {
     extern __shared__ __align__(16) double sm[];
