@@ -83,6 +83,11 @@ __global__ void k_finalize_stats(FinalizeArgs a, size_t count) {
 void launch_sstats(const SstatsArgs& a, cudaStream_t st) {
     const int cps = ((a.d.n + a.nsplit - 1) / a.nsplit + CH - 1) / CH * CH;
     const size_t smem = sizeof(double) * (size_t(CH) * a.d.K0 + CH);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(k_sstats, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr = smem;
+    }
     dim3 grid(a.d.M0, a.nsplit);
     k_sstats<<<grid, 256, smem, st>>>(a, cps);
 }

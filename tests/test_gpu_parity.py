@@ -32,6 +32,9 @@ CASES = [
     (900, 520, 6, 5, 12, 7, 3, 1, False),    # K0 + M0 > 16
     (64, 40, 1, 2, 1, 2, 2, 1, False),       # K0 = 1, tiny
     (1500, 1000, 6, 3, 10, 3, 3, 1, False),  # config C1 shape (vignette simulation, K0 = 10, M0 = 3)
+    (1200, 700, 8, 6, 20, 20, 3, 1, False),  # config C4 factor / cluster counts (K0 = M0 = 20)
+    (900, 400, 8, 5, 30, 20, 2, 1, False),   # config C5 maximum (K0 = 30, M0 = 20): M_m tables read from L2
+    (700, 300, 4, 4, 32, 32, 2, 1, True),    # ABI limits K0 = M0 = 32, per-cluster sigma
 ]
 
 
