@@ -127,13 +127,15 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         }
         __syncwarp();
 
-        // ---- 3a. classify every zero entry with a cheap FP32 screen of the Bernoulli test ----
-        // Phi(r) ~ 0.5 + 0.5 tanh(sqrt(2/pi)(r + 0.044715 r^3)) (|err| < 5e-4 incl. MUFU.TANH); an entry whose
-        // test statistic clears the 1.5e-3 band is a CERTAIN dropout and never needs the FP64 pnorm.
-        // Lists: Dc = certain dropout & central quantile, Dt = certain dropout & tail quantile, X = exact path.
-        int nDc = 0, nDt = 0, nX = 0;
+        // ---- 3a. classify every zero entry with an FP32 screen of the Bernoulli test ----
+        // Phi(r) in float by Abramowitz-Stegun 7.1.26 (|err| < 5e-7 incl. MUFU.RCP / MUFU.EX2); an entry whose
+        // test statistic clears the +-4e-6 band has a CERTAIN outcome:
+        //   Dc: certain dropout, central quantile  -> x = ms + sds qnorm_central(ub), no FP64 pnorm at all
+        //   S : certain dropout with a tail quantile (ub stored) or certain "expressed but <= cutoff" (-ub stored)
+        //   U : inside the band (~1e-5 of the entries) -> exact FP64 decision
+        int nDc = 0, nS = 0, nU = 0;
         const int rounds = (total + 31) >> 5;
-#pragma unroll 1
+#pragma unroll 2
         for (int it = 0; it < rounds; ++it) {
             const int e = it * 32 + lane;
             const bool valid = e < total;
@@ -141,33 +143,45 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
             const int r = code >> 5, gl = code & 31;
             const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
             const double ms = msW[r * MSS + gl];
-            const double p = b.pg[gl * MB + ct];
             const Philox4 px = entry_philox(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + wc0 + r),
                                             (uint32_t)(chunk * SG + gl));
             const double ub = u52(px.x2, px.x3);
             const float rf = (float)((a.cutoff - ms) * b.isd[gl * M0 + im]);
-            float th;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.7978845608f * fmaf(0.044715f * rf * rf, rf, rf)));
-            const float pf = fmaf(0.5f, th, 0.5f);
+            const float ax = fabsf(rf) * 0.70710678f;
+            float tt, ex;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tt) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950f * ax * ax));
+            float po = fmaf(tt, 1.061405429f, -1.453152027f);
+            po = fmaf(tt, po, 1.421413741f);
+            po = fmaf(tt, po, -0.284496736f);
+            po = fmaf(tt, po, 0.254829592f);
+            const float hc = 0.5f * po * tt * ex;                        // 0.5 erfc(|r| / sqrt 2)
+            const float pf = rf < 0.0f ? hc : 1.0f - hc;
             const float uaf = (float)(px.x0 >> 8) * 5.9604644775390625e-8f;
-            const float pfl = (float)p, q1f = 1.0f - pfl;
+            const float pfl = (float)b.pg[gl * MB + ct], q1f = 1.0f - pfl;
             const float d = fmaf(uaf, fmaf(pf, pfl, q1f), -q1f);
-            const bool isD = valid && (d < -1.5e-3f);
+            const bool isD = valid && (d < -4e-6f);
+            const bool isT = valid && (d > 4e-6f);
             const bool cen = fabs(ub - 0.5) <= 0.425;
-            const unsigned bDc = __ballot_sync(0xffffffffu, isD && cen);
-            const unsigned bDt = __ballot_sync(0xffffffffu, isD && !cen);
-            const unsigned bX = __ballot_sync(0xffffffffu, valid && !isD);
+            const bool toDc = isD && cen, toS = (isD && !cen) || isT, toU = valid && !isD && !isT;
+            const unsigned bDc = __ballot_sync(0xffffffffu, toDc);
+            const unsigned bS = __ballot_sync(0xffffffffu, toS);
+            const unsigned bU = __ballot_sync(0xffffffffu, toU);
             const unsigned lt = (1u << lane) - 1u;
-            if (isD) {
-                const int pos = cen ? nDc + __popc(bDc & lt) : 255 - (nDt + __popc(bDt & lt));
+            if (toDc) {
+                const int pos = nDc + __popc(bDc & lt);
                 dcode[pos] = (unsigned char)code;
                 dub[pos] = ub;
-            } else if (valid) {
-                xcode[nX + __popc(bX & lt)] = (unsigned char)code;
+            } else if (toS) {
+                const int pos = 255 - (nS + __popc(bS & lt));
+                dcode[pos] = (unsigned char)code;
+                dub[pos] = isT ? -ub : ub;
+            } else if (toU) {
+                xcode[nU + __popc(bU & lt)] = (unsigned char)code;
             }
             nDc += __popc(bDc);
-            nDt += __popc(bDt);
-            nX += __popc(bX);
+            nS += __popc(bS);
+            nU += __popc(bU);
         }
         __syncwarp();
 
@@ -192,17 +206,18 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
             const double z = qnorm_central(dub[e]);
             finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], z, msW[r * MSS + gl]));
         }
-        // ---- 3c. certain dropouts, tail quantile ----
+        // ---- 3c. slow list: tail-quantile dropouts and certain truncated-normal draws (R/EM_impute.R:191-192) ----
 #pragma unroll 1
-        for (int e = lane; e < nDt; e += 32) {
+        for (int e = lane; e < nS; e += 32) {
             const int code = dcode[255 - e];
+            const double v = dub[255 - e];
             const int r = code >> 5, gl = code & 31;
-            const double z = qnorm_tail(dub[255 - e]);
-            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], z, msW[r * MSS + gl]));
+            const int im = cellinfo[r * 2];
+            finish(r, gl, sample_slow(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], a.cutoff, v));
         }
-        // ---- 3d. exact path: FP64 pnorm, exact Bernoulli test, normal or truncated-normal draw ----
+        // ---- 3d. inside the screening band: exact FP64 Bernoulli test and draw ----
 #pragma unroll 1
-        for (int e = lane; e < nX; e += 32) {
+        for (int e = lane; e < nU; e += 32) {
             const int code = xcode[e];
             const int r = code >> 5, gl = code & 31;
             const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
