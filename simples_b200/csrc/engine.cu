@@ -272,7 +272,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.cc.offq, size_t(M0) * K0));
     CKR(c->dalloc(&s.cc.cmu, size_t(M0)));
     CKR(c->dalloc(&s.cc.logpi, size_t(M0)));
-    s.ncta_cell = std::min((n + 63) / 64, NUM_SMS_B200 * 4);
+    s.ncta_cell = std::min((n + 63) / 64, NUM_SMS_B200 * 8);
     CKR(c->dalloc(&s.part_cell, size_t(s.ncta_cell) * (2 * M0 + 1)));
     CKR(c->dalloc(&c->cellsum_main, size_t(2 * M0 + 1)));
     CKR(c->dalloc(&c->cellsum_last, size_t(2 * M0 + 1)));

@@ -22,7 +22,7 @@ struct CellSmem {
     int* im;
 };
 
-__global__ void __launch_bounds__(CW * 32) k_cell(CellArgs a, int mm_in_smem) {
+__global__ void __launch_bounds__(CW * 32, 4) k_cell(CellArgs a, int mm_in_smem, int pw_doubles) {
     extern __shared__ __align__(16) double sm[];
     const int M0 = a.d.M0, K0 = a.d.K0, NS = a.d.NS, n = a.d.n, NQP = a.d.NQP;
     const int KS = (K0 + 3) / 4, NT = (K0 + 7) / 8, KR = 4 * KS, KPS = 8 * NT + 4;   // padded M_m: [KR][KPS]
@@ -45,13 +45,13 @@ __global__ void __launch_bounds__(CW * 32) k_cell(CellArgs a, int mm_in_smem) {
     double* sRed = p;      p += CW * (2 * M0 + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int PWS = NQP + 4;
-    double* Pa = p + warp * (2 * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR);   // [8][PWS]  x2 source for the quadratic form
-    double* Pb = Pa + 8 * PWS;                                               // [8][PWS]  x2 source for W, mu column
-    double* llw = Pb + 8 * PWS;                                              // [8][M0]
+    double* Pa = p + warp * pw_doubles;                                      // [8][PWS]  x2 source for the quadratic form
+    double* Pb = Pa + 8 * PWS;                                               // [8][PWS]  x2 source for W, mu column (general path only)
+    double* llw = Pa + (NS == 1 ? 1 : 2) * 8 * PWS;                          // [8][M0]
     double* zw = llw + 8 * M0;                                               // [8][M0]
     double* wsw = zw + 8 * M0;                                               // [8][KPS]  W of the sampled cluster
     double* epw = wsw + 8 * KPS;                                             // [8][KR]   factor normals
-    p += CW * (2 * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR);
+    p += CW * pw_doubles;
     int* imw = reinterpret_cast<int*>(p) + warp * 8;
 
     for (int i = threadIdx.x; i < M0 * KR; i += blockDim.x) {
@@ -315,18 +315,19 @@ __global__ void k_finalize_cell(const double* part, int ncta, int R, double* out
 void launch_cell(const CellArgs& a, cudaStream_t st) {
     const int M0 = a.d.M0, K0 = a.d.K0;
     const int KS = (K0 + 3) / 4, NT = (K0 + 7) / 8, KR = 4 * KS, KPS = 8 * NT + 4, PWS = a.d.NQP + 4;
-    const size_t fixed = sizeof(double) * (size_t(2) * M0 * KR + 3 * M0 + CW * (2 * M0 + 1) +
-                                           size_t(CW) * (2 * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR)) +
+    const int pw_doubles = (a.d.NS == 1 ? 1 : 2) * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR;
+    const size_t fixed = sizeof(double) * (size_t(2) * M0 * KR + 3 * M0 + CW * (2 * M0 + 1) + size_t(CW) * pw_doubles) +
                          sizeof(int) * CW * 8;
-    const size_t mm = sizeof(double) * size_t(M0) * KR * KPS;
-    const int mm_in_smem = (fixed + mm <= 160 * 1024) ? 1 : 0;
-    const size_t smem = fixed + (mm_in_smem ? mm : 0);
+    // The padded M_m tables (M0 * KR * KPS doubles, 19 KB at K0 = M0 = 10) are read through L1 instead of being
+    // copied to shared memory by every CTA: same latency, and the smaller footprint lets 4-5 CTAs share an SM.
+    const int mm_in_smem = 0;
+    const size_t smem = fixed;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         cudaFuncSetAttribute(k_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr = smem;
     }
-    k_cell<<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem);
+    k_cell<<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem, pw_doubles);
 }
 
 void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out, cudaStream_t st) {
