@@ -22,7 +22,8 @@ struct CellSmem {
     int* im;
 };
 
-__global__ void __launch_bounds__(CW * 32, 4) k_cell(CellArgs a, int mm_in_smem, int pw_doubles) {
+template <int KSX, int NTX>
+__global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a, int mm_in_smem, int pw_doubles) {
     extern __shared__ __align__(16) double sm[];
     const int M0 = a.d.M0, K0 = a.d.K0, NS = a.d.NS, n = a.d.n, NQP = a.d.NQP;
     const int KS = (K0 + 3) / 4, NT = (K0 + 7) / 8, KR = 4 * KS, KPS = 8 * NT + 4;   // padded M_m: [KR][KPS]
@@ -102,18 +103,25 @@ __global__ void __launch_bounds__(CW * 32, 4) k_cell(CellArgs a, int mm_in_smem,
             }
             const double* off = (a.stale_q ? sOffq : sOff) + m * KR;
             const double* Mp = sMp + m * MMSZ;
+            double av[KSX];
+#pragma unroll
+            for (int ks = 0; ks < KSX; ++ks) {
+                const int k = 4 * ks + t;
+                av[ks] = (ks < KS && k < K0) ? Pa[g * PWS + k] - off[k] : 0.0;
+            }
             double qd = 0.0;
-            for (int nt = 0; nt < NT; ++nt) {
-                double c0 = 0.0, c1 = 0.0;
-                for (int ks = 0; ks < KS; ++ks) {
-                    const int k = 4 * ks + t;
-                    const double av = (k < K0) ? Pa[g * PWS + k] - off[k] : 0.0;
-                    dmma(c0, c1, av, Mp[k * KPS + nt * 8 + g]);
+#pragma unroll
+            for (int nt = 0; nt < NTX; ++nt) {
+                if (nt < NT) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KSX; ++ks)
+                        if (ks < KS) dmma(c0, c1, av[ks], Mp[(4 * ks + t) * KPS + nt * 8 + g]);
+                    const int k0 = nt * 8 + 2 * t;
+                    const double x0 = (k0 < K0) ? Pa[g * PWS + k0] - off[k0] : 0.0;
+                    const double x1 = (k0 + 1 < K0) ? Pa[g * PWS + k0 + 1] - off[k0 + 1] : 0.0;
+                    qd = fma(c0, x0, fma(c1, x1, qd));
                 }
-                const int k0 = nt * 8 + 2 * t;
-                const double x0 = (k0 < K0) ? Pa[g * PWS + k0] - off[k0] : 0.0;
-                const double x1 = (k0 + 1 < K0) ? Pa[g * PWS + k0 + 1] - off[k0 + 1] : 0.0;
-                qd = fma(c0, x0, fma(c1, x1, qd));
             }
             qd += __shfl_xor_sync(0xffffffffu, qd, 1);
             qd += __shfl_xor_sync(0xffffffffu, qd, 2);
@@ -185,9 +193,9 @@ __global__ void __launch_bounds__(CW * 32, 4) k_cell(CellArgs a, int mm_in_smem,
         const int im_g = a.sample ? imw[g] : -1;
 
         // ---- pass 2: factor posterior means W_m = x2_m M_m, Wbar = sum_m z_m W_m ----
-        double wb[4][2];
+        double wb[NTX][2];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) wb[nt][0] = wb[nt][1] = 0.0;
+        for (int nt = 0; nt < NTX; ++nt) wb[nt][0] = wb[nt][1] = 0.0;
         for (int m = 0; m < M0; ++m) {
             const int cs = (NS == 1) ? 0 : m;
             if (NS > 1) {
@@ -201,15 +209,19 @@ __global__ void __launch_bounds__(CW * 32, 4) k_cell(CellArgs a, int mm_in_smem,
             const double* off = sOff + m * KR;
             const double* Mp = sMp + m * MMSZ;
             const double zm = zw[g * M0 + m];
+            double av[KSX];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
+            for (int ks = 0; ks < KSX; ++ks) {
+                const int k = 4 * ks + t;
+                av[ks] = (ks < KS && k < K0) ? PbT[g * PWS + k] - off[k] : 0.0;
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTX; ++nt) {
                 if (nt < NT) {
                     double c0 = 0.0, c1 = 0.0;
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const int k = 4 * ks + t;
-                        const double av = (k < K0) ? PbT[g * PWS + k] - off[k] : 0.0;
-                        dmma(c0, c1, av, Mp[k * KPS + nt * 8 + g]);
-                    }
+#pragma unroll
+                    for (int ks = 0; ks < KSX; ++ks)
+                        if (ks < KS) dmma(c0, c1, av[ks], Mp[(4 * ks + t) * KPS + nt * 8 + g]);
                     wb[nt][0] = fma(zm, c0, wb[nt][0]);
                     wb[nt][1] = fma(zm, c1, wb[nt][1]);
                     const int k0 = nt * 8 + 2 * t;
@@ -236,7 +248,7 @@ __global__ void __launch_bounds__(CW * 32, 4) k_cell(CellArgs a, int mm_in_smem,
         if (rv) {
             double* vrow = a.V + size_t(cell) * a.d.VS;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
+            for (int nt = 0; nt < NTX; ++nt) {
                 const int k0 = nt * 8 + 2 * t;
                 if (nt < NT) {
                     if (k0 < K0) vrow[k0] = wb[nt][0];
@@ -322,12 +334,21 @@ void launch_cell(const CellArgs& a, cudaStream_t st) {
     // copied to shared memory by every CTA: same latency, and the smaller footprint lets 4-5 CTAs share an SM.
     const int mm_in_smem = 0;
     const size_t smem = fixed;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
+    if (K0 <= 16) {
+        static size_t attr = 0;
+        if (smem > 48 * 1024 && smem > attr) {
+            cudaFuncSetAttribute(k_cell<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            attr = smem;
+        }
+        k_cell<4, 2><<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem, pw_doubles);
+    } else {
+        static size_t attr = 0;
+        if (smem > 48 * 1024 && smem > attr) {
+            cudaFuncSetAttribute(k_cell<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            attr = smem;
+        }
+        k_cell<8, 4><<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem, pw_doubles);
     }
-    k_cell<<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem, pw_doubles);
 }
 
 void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out, cudaStream_t st) {
