@@ -64,6 +64,9 @@ struct simples_ctx {
     std::vector<void*> allocs;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;          // side stream: cluster_prep / sstats overlap the big GEMM kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool cluster_pending = false;
     // scalars of the call
     double cutoff = 0, penl = 1, sigma0 = 100, pi_alpha = 1, lower = -INFINITY, upper = INFINITY;
     int est_z = 2, max_lambda = 1, est_lam = 2, impt_it = 5, num_mc = 3;
@@ -141,6 +144,9 @@ struct simples_ctx {
         }
         for (auto e : iter_ev) cudaEventDestroy(e);
         for (void* p : allocs) cudaFree(p);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -352,6 +358,10 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
                     s.S2 + size_t(sc) * d.n, d.n, d.ldG, d.NQP, d.QS};
         launch_proj(pa, c->tmapY, c->stream);
     }
+    if (c->cluster_pending) {
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        c->cluster_pending = false;
+    }
     {
         P p(c, KC_CELL);
         CellArgs ca{};
@@ -387,7 +397,20 @@ int run_prep(simples_ctx* c) {
     DevState& s = c->s;
     P p(c, KC_PREP, 2);
     PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.igs, s.cc, 0};
-    launch_prep(pa, c->stream);
+    if (c->profile) {                      // serial on the main stream so the per-class events mean something
+        launch_prep(pa, c->stream, c->stream);
+    } else {
+        if (!c->side) {
+            CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(c->ev_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        launch_prep(pa, c->stream, c->side);
+        CK(cudaEventRecord(c->ev_join, c->side));
+        c->cluster_pending = true;         // joined right before the first cell_post
+    }
     CK(cudaGetLastError());
     return SIMPLES_OK;
 }
@@ -453,16 +476,23 @@ int em_iteration(simples_ctx* c) {
     double* stats;
     size_t count;
     if (!general) {
+        const bool overlap = !c->profile && c->side != nullptr;
+        if (overlap) {      // sstats (latency-bound, few CTAs) runs beside the mstats GEMM
+            CK(cudaEventRecord(c->ev_fork, c->stream));
+            CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        }
+        {
+            P p(c, KC_SSTATS);
+            SstatsArgs sa{d, s.W, s.z, s.part_ss, s.nsplit_ss};
+            launch_sstats(sa, overlap ? c->side : c->stream);
+        }
+        if (overlap) CK(cudaEventRecord(c->ev_join, c->side));
         {
             P p(c, KC_MSTATS);
             MstatsArgs ma{s.Y, s.V, s.zsum, s.part_ms, d.n, d.ldG, d.NVP, d.VS, s.splitK};
             launch_mstats(ma, c->stream);
         }
-        {
-            P p(c, KC_SSTATS);
-            SstatsArgs sa{d, s.W, s.z, s.part_ss, s.nsplit_ss};
-            launch_sstats(sa, c->stream);
-        }
+        if (overlap) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         {
             P p(c, KC_REDUCE, 2);
             launch_finalize_cell(s.part_cell, s.ncta_cell, d.M0, c->cellsum_last, c->stream);

@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(256) k_cluster(PrepArgs a) {
 
 }  // namespace
 
-void launch_prep(const PrepArgs& a, cudaStream_t st) {
+void launch_prep(const PrepArgs& a, cudaStream_t st, cudaStream_t st_cluster) {
+    // the GEMM operands (needed by estep_project / impute_sweep) and the per-cluster constants (needed only by
+    // cell_post) are independent: the latter may run on a side stream and overlap the first projection.
     k_build_ops<<<(a.d.ldG + 127) / 128, 128, 0, st>>>(a);
     const int K0 = a.d.K0;
     const size_t smem = sizeof(double) * (size_t(GT) * K0 + 5 * GT + 4 * K0 * K0 + 2);
@@ -159,7 +161,7 @@ void launch_prep(const PrepArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr = smem;
     }
-    k_cluster<<<a.d.M0, 256, smem, st>>>(a);
+    k_cluster<<<a.d.M0, 256, smem, st_cluster>>>(a);
 }
 
 }  // namespace sb

@@ -149,7 +149,7 @@ struct PrepArgs {
     Dims d; const double *beta, *sigma, *mu, *lam, *pi, *gmean, *gsd;
     double *Q, *isg, *Qs, *sdsA, *isdA, *igs; ClusterConsts cc; int stale_q;
 };
-void launch_prep(const PrepArgs& a, cudaStream_t st);
+void launch_prep(const PrepArgs& a, cudaStream_t st, cudaStream_t st_cluster);
 
 struct MstepArgs {
     Dims d;
