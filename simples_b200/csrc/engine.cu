@@ -106,7 +106,7 @@ struct simples_ctx {
     int dalloc(T** p, size_t count, bool zero = true) {
         void* q = nullptr;
         if (count == 0) count = 1;
-        CK(cudaMalloc(&q, count * sizeof(T)));
+        CK(cudaMallocAsync(&q, count * sizeof(T), stream));   // stream-ordered pool: repeated calls reuse the blocks
         allocs.push_back(q);
         if (zero) CK(cudaMemsetAsync(q, 0, count * sizeof(T), stream));
         *p = static_cast<T*>(q);
@@ -143,7 +143,8 @@ struct simples_ctx {
             cudaEventDestroy(r.b);
         }
         for (auto e : iter_ev) cudaEventDestroy(e);
-        for (void* p : allocs) cudaFree(p);
+        for (void* p : allocs) cudaFreeAsync(p, stream);
+        if (stream) cudaStreamSynchronize(stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (side) cudaStreamDestroy(side);
@@ -182,6 +183,14 @@ int ensure_device() {
         return fail(SIMPLES_ENODEV, buf);
     }
     CK(cudaSetDevice(g_device));
+    static int pool_dev = -1;
+    if (pool_dev != g_device) {            // keep freed blocks cached in the default pool between calls
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, g_device));
+        unsigned long long thr = ~0ull;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        pool_dev = g_device;
+    }
     return SIMPLES_OK;
 }
 
@@ -339,11 +348,11 @@ int upload_z(simples_ctx* c, const double* z) {
     DevState& s = c->s;
     const int n = s.d.n, M0 = s.d.M0;
     double* tmp = nullptr;
-    CK(cudaMalloc(&tmp, size_t(n) * M0 * 8));
+    CK(cudaMallocAsync(&tmp, size_t(n) * M0 * 8, c->stream));
     CK(cudaMemcpyAsync(tmp, z, size_t(n) * M0 * 8, cudaMemcpyHostToDevice, c->stream));
     launch_transpose(tmp, s.z, M0, n, n, M0, c->stream);
+    CK(cudaFreeAsync(tmp, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaFree(tmp));
     return SIMPLES_OK;
 }
 
@@ -610,11 +619,11 @@ int fetch_genemajor(simples_ctx* c, const double* dev, int cols, double* host) {
 // device [rows][cols] -> host col-major rows x cols via device transpose
 int fetch_transposed(simples_ctx* c, const double* dev, int rows, int cols, int ld, double* host) {
     double* tmp = nullptr;
-    CK(cudaMalloc(&tmp, size_t(rows) * cols * 8));
+    CK(cudaMallocAsync(&tmp, size_t(rows) * cols * 8, c->stream));
     launch_transpose(dev, tmp, rows, cols, ld, rows, c->stream);
     CK(cudaMemcpyAsync(host, tmp, size_t(rows) * cols * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(tmp, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaFree(tmp));
     return SIMPLES_OK;
 }
 
