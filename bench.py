@@ -109,7 +109,7 @@ def em_kwargs(st, comm=None):
 def algorithmic(n, G, K0, M0, num_mc, rho):
     """Per-launch algorithmic bytes / flops of each hot kernel."""
     NQP = (K0 + M0 + 7) // 8 * 8
-    NVP = (K0 + 2 * M0 + 7) // 8 * 8
+    NVP = (K0 + M0 + 1 + 7) // 8 * 8
     NFP = (K0 + M0 + 1 + 7) // 8 * 8
     return {
         "estep_project": dict(bytes=8.0 * G * n, flops=2.0 * n * G * NQP + 3.0 * n * G),

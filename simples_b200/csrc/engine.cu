@@ -224,7 +224,7 @@ void set_dims(Dims& d, int G, int n, int M0, int K0, int MB, long long n_total, 
     d.NF = K0 + M0 + 1;
     d.NFP = round_up(d.NF, 8);
     d.FS = d.NFP + 4;
-    d.NV = K0 + 2 * M0;
+    d.NV = K0 + M0 + 1;
     d.NVP = round_up(d.NV, 8);
     d.VS = d.NVP + 4;
     d.n_total = n_total > 0 ? n_total : n;

@@ -255,19 +255,24 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
                     if (k0 + 1 < K0) vrow[k0 + 1] = wb[nt][1];
                 }
             }
-            double zs = 0.0;
+            double zs = 0.0, zq = 0.0;
             for (int m = t; m < M0; m += 4) {
                 const double z = zw[g * M0 + m];
                 vrow[K0 + m] = z;
-                vrow[K0 + M0 + m] = sqrt(z);
                 if (a.write_Vg) {
                     double* vg = a.Vg + size_t(cell) * VGS + K0 * M0;
                     vg[m] = z;
                     vg[M0 + m] = sqrt(z);
                 }
             }
-            for (int m = 0; m < M0; ++m) zs += zw[g * M0 + m];
-            if (t == 0) a.zsum[cell] = zs;
+            for (int m = 0; m < M0; ++m) {
+                zs += zw[g * M0 + m];
+                zq += sqrt(zw[g * M0 + m]);
+            }
+            if (t == 0) {
+                a.zsum[cell] = zs;
+                vrow[K0 + M0] = zq;        // sum_m sqrt(z_im): with cluster-shared sigma only sum_m Uh[,m] is needed
+            }
         }
 
         // ---- factor draw: f = W_im[i,] + eps Mh_im  (symmetric sqrt, as mixtools::rmvnorm) ----

@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(GW * 32) k_gene_solve(MstepArgs a) {
                 if (kl) s -= mum * sa[m * K0 + lane];
             }
             bt = rhs = s;
-            const double U = ml ? Cg[K0 + lane] : 0.0, Uh = ml ? Cg[K0 + M0 + lane] : 0.0;
+            const double U = ml ? Cg[K0 + lane] : 0.0;
             d2 = sv.R2[g] + warp_sum(-2.0 * mu * U + mu * mu * nzm);
-            sumY = warp_sum(Uh - mu * cm) / sqrt(sg0);
+            sumY = (Cg[K0 + M0] - warp_sum(mu * cm)) / sqrt(sg0);      // sum_m (Uh[g,m] - mu_gm c_m) / sqrt(sigma_g)
             sumY2 = d2 / sg0;
             var = (sumY2 - sumY * sumY / N) / (N - 1.0);
             kappa = a.penl * var * sg0;     // objective scaled by sigma_g

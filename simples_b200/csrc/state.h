@@ -9,7 +9,7 @@
 //   Qs     [ldG][FS]       sweep operand       [B*sd | mu*sd | mean | 0-pad]
 //   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  igs [ldG] = 1/sd
 //   P      [NS][n][NQP]    Y^T Q          S2 [NS][n]   sum_g Y^2/sigma_s
-//   V      [n][VS]         M-step operand [Wbar (K0) | z (M0) | sqrt z (M0) | 0-pad],  zsum [n]
+//   V      [n][VS]         M-step operand [Wbar (K0) | z (M0) | sum_m sqrt z_m (1) | 0-pad],  zsum [n]
 //   Fh     [n][FS]         sweep operand  [f_i (K0) | onehot(m_i) (M0) | 1 | 0-pad]
 //   W      [M0][n][K0]     factor posterior means (Ef)
 // ldG = G rounded up to 64; padded genes have Y = 0, mask = 0, beta = mu = 0, sigma = 1.
@@ -45,7 +45,7 @@ struct Dims {
     int NS;            // distinct sigma columns in use: 1 (cluster-shared) or M0
     int NQ, NQP, QS;   // projection cols: NQ = K0 + M0 (per sigma column), padded to 8; row stride QS = NQP + 4
     int NF, NFP, FS;   // sweep GEMM depth: NF = K0 + M0 + 1 padded to 4 (NFP); row stride FS = NFP + 4 (== 4 mod 8)
-    int NV, NVP, VS;   // M-step cols: NV = K0 + 2 M0, padded to 8; row stride VS = NVP + 4
+    int NV, NVP, VS;   // M-step cols: NV = K0 + M0 + 1, padded to 8; row stride VS = NVP + 4
     long long n_total, cell_offset;
 };
 
