@@ -174,6 +174,12 @@ SIMPLES_API int simples_em_set_profile(simples_ctx *ctx, int enable);
 SIMPLES_API int simples_em_profile(simples_ctx *ctx, int64_t *launches, double *total_ms, int cap);
 SIMPLES_API const char *simples_kernel_name(int k);
 SIMPLES_API int simples_kernel_count(void);
+/* Driver-side consumers of the EM result (R/SIMPLE.R:421-430, R/SIMPLE_B.R:429-437):
+ * Yimp0 = sum_m z_im (mu_m + B Ef_m[i,]) * geneSd + geneM  (G x n, this shard's cells) from the resident state
+ * (post-M-step mu / beta with the z / Ef of the last E-pass, exactly as the reference mixes them), and the two
+ * BIC variants from the last log-likelihood and the GLOBAL n. */
+SIMPLES_API int simples_em_yimp0(simples_ctx *ctx, double *Yimp0);
+SIMPLES_API int simples_bic(double loglik_last, int64_t n_total, int32_t G, int32_t K0, int32_t M0, double *bic, double *bic0);
 /* Number of entries with Y0 <= cutoff in this context's shard. */
 SIMPLES_API int64_t simples_em_nnz0(simples_ctx *ctx);
 /* CUDA kernels enqueued by the last simples_em_run on this context. */

@@ -34,7 +34,7 @@ __all__ = [
     "cluster_terms", "epass", "factor_means", "sample_sweep",
     "local_stats", "stats_pack", "stats_unpack", "mstep_from_stats",
     "em_impute_ref", "em_impute_fast", "do_impute_ref",
-    "simulate", "bench_state", "expected_impute",
+    "simulate", "bench_state", "expected_impute", "yimp0_ref", "bic_ref",
 ]
 
 PI_REF = 3.14159265359          # R/EM_impute.R:80, R/do_impute.R:31  (Q2)
@@ -765,3 +765,25 @@ def bench_state(sim, K0, M0, cutoff=0.1, pgv=0.6, seed=1):
     Yi[gi, ci] = gm[gi] + gs[gi] * trunc_z(rng.random(gi.shape[0]) * 0.999 + 0.0005, r)
     return dict(Y=np.asfortranarray(Yi), Y0=Y2, pg=pg, beta=beta, sigma=sigma, lam=lam, pi=pi, z=z,
                 celltype=clus.astype(np.int32))
+
+
+# ----------------------------------------------------------------------------
+# Driver-side consumers of the EM result
+# ----------------------------------------------------------------------------
+def yimp0_ref(res):
+    """R/SIMPLE.R:421-426 (= R/SIMPLE_B.R:429-434)."""
+    M0 = len(res["Ef"])
+    n = res["z"].shape[0]
+    G = res["beta"].shape[0]
+    imp = np.zeros((n, G))
+    for m in range(M0):
+        imp += (res["mu"][:, m][:, None] + res["beta"] @ res["Ef"][m].T).T * res["z"][:, m][:, None]
+    return imp.T * res["geneSd"][:, None] + res["geneM"][:, None]
+
+
+def bic_ref(loglik_tot, n, G, K0, M0):
+    """R/SIMPLE.R:429-430."""
+    bic0 = -2 * loglik_tot + math.log(n) * (2 * G * M0 + G * (K0 + 1) + K0 * (M0 - 1))
+    bic = (-2 * loglik_tot + math.log(n) * (2 * G * M0 + G) + math.log(n * G) * K0 * (M0 - 1)
+           + K0 * math.log((G * n) / (G + n)) * (G + n))
+    return bic, bic0

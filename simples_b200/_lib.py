@@ -76,6 +76,7 @@ EXPORTS = [
     "simples_em_impute", "simples_do_impute", "simples_em_create", "simples_em_run", "simples_em_fetch",
     "simples_em_sync", "simples_em_iter_ms", "simples_em_set_profile", "simples_em_profile",
     "simples_kernel_name", "simples_kernel_count", "simples_em_nnz0", "simples_em_kernel_launches",
+    "simples_em_yimp0", "simples_bic",
     "simples_ctx_destroy",
 ]
 
@@ -111,6 +112,8 @@ def load():
     lib.simples_em_nnz0.restype = C.c_int64
     lib.simples_em_kernel_launches.argtypes = [C.c_void_p]
     lib.simples_em_kernel_launches.restype = C.c_int64
+    lib.simples_em_yimp0.argtypes = [C.c_void_p, C.c_void_p]
+    lib.simples_bic.argtypes = [C.c_double, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p]
     lib.simples_ctx_destroy.argtypes = [C.c_void_p]
     lib.simples_ctx_destroy.restype = None
     _lib = lib

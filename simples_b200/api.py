@@ -208,6 +208,13 @@ class EMContext:
         check(self._lib.simples_em_fetch(self._h, C.byref(o)))
         return _em_result(bufs, self.M0, self.iters_done)
 
+    def yimp0(self, out=None):
+        """``Yimp0`` of SIMPLE()/SIMPLE_B() (R/SIMPLE.R:421-426) for this shard, G x n."""
+        if out is None:
+            out = np.empty((self.G, self.n), order="F")
+        check(self._lib.simples_em_yimp0(self._h, _ptr(out)))
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.simples_ctx_destroy(self._h)
@@ -276,3 +283,10 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
     check(rc)
     return {"loglik": float(bufs["loglik"][0]), "impt": bufs["impt"], "impt_var": bufs["impt_var"], "EF": bufs["EF"],
             "varF": bufs["varF"], "consensus_cluster": bufs["consensus_cluster"]}
+
+
+def bic(loglik_last, n, G, K0, M0):
+    """(BIC, BIC0) of SIMPLE()/SIMPLE_B() (R/SIMPLE.R:429-430); ``n`` is the global number of cells."""
+    b, b0 = C.c_double(), C.c_double()
+    check(_lib.load().simples_bic(float(loglik_last), int(n), int(G), int(K0), int(M0), C.byref(b), C.byref(b0)))
+    return b.value, b0.value

@@ -867,6 +867,27 @@ int simples_em_fetch(simples_ctx* c, simples_em_out* o) {
     return SIMPLES_OK;
 }
 
+int simples_em_yimp0(simples_ctx* c, double* out) {
+    if (!c || !out || c->kind != 0) return fail(SIMPLES_EINVAL, "not an EM context");
+    if (c->it < 1) return fail(SIMPLES_EINVAL, "simples_em_yimp0 needs at least one completed EM iteration");
+    CKR(simples_em_sync(c));
+    DevState& s = c->s;
+    const Dims& d = s.d;
+    return fetch_big(c, out, [&](double* dst, size_t c0, size_t nc) {
+        launch_yimp0(d, s.mu, s.beta, s.z, s.V, s.gmean, s.gsd, dst, int(c0), int(nc), c->stream);
+    });
+}
+
+int simples_bic(double loglik_last, int64_t n, int32_t G, int32_t K0, int32_t M0, double* bic, double* bic0) {
+    if (n < 1 || G < 1) return fail(SIMPLES_EINVAL, "n and G must be >= 1");
+    const double dn = double(n), dG = double(G);
+    if (bic0) *bic0 = -2.0 * loglik_last + std::log(dn) * (2.0 * dG * M0 + dG * (K0 + 1) + K0 * (M0 - 1));      // R/SIMPLE.R:429
+    if (bic)                                                                                                    // R/SIMPLE.R:430
+        *bic = -2.0 * loglik_last + std::log(dn) * (2.0 * dG * M0 + dG) + std::log(dn * dG) * K0 * (M0 - 1) +
+               K0 * std::log((dG * dn) / (dG + dn)) * (dG + dn);
+    return SIMPLES_OK;
+}
+
 int simples_em_impute(const simples_em_args* a, simples_em_out* o) {
     using clk = std::chrono::steady_clock;
     const bool trace = getenv("SIMPLES_TRACE") != nullptr;

@@ -138,6 +138,40 @@ __global__ void k_consensus(const double* z, double* cons, int n, int M0) {
     cons[size_t(j) * n + i] += s;   // symmetric; column-major n x n
 }
 
+// Yimp0 chunk (R/SIMPLE.R:421-426): out[i][g] = (sum_m mu[g,m] z[i,m] + sum_k beta[g,k] Wbar[i,k]) gsd[g] + gmean[g],
+// Wbar_i = sum_m z_im Ef_m[i,] (first K0 columns of the M-step operand row V_i).
+__global__ void k_yimp0(Dims d, const double* mu, const double* beta, const double* z, const double* V, const double* gmean,
+                        const double* gsd, double* out, int cell0, int ncell) {
+    extern __shared__ double sh[];          // [8][M0 + K0]
+    const int M0 = d.M0, K0 = d.K0, W = M0 + K0;
+    const int c0 = blockIdx.y * 8;
+    for (int idx = threadIdx.x; idx < 8 * W; idx += blockDim.x) {
+        const int r = idx / W, c = idx - r * W;
+        const int cell = cell0 + c0 + r;
+        double v = 0.0;
+        if (c0 + r < ncell) v = (c < M0) ? z[size_t(cell) * M0 + c] : V[size_t(cell) * d.VS + (c - M0)];
+        sh[idx] = v;
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.G) return;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < M0; ++m) {
+        const double a = mu[size_t(g) * M0 + m];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fma(a, sh[r * W + m], acc[r]);
+    }
+    for (int k = 0; k < K0; ++k) {
+        const double b = beta[size_t(g) * K0 + k];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fma(b, sh[r * W + M0 + k], acc[r]);
+    }
+    const double sd = gsd[g], mean = gmean[g];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (c0 + r < ncell) out[size_t(c0 + r) * d.G + g] = acc[r] * sd + mean;
+}
+
 inline int gs_grid(size_t total) {
     size_t g = (total + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
@@ -181,6 +215,11 @@ void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec
 void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
                               double* rVF, cudaStream_t st) {
     k_mi_record_factors<<<gs_grid(size_t(d.n) * d.K0), 256, 0, st>>>(d, W, z, Mm, rEF, rF2, rVF);
+}
+void launch_yimp0(const Dims& d, const double* mu, const double* beta, const double* z, const double* V, const double* gmean,
+                  const double* gsd, double* out, int cell0, int ncell, cudaStream_t st) {
+    dim3 grid((d.G + 127) / 128, (ncell + 7) / 8);
+    k_yimp0<<<grid, 128, sizeof(double) * 8 * (d.M0 + d.K0), st>>>(d, mu, beta, z, V, gmean, gsd, out, cell0, ncell);
 }
 void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t st) {
     dim3 grid((n + 15) / 16, (n + 15) / 16), block(16, 16);

@@ -200,3 +200,32 @@ def test_full_size_properties(sb):
          out["sigma"], out["lambda"], out["pi"], out["z"][sl])
     kw1 = dict(celltype=st["celltype"][sl], est_z=1, est_lam=1, impt_it=5, mu=out["mu"])
     assert_em_close(sb.EM_impute(*a, **kw1), O.em_impute_fast(*a, **kw1), M0)
+
+
+def test_yimp0_and_bic(sb):
+    """Yimp0 and BIC / BIC0 of the drivers (R/SIMPLE.R:421-430) from the resident EM state."""
+    K0, M0 = 5, 3
+    st = make_case(210, 170, 3, 3, K0, M0, seed=14)
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=4)
+    ref = O.em_impute_fast(*em_args(st, M0, K0, 3), **kw)
+    with sb.EMContext(st["Y"], st["Y0"], st["pg"], M0, K0, 0.1, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"],
+                      iter=3, **kw) as ctx:
+        ctx.run(3)
+        got = ctx.yimp0()
+        ll = ctx.fetch(big=False)["loglik"]
+    assert rel(got, O.yimp0_ref(ref)) <= 1e-8
+    G, n = st["Y"].shape
+    b, b0 = sb.bic(ll[-1], n, G, K0, M0)
+    rb, rb0 = O.bic_ref(ref["loglik"][-1], n, G, K0, M0)
+    assert abs(b - rb) <= 1e-10 * abs(rb) and abs(b0 - rb0) <= 1e-10 * abs(rb0)
+
+
+def test_c4_shape_slice(sb):
+    """BASELINE.json configs[3] shape (G = 5000 genes, K0 = M0 = 20) on a slice of cells: exercises ldG = 5056
+    (79 gene tiles), NQP = 40, NVP = 48, NFP = 48 template variants against the oracle."""
+    K0, M0 = 20, 20
+    st = make_case(2500, 5000, 20, 20, K0, M0, seed=15)
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=8, num_mc=2)
+    ref = O.em_impute_fast(*em_args(st, M0, K0, 3), **kw)
+    got = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
+    assert_em_close(got, ref, M0)
