@@ -570,7 +570,7 @@ def _mstep_literal(Yc, z, Wm, Ms, nz, beta, sigma, lam, mu, M0, K0, it, penl, ma
 
 def _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
                est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
-               seed, compat, literal, shards=None, trace=None):
+               seed, compat, literal, shards=None, trace=None, cell0=0):
     pi_const = PI_REF if compat & COMPAT_PI else math.pi
     z = None if z is None else np.array(z, dtype=np.float64)
     Yc, gene_mean, gene_sd, mu = _prologue(Y, z, mu, M0, lower, upper, compat)
@@ -599,7 +599,7 @@ def _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, cel
         if it >= impt_it + 1:                                                # :161
             for _ in range(num_mc):                                          # :162
                 sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, gene_mean,
-                             gene_sd, cutoff, seed, sweep, 0, draw_membership=(M0 > 1),
+                             gene_sd, cutoff, seed, sweep, cell0, draw_membership=(M0 > 1),
                              lower=lower, upper=upper, clip=True)
                 sweep += 1
                 if compat & COMPAT_STALE_DT:                                 # :202-213  (Q1)
@@ -646,12 +646,12 @@ def em_impute_ref(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=N
 def em_impute_fast(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=None, celltype=None,
                    penl=1, est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1,
                    num_mc=3, lower=-np.inf, upper=np.inf, seed=0, compat=COMPAT_DEFAULT,
-                   shards=None, trace=None):
+                   shards=None, trace=None, cell0=0):
     """Same algorithm with the sufficient-statistic M-step; ``shards`` = list of
     cell boundaries emulating the multi-GPU partition + all-reduce."""
     return _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
                       est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
-                      seed, compat, literal=False, shards=shards, trace=trace)
+                      seed, compat, literal=False, shards=shards, trace=trace, cell0=cell0)
 
 
 # ----------------------------------------------------------------------------

@@ -229,3 +229,30 @@ def test_c4_shape_slice(sb):
     ref = O.em_impute_fast(*em_args(st, M0, K0, 3), **kw)
     got = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
     assert_em_close(got, ref, M0)
+
+
+class _SoloShard:
+    """Single-rank stand-in for simples_b200.dist.CellShard: exercises n_total / cell_offset / the
+    all-reduce callback plumbing of the C ABI without a process group."""
+
+    def __init__(self, n_total, cell_offset):
+        self.n_total, self.cell_offset, self.calls = n_total, cell_offset, 0
+
+    def allreduce_sum_(self, ptr, count, stream=None):
+        self.calls += 1          # sum over one rank = identity
+
+
+def test_global_cell_index_64bit_and_seed_hi(sb):
+    """The Philox counter carries the GLOBAL cell index (64 bit) and the key the full 64-bit seed."""
+    K0, M0 = 4, 3
+    st = make_case(200, 150, 3, 3, K0, M0, seed=16)
+    off = 2**33 + 7
+    seed = (0xA5A5A5A5 << 32) | 0x1234567
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=seed)
+    sh = _SoloShard(st["Y"].shape[1], off)
+    got = sb.EM_impute(*em_args(st, M0, K0, 3), comm=sh, **kw)
+    ref = O.em_impute_fast(*em_args(st, M0, K0, 3), cell0=off, **kw)
+    assert_em_close(got, ref, M0)
+    assert sh.calls == 2 + 3        # gene means, default mu, one per EM iteration
+    other = O.em_impute_fast(*em_args(st, M0, K0, 3), cell0=7, **kw)
+    assert rel(other["Y"], ref["Y"]) > 1e-3       # the high word really changes the stream
