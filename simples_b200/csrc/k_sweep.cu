@@ -198,22 +198,74 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
                 a.rec2[o] += v * v;
             }
         };
-        // ---- 3b. certain dropouts, central quantile: x = ms + sds Phi^-1(ub)   (R/EM_impute.R:186) ----
+        // ---- 3b. T-stage: for the certain "expressed but <= cutoff" entries of the back list compute the quantile
+        //      argument ub * Phi(r) (the only place the FP64 pnorm runs) and re-file them by quantile region:
+        //      central -> appended to the Dc list, tail -> compacted back list.  Stored value < 0 marks a
+        //      truncated draw (clamped to the cutoff, R/EM_impute.R:191-192).
+        int nTail = 0;
+        {
+            const int srounds = (nS + 31) >> 5;
+#pragma unroll 1
+            for (int it = 0; it < srounds; ++it) {
+                const int e = it * 32 + lane;
+                const bool valid = e < nS;
+                const int code = valid ? dcode[255 - e] : 0;
+                const double v = valid ? dub[255 - e] : 1.0;
+                const int r = code >> 5, gl = code & 31;
+                const int im = cellinfo[r * 2];
+                const bool isT = v < 0.0;
+                double arg = v;                      // tail-quantile dropout: stays a tail entry as it is
+                bool toC = false, toTail = valid;
+                if (isT) {
+                    const double ms = msW[r * MSS + gl];
+                    const double rr = (a.cutoff - ms) * b.isd[gl * M0 + im];
+                    if (rr < -30.0) {                // deep tail: log-space Newton, finished right here (cold)
+                        finish(r, gl, fma(b.sds[gl * M0 + im], trunc_z_deep(-v, rr), ms));
+                        toTail = false;
+                    } else {
+                        const double q = -v * pnorm(rr);
+                        arg = -q;
+                        toC = fabs(q - 0.5) <= 0.425;
+                        toTail = !toC;
+                    }
+                }
+                __syncwarp();                        // every lane has read its slot before slots are rewritten
+                const unsigned bC = __ballot_sync(0xffffffffu, toC);
+                const unsigned bT = __ballot_sync(0xffffffffu, toTail);
+                const unsigned lt = (1u << lane) - 1u;
+                if (toC) {
+                    const int pos = nDc + __popc(bC & lt);
+                    dcode[pos] = (unsigned char)code;
+                    dub[pos] = arg;
+                } else if (toTail) {
+                    const int pos = 255 - (nTail + __popc(bT & lt));
+                    dcode[pos] = (unsigned char)code;
+                    dub[pos] = arg;
+                }
+                nDc += __popc(bC);
+                nTail += __popc(bT);
+                __syncwarp();
+            }
+        }
+        // ---- 3c. central quantiles: x = ms + sds Phi^-1(arg)   (R/EM_impute.R:186 / :191-192) ----
 #pragma unroll 1
         for (int e = lane; e < nDc; e += 32) {
             const int code = dcode[e];
+            const double v = dub[e];
             const int r = code >> 5, gl = code & 31;
-            const double z = qnorm_central(dub[e]);
-            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], z, msW[r * MSS + gl]));
+            double x = fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_central(fabs(v)), msW[r * MSS + gl]);
+            if (v < 0.0) x = fmin(x, a.cutoff);
+            finish(r, gl, x);
         }
-        // ---- 3c. slow list: tail-quantile dropouts and certain truncated-normal draws (R/EM_impute.R:191-192) ----
+        // ---- 3c'. tail quantiles ----
 #pragma unroll 1
-        for (int e = lane; e < nS; e += 32) {
+        for (int e = lane; e < nTail; e += 32) {
             const int code = dcode[255 - e];
             const double v = dub[255 - e];
             const int r = code >> 5, gl = code & 31;
-            const int im = cellinfo[r * 2];
-            finish(r, gl, sample_slow(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], a.cutoff, v));
+            double x = fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_tail(fabs(v)), msW[r * MSS + gl]);
+            if (v < 0.0) x = fmin(x, a.cutoff);
+            finish(r, gl, x);
         }
         // ---- 3d. inside the screening band: exact FP64 Bernoulli test and draw ----
 #pragma unroll 1
