@@ -58,24 +58,32 @@ __device__ __forceinline__ void load_chunk(const SweepArgs& a, const ChunkBuf& b
     cp_async_commit();
 }
 
+template <bool FREG>
 __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB, ldG = a.d.ldG, n = a.d.n;
     const int KST = a.d.NFP / 4;
     const int CD = chunk_doubles(FS, M0, MB);
-    double* sF = sm;                                 // [SC][FS]
-    double* sMs = sF + SC * FS;                      // [SW][8][MSS]
-    double* sBuf = sMs + SW * 8 * MSS;               // [CD]  (single buffer: 3 CTAs / SM hide the refill)
-    double* sDub = sBuf + CD;                    // [SW][256]  value uniforms of the certain-dropout lists
+    double* sF = sm;                                 // [SC][FS]  (only when the Fh fragments do not fit registers)
+    double* sMs = sF + (FREG ? 0 : SC * FS);         // [SW][8][MSS]
+    double* sBuf = sMs + SW * 8 * MSS;               // [2][CD]  double-buffered gene-chunk parameters
+    double* sDub = sBuf + 2 * CD;                    // [SW][256]  value uniforms of the certain-dropout lists
     unsigned char* sList = reinterpret_cast<unsigned char*>(sDub + SW * 256);   // [SW][3][256]  all / D / X entry codes
     int* sCell = reinterpret_cast<int*>(sList + SW * 768);                      // [SW][8][2]  (im, celltype)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cell0 = blockIdx.x * SC;
     const int wc0 = cell0 + warp * 8;           // first cell of this warp
-    for (int idx = tid; idx < SC * FS; idx += blockDim.x) {
-        const int r = idx / FS, c = idx - r * FS;
-        sF[idx] = (cell0 + r < n) ? a.Fh[size_t(cell0 + r) * FS + c] : 0.0;
+    double fr[6];                                     // FREG: A-fragments Fh[cell g][4 ks + t], NFP <= 24
+    if (FREG) {
+        const int cell = wc0 + g;
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) fr[ks] = (ks < KST && cell < n) ? a.Fh[size_t(cell) * FS + ks * 4 + t] : 0.0;
+    } else {
+        for (int idx = tid; idx < SC * FS; idx += blockDim.x) {
+            const int r = idx / FS, c = idx - r * FS;
+            sF[idx] = (cell0 + r < n) ? a.Fh[size_t(cell0 + r) * FS + c] : 0.0;
+        }
     }
     if (lane < 8) {
         const int cell = wc0 + lane;
@@ -83,6 +91,7 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         sCell[(warp * 8 + lane) * 2 + 1] = cell < n ? a.celltype0[cell] : 0;
     }
     const int nchunks = ldG / SG;
+    load_chunk(a, chunk_buf(sBuf, FS, M0, MB), 0, tid, blockDim.x);
 
     double* msW = sMs + warp * 8 * MSS;
     unsigned char* list = sList + warp * 768;
@@ -93,11 +102,10 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     const double* fa = sF + (warp * 8 + g) * FS + t;
 
     for (int chunk = 0; chunk < nchunks; ++chunk) {
-        __syncthreads();                               // every warp is done with the previous chunk's parameters
-        const ChunkBuf b = chunk_buf(sBuf, FS, M0, MB);
-        load_chunk(a, b, chunk, tid, blockDim.x);
         cp_async_wait_all();
-        __syncthreads();                               // chunk's parameters visible
+        __syncthreads();                               // chunk's parameters visible; the other buffer is free
+        if (chunk + 1 < nchunks) load_chunk(a, chunk_buf(sBuf + ((chunk + 1) & 1) * CD, FS, M0, MB), chunk + 1, tid, blockDim.x);
+        const ChunkBuf b = chunk_buf(sBuf + (chunk & 1) * CD, FS, M0, MB);
 
         // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes)
         unsigned word = 0u;
@@ -108,10 +116,20 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         double acc[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-        for (int ks = 0; ks < KST; ++ks) {
-            const double av = fa[ks * 4];
+        if (FREG) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], av, b.Q[(nt * 8 + g) * FS + ks * 4 + t]);
+            for (int ks = 0; ks < 6; ++ks) {
+                if (ks < KST) {
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], fr[ks], b.Q[(nt * 8 + g) * FS + ks * 4 + t]);
+                }
+            }
+        } else {
+            for (int ks = 0; ks < KST; ++ks) {
+                const double av = fa[ks * 4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], av, b.Q[(nt * 8 + g) * FS + ks * 4 + t]);
+            }
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
@@ -285,15 +303,25 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
 }  // namespace
 
 void launch_sweep(const SweepArgs& a, cudaStream_t st) {
-    const size_t smem = sizeof(double) * (size_t(SC) * a.d.FS + size_t(SW) * 8 * MSS + chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
+    const bool freg = a.d.NFP <= 24;
+    const size_t smem = sizeof(double) * ((freg ? 0 : size_t(SC) * a.d.FS) + size_t(SW) * 8 * MSS +
+                                          2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
                         SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
-    }
     const int grid = (a.d.n + SC - 1) / SC;
-    k_sweep<<<grid, SW * 32, smem, st>>>(a);
+    static size_t attr[2] = {0, 0};
+    if (freg) {
+        if (smem > 48 * 1024 && smem > attr[0]) {
+            cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            attr[0] = smem;
+        }
+        k_sweep<true><<<grid, SW * 32, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024 && smem > attr[1]) {
+            cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            attr[1] = smem;
+        }
+        k_sweep<false><<<grid, SW * 32, smem, st>>>(a);
+    }
 }
 
 }  // namespace sb
