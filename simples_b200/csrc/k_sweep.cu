@@ -58,6 +58,18 @@ __device__ __forceinline__ void load_chunk(const SweepArgs& a, const ChunkBuf& b
     cp_async_commit();
 }
 
+// one thread: TMA bulk copies of the six parameter spans of gene chunk `chunk`, completing on `bar`
+__device__ __forceinline__ void load_chunk_bulk(const SweepArgs& a, const ChunkBuf& b, int chunk, uint64_t* bar) {
+    const int g0 = chunk * SG, FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB;
+    mbar_arrive_expect_tx(bar, uint32_t(chunk_doubles(FS, M0, MB)) * 8u);
+    bulk_g2s(b.Q, a.Qs + size_t(g0) * FS, SG * FS * 8, bar);
+    bulk_g2s(b.sds, a.sdsA + size_t(g0) * M0, SG * M0 * 8, bar);
+    bulk_g2s(b.isd, a.isdA + size_t(g0) * M0, SG * M0 * 8, bar);
+    bulk_g2s(b.pg, a.pg + size_t(g0) * MB, SG * MB * 8, bar);
+    bulk_g2s(b.gm, a.gmean + g0, SG * 8, bar);
+    bulk_g2s(b.igs, a.igs + g0, SG * 8, bar);
+}
+
 template <bool FREG>
 __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     extern __shared__ __align__(16) double sm[];
@@ -70,6 +82,7 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     double* sDub = sBuf + 2 * CD;                    // [SW][256]  value uniforms of the certain-dropout lists
     unsigned char* sList = reinterpret_cast<unsigned char*>(sDub + SW * 256);   // [SW][3][256]  all / D / X entry codes
     int* sCell = reinterpret_cast<int*>(sList + SW * 768);                      // [SW][8][2]  (im, celltype)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sCell + SW * 16);              // full[2], empty[2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cell0 = blockIdx.x * SC;
@@ -91,7 +104,18 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         sCell[(warp * 8 + lane) * 2 + 1] = cell < n ? a.celltype0[cell] : 0;
     }
     const int nchunks = ldG / SG;
-    load_chunk(a, chunk_buf(sBuf, FS, M0, MB), 0, tid, blockDim.x);
+    // Parameter pipeline: two buffers with full / empty mbarriers.  Warps are NOT barrier-synchronised per chunk:
+    // a warp starts chunk c as soon as full[c & 1] has completed; thread 0 refills a buffer once all 8 warps have
+    // released it (the warps of a CTA drift by at most one chunk).
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], SW);
+        mbar_init(&bars[3], SW);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) load_chunk_bulk(a, chunk_buf(sBuf, FS, M0, MB), 0, &bars[0]);
 
     double* msW = sMs + warp * 8 * MSS;
     unsigned char* list = sList + warp * 768;
@@ -102,15 +126,22 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     const double* fa = sF + (warp * 8 + g) * FS + t;
 
     for (int chunk = 0; chunk < nchunks; ++chunk) {
-        cp_async_wait_all();
-        __syncthreads();                               // chunk's parameters visible; the other buffer is free
-        if (chunk + 1 < nchunks) load_chunk(a, chunk_buf(sBuf + ((chunk + 1) & 1) * CD, FS, M0, MB), chunk + 1, tid, blockDim.x);
-        const ChunkBuf b = chunk_buf(sBuf + (chunk & 1) * CD, FS, M0, MB);
+        const int sb_ = chunk & 1;
+        if (tid == 0 && chunk + 1 < nchunks) {         // refill the other buffer for chunk + 1
+            if (chunk >= 1) mbar_wait(&bars[2 + (sb_ ^ 1)], ((chunk - 1) >> 1) & 1);
+            load_chunk_bulk(a, chunk_buf(sBuf + (sb_ ^ 1) * CD, FS, M0, MB), chunk + 1, &bars[sb_ ^ 1]);
+        }
+        __syncwarp();
+        mbar_wait(&bars[sb_], (chunk >> 1) & 1);        // this chunk's parameters have landed
+        const ChunkBuf b = chunk_buf(sBuf + sb_ * CD, FS, M0, MB);
 
         // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes)
         unsigned word = 0u;
         if (lane < 8 && wc0 + lane < n) word = a.mask[size_t(chunk) * a.n_alloc + wc0 + lane];
-        if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;
+        if (__ballot_sync(0xffffffffu, word != 0u) == 0u) {
+            if (lane == 0) mbar_arrive(&bars[2 + sb_]);
+            continue;
+        }
 
         // ---- 1. conditional means of the 8 x 32 block ----
         double acc[4][2];
@@ -297,6 +328,7 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
                                        a.cutoff, ua, ub));
         }
         __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 + sb_]);     // this warp no longer reads the chunk's parameters
     }
 }
 
@@ -306,7 +338,7 @@ void launch_sweep(const SweepArgs& a, cudaStream_t st) {
     const bool freg = a.d.NFP <= 24;
     const size_t smem = sizeof(double) * ((freg ? 0 : size_t(SC) * a.d.FS) + size_t(SW) * 8 * MSS +
                                           2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
-                        SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int);
+                        SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int) + 64;
     const int grid = (a.d.n + SC - 1) / SC;
     static size_t attr[2] = {0, 0};
     if (freg) {
