@@ -9,6 +9,8 @@
 //   3. each list entry draws from the Philox tape and writes the centred value to Y.
 // Gene-chunk parameters (Qs, sds, 1/sds, pg, mean, 1/sd) are double-buffered in shared memory with
 // cp.async.
+#include <cmath>
+
 #include "ptx.cuh"
 #include "rng.cuh"
 #include "state.h"
@@ -103,7 +105,11 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         sCell[(warp * 8 + lane) * 2 + 0] = cell < n ? a.im[cell] : 0;
         sCell[(warp * 8 + lane) * 2 + 1] = cell < n ? a.celltype0[cell] : 0;
     }
-    const int nchunks = ldG / SG;
+    // gridDim.y splits the gene range (wave-quantisation fix: more, smaller CTAs); this CTA walks chunks [cbeg, cend)
+    const int nchunks_all = ldG / SG;
+    const int cbeg = int((long long)nchunks_all * blockIdx.y / gridDim.y);
+    const int cend = int((long long)nchunks_all * (blockIdx.y + 1) / gridDim.y);
+    const int nchunks = cend - cbeg;
     // Parameter pipeline: two buffers with full / empty mbarriers.  Warps are NOT barrier-synchronised per chunk:
     // a warp starts chunk c as soon as full[c & 1] has completed; thread 0 refills a buffer once all 8 warps have
     // released it (the warps of a CTA drift by at most one chunk).
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) load_chunk_bulk(a, chunk_buf(sBuf, FS, M0, MB), 0, &bars[0]);
+    if (tid == 0 && nchunks > 0) load_chunk_bulk(a, chunk_buf(sBuf, FS, M0, MB), cbeg, &bars[0]);
 
     double* msW = sMs + warp * 8 * MSS;
     unsigned char* list = sList + warp * 768;
@@ -125,14 +131,15 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     const int* cellinfo = sCell + warp * 16;
     const double* fa = sF + (warp * 8 + g) * FS + t;
 
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int sb_ = chunk & 1;
-        if (tid == 0 && chunk + 1 < nchunks) {         // refill the other buffer for chunk + 1
-            if (chunk >= 1) mbar_wait(&bars[2 + (sb_ ^ 1)], ((chunk - 1) >> 1) & 1);
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int chunk = cbeg + ci;                   // absolute gene-chunk index
+        const int sb_ = ci & 1;
+        if (tid == 0 && ci + 1 < nchunks) {            // refill the other buffer for the next chunk
+            if (ci >= 1) mbar_wait(&bars[2 + (sb_ ^ 1)], ((ci - 1) >> 1) & 1);
             load_chunk_bulk(a, chunk_buf(sBuf + (sb_ ^ 1) * CD, FS, M0, MB), chunk + 1, &bars[sb_ ^ 1]);
         }
         __syncwarp();
-        mbar_wait(&bars[sb_], (chunk >> 1) & 1);        // this chunk's parameters have landed
+        mbar_wait(&bars[sb_], (ci >> 1) & 1);           // this chunk's parameters have landed
         const ChunkBuf b = chunk_buf(sBuf + sb_ * CD, FS, M0, MB);
 
         // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes)
@@ -339,7 +346,20 @@ void launch_sweep(const SweepArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(double) * ((freg ? 0 : size_t(SC) * a.d.FS) + size_t(SW) * 8 * MSS +
                                           2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
                         SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int) + 64;
-    const int grid = (a.d.n + SC - 1) / SC;
+    const int tiles = (a.d.n + SC - 1) / SC;
+    // pick the gene split (1..4) that minimises wave quantisation for ~3 resident CTAs per SM
+    int gsplit = 1;
+    {
+        const double slots = 3.0 * NUM_SMS_B200;
+        double best = 1e30;
+        for (int gsp = 1; gsp <= 4; ++gsp) {
+            if ((a.d.ldG / SG) / gsp < 8) break;
+            const double w = tiles * double(gsp) / slots;
+            const double loss = std::ceil(w) / w + 0.01 * gsp;      // small penalty for per-CTA start-up
+            if (loss < best) { best = loss; gsplit = gsp; }
+        }
+    }
+    const dim3 grid(tiles, gsplit);
     static size_t attr[2] = {0, 0};
     if (freg) {
         if (smem > 48 * 1024 && smem > attr[0]) {
