@@ -72,8 +72,10 @@ __device__ __forceinline__ double fast_rcp(double y) {
     return r;
 }
 
-// exp(h) for -700 < h <= 0 (no overflow / denormal handling needed on this range): 2^k * e^r.
+// exp(h) for h <= 0: 2^k * e^r with the exponent patched in directly; below -700 (denormal / underflow
+// territory, only reached from the cold |x| > 8 pnorm path) it defers to the library exp.
 __device__ __forceinline__ double exp_neg(double h) {
+    if (h < -700.0) return exp(h);
     const double MAGIC = 6755399441055744.0;                    // 1.5 * 2^52: round-to-nearest-integer trick
     const double t = fma(h, 1.4426950408889634074, MAGIC);
     const double kd = t - MAGIC;

@@ -256,3 +256,23 @@ def test_global_cell_index_64bit_and_seed_hi(sb):
     assert sh.calls == 2 + 3        # gene means, default mu, one per EM iteration
     other = O.em_impute_fast(*em_args(st, M0, K0, 3), cell0=7, **kw)
     assert rel(other["Y"], ref["Y"]) > 1e-3       # the high word really changes the stream
+
+
+def test_extreme_tails_and_degenerate_dropout_prior(sb):
+    """pg = 1 (no dropout possible: every zero is a truncated-normal draw), pg = 0.99, and genes whose mean sits
+    40-80 sd above the cutoff (r << -30: log-space Newton branch of the truncated quantile, cold pnorm tails)."""
+    K0, M0 = 4, 3
+    st = make_case(260, 160, 3, 3, K0, M0, seed=18)
+    pg = st["pg"].copy()
+    pg[:6] = 1.0
+    pg[6:12] = 0.99
+    pg[12:18] = 1e-3
+    Y = np.array(st["Y"])
+    Y[:4] += 25.0            # huge expression with small noise => (cutoff - ms) / sds << -30 at the zero entries
+    Y[20:24] -= 30.0         # far below the cutoff => r >> 8
+    st = dict(st, pg=pg, Y=np.asfortranarray(Y), sigma=np.full_like(st["sigma"], 0.3))
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=21, num_mc=2)
+    ref = O.em_impute_fast(*em_args(st, M0, K0, 3), **kw)
+    got = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
+    assert np.all(np.isfinite(got["Y"])) and np.all(np.isfinite(ref["Y"]))
+    assert_em_close(got, ref, M0)
