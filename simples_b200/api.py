@@ -235,7 +235,7 @@ class EMContext:
 
 def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, celltype=None, mcmc=10, burnin=2,
               verbose=False, pg=0.5, cutoff=0.1, *, seed=0, ref_compat=COMPAT_DEFAULT, consensus=True, comm=None,
-              stream=None):
+              stream=None, out=None):
     """Multiple imputation at fixed parameters on B200 -- drop-in for
     ``do_impute`` (R/do_impute.R:29-160).  Returns loglik, impt, impt_var, EF,
     varF, consensus_cluster.  ``consensus=False`` (or sharded cells) returns
@@ -271,9 +271,15 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
         cw = _Comm(comm)
         a.n_total, a.cell_offset, a.allreduce = int(comm.n_total), int(comm.cell_offset), cw.cb
     a.stream = stream
-    bufs = dict(loglik=np.zeros(1), impt=np.zeros((G, n), order="F"), impt_var=np.zeros((G, n), order="F"),
+    out = out or {}
+    bufs = dict(loglik=np.zeros(1),
+                impt=out.get("impt") if out.get("impt") is not None else np.empty((G, n), order="F"),
+                impt_var=out.get("impt_var") if out.get("impt_var") is not None else np.empty((G, n), order="F"),
                 EF=np.zeros((n, K0), order="F"), varF=np.zeros((n, K0), order="F"),
                 consensus_cluster=np.zeros((n, n), order="F") if want_cons else None)
+    for k in ("impt", "impt_var"):
+        if bufs[k].shape != (G, n) or not bufs[k].flags.f_contiguous or bufs[k].dtype != np.float64:
+            raise ValueError(f"out[{k!r}] must be a float64 F-ordered {G} x {n} array")
     o = MiOut()
     for k, v in bufs.items():
         setattr(o, k, _ptr(v))

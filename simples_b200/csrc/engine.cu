@@ -965,6 +965,10 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     if (a->want_consensus && o->consensus_cluster) CKR(c->dalloc(&c->cons, size_t(n) * n));
     const double pi_const = (c->compat & SIMPLES_COMPAT_PI) ? 3.14159265359 : M_PI;
 
+    using clk_mi = std::chrono::steady_clock;
+    const bool trace_mi = getenv("SIMPLES_TRACE") != nullptr;
+    if (trace_mi) cudaStreamSynchronize(c->stream);
+    const auto tm0 = clk_mi::now();
     CKR(run_prep(c));   // parameters are fixed: cluster constants computed once, not per sweep
     for (int it = 1; it <= nit; ++it) {                                       // :67
         const bool rec = it > a->burnin;
@@ -978,6 +982,10 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     CK(cudaGetLastError());
     CKR(allreduce(c, c->tot_mi, size_t(nit) * (2 * M0 + 1)));
     CK(cudaStreamSynchronize(c->stream));
+    if (trace_mi)
+        fprintf(stderr, "[simples_b200] do_impute: %d sweeps on device %.1f ms (%.2f ms/sweep), nnz0 %lld\n", nit,
+                std::chrono::duration<double, std::milli>(clk_mi::now() - tm0).count(),
+                std::chrono::duration<double, std::milli>(clk_mi::now() - tm0).count() / nit, c->nnz0);
 
     // ---- outputs (R/do_impute.R:156-159) ----
     if (o->loglik) {
