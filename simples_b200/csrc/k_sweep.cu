@@ -78,14 +78,14 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     const int FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB, ldG = a.d.ldG, n = a.d.n;
     const int KST = a.d.NFP / 4;
     const int CD = chunk_doubles(FS, M0, MB);
-    double* sF = sm;                                 // [SC][FS]  (only when the Fh fragments do not fit registers)
-    double* sMs = sF + (FREG ? 0 : SC * FS);         // [SW][8][MSS]
-    double* sBuf = sMs + SW * 8 * MSS;               // [2][CD]  double-buffered gene-chunk parameters
-    double* sDub = sBuf + 2 * CD;                    // [SW][256]  value uniforms of the certain-dropout lists
-    unsigned char* sList = reinterpret_cast<unsigned char*>(sDub + SW * 256);   // [SW][3][256]  all / D / X entry codes
-    int* sCell = reinterpret_cast<int*>(sList + SW * 768);                      // [SW][8][2]  (im, celltype)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sCell + SW * 16);              // full[2], empty[2]
-
+    // Shared-memory layout: fixed-size blocks first (barriers, then one statically laid out block per warp) so that
+    // all per-warp addressing is `warp base + compile-time offset`; the runtime-sized parameter buffers follow.
+    constexpr int WBLK = 8 * MSS * 8 + 256 * 8 + 768 + 64;      // bytes per warp: ms tile | dub | codes | cell info
+    unsigned char* smb = reinterpret_cast<unsigned char*>(sm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smb);                            // full[2], empty[2]
+    unsigned char* wblk = smb + 64 + (threadIdx.x >> 5) * WBLK;
+    double* sBuf = reinterpret_cast<double*>(smb + 64 + SW * WBLK);               // [2][CD] parameter chunks
+    double* sF = sBuf + 2 * CD;                                                    // [SC][FS] (only when !FREG)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cell0 = blockIdx.x * SC;
     const int wc0 = cell0 + warp * 8;           // first cell of this warp
@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     }
     if (lane < 8) {
         const int cell = wc0 + lane;
-        sCell[(warp * 8 + lane) * 2 + 0] = cell < n ? a.im[cell] : 0;
-        sCell[(warp * 8 + lane) * 2 + 1] = cell < n ? a.celltype0[cell] : 0;
+        int* ci = reinterpret_cast<int*>(wblk + 8 * MSS * 8 + 256 * 8 + 768);
+        ci[lane * 2 + 0] = cell < n ? a.im[cell] : 0;
+        ci[lane * 2 + 1] = cell < n ? a.celltype0[cell] : 0;
     }
     // gridDim.y splits the gene range (wave-quantisation fix: more, smaller CTAs); this CTA walks chunks [cbeg, cend)
     const int nchunks_all = ldG / SG;
@@ -123,12 +124,12 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     __syncthreads();
     if (tid == 0 && nchunks > 0) load_chunk_bulk(a, chunk_buf(sBuf, FS, M0, MB), cbeg, &bars[0]);
 
-    double* msW = sMs + warp * 8 * MSS;
-    unsigned char* list = sList + warp * 768;
-    unsigned char* dcode = list + 256;
-    unsigned char* xcode = list + 512;
-    double* dub = sDub + warp * 256;
-    const int* cellinfo = sCell + warp * 16;
+    double* msW = reinterpret_cast<double*>(wblk);                     // [8][MSS] conditional means / deltas
+    double* dub = msW + 8 * MSS;                                       // [256]    list values
+    unsigned char* list = reinterpret_cast<unsigned char*>(dub + 256); // [256] all zero entries
+    unsigned char* dcode = list + 256;                                 // [256] Dc (front) / back list codes
+    unsigned char* xcode = list + 512;                                 // [256] uncertain entries
+    int* cellinfo = reinterpret_cast<int*>(list + 768);                // [8][2] (im, celltype)
     const double* fa = sF + (warp * 8 + g) * FS + t;
 
     for (int ci = 0; ci < nchunks; ++ci) {
