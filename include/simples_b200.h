@@ -146,6 +146,43 @@ typedef struct simples_mi_out {     /* R/do_impute.R:158-159 */
     double *consensus_cluster;      /* n x n or NULL                                   */
 } simples_mi_out;
 
+/* ---- low-quality-gene fit between the two EM_impute calls ----------------
+ * R/SIMPLE.R:305-411 (= R/SIMPLE_B.R:332-419): with the high-quality-gene fit
+ * (z, Ef, Varf) fixed, every remaining gene gets M0 unpenalised intercepts and
+ * K0 lasso loadings from one augmented regression (:312-366), a shared variance
+ * (:365, clipped :371-373), and its zero entries are drawn once with the factor
+ * held at its posterior mean (:376-411).  All arrays hold the lq genes only
+ * (Gq rows); cells may be sharded exactly like EM_impute. */
+typedef struct simples_lq_args {
+    int32_t Gq, n, M0, K0, MB;
+    const double *dat;              /* Gq x n observed rows dat[lq_ind, ]               */
+    const double *resp;             /* Gq x n regression response: NULL => dat; init_imp[lq_ind, ] when SIMPLE() got one */
+    const double *sigma;            /* Gq x M0 current sigma[lq_ind, ]                  */
+    const double *pg;               /* Gq x MB                                          */
+    const double *z;                /* n x M0   impute_hq$z                             */
+    const double *Ef;               /* M0 matrices n x K0, back to back                 */
+    const double *Varf;             /* M0 matrices K0 x K0, back to back                */
+    const int32_t *celltype;        /* n, 1-based, or NULL                              */
+    double penl, cutoff;
+    int32_t resid_mode;             /* 0: sg without the residual sum (SIMPLE() with init_imp = NULL, the inverted
+                                       branch of R/SIMPLE.R:354-359); 1: residual of dat (R/SIMPLE.R:360-364,
+                                       R/SIMPLE_B.R:370-374)                            */
+    int32_t impute;                 /* 0: regression only; 1: also the draw of :376-411 */
+    uint64_t seed;
+    uint32_t sweep;                 /* tape position of the draw (any value not used by the EM calls) */
+    int64_t n_total, cell_offset;
+    simples_allreduce_fn allreduce;
+    void *allreduce_user;
+    void *stream;
+} simples_lq_args;
+
+typedef struct simples_lq_out {
+    double *mu;                     /* Gq x M0                                          */
+    double *beta;                   /* Gq x K0                                          */
+    double *sigma;                  /* Gq x M0 (columns equal)                          */
+    double *Y;                      /* Gq x n  dat with the entries <= cutoff redrawn (NULL when impute = 0) */
+} simples_lq_out;
+
 /* ---- lifecycle / errors ------------------------------------------------ */
 SIMPLES_API int simples_abi_version(void);
 /* Select the device this process drives (ndev must be 1: one process per GPU). */
@@ -156,6 +193,7 @@ SIMPLES_API const char *simples_last_error(void);
 /* ---- one-shot calls with HOST buffers (what the .Call shim binds) ------- */
 SIMPLES_API int simples_em_impute(const simples_em_args *args, simples_em_out *out);
 SIMPLES_API int simples_do_impute(const simples_mi_args *args, simples_mi_out *out);
+SIMPLES_API int simples_lq_fit(const simples_lq_args *args, simples_lq_out *out);
 
 /* ---- resident-context API (keeps Y/mask/state in HBM between calls; used
  *      by SIMPLE()-level drivers and by bench.py's device-resident timing) -- */

@@ -35,6 +35,7 @@ __all__ = [
     "local_stats", "stats_pack", "stats_unpack", "mstep_from_stats",
     "em_impute_ref", "em_impute_fast", "do_impute_ref",
     "simulate", "bench_state", "expected_impute", "yimp0_ref", "bic_ref",
+    "lq_regress_ref", "lq_regress_fast", "lq_impute_ref",
 ]
 
 PI_REF = 3.14159265359          # R/EM_impute.R:80, R/do_impute.R:31  (Q2)
@@ -154,31 +155,36 @@ def sym_sqrt(M):
 #   0.5 b'Ab - rhs'b + kappa |b|_1
 # ----------------------------------------------------------------------------
 def _polish(A, rhs, kappa, beta):
-    S = beta != 0.0
+    """kappa: scalar or per-coordinate vector (0 = unpenalised coordinate, always active)."""
+    kv = np.broadcast_to(np.asarray(kappa, dtype=np.float64), beta.shape)
+    S = (beta != 0.0) | (kv == 0.0)
     if not S.any():
-        return beta if np.all(np.abs(rhs) <= kappa * (1 + 1e-12)) else None
+        return beta if np.all(np.abs(rhs) <= kv * (1 + 1e-12)) else None
     sgn = np.sign(beta[S])
     try:
-        x = np.linalg.solve(A[np.ix_(S, S)], rhs[S] - kappa * sgn)
+        x = np.linalg.solve(A[np.ix_(S, S)], rhs[S] - kv[S] * sgn)
     except np.linalg.LinAlgError:
         return None
-    if np.any(np.sign(x) != sgn):
+    pen = kv[S] > 0
+    if np.any(np.sign(x[pen]) != sgn[pen]):
         return None
     full = np.zeros_like(beta)
     full[S] = x
     grad = rhs - A @ full
-    if np.any(np.abs(grad[~S]) > kappa * (1 + 1e-10) + 1e-300):
+    if np.any(np.abs(grad[~S]) > kv[~S] * (1 + 1e-10) + 1e-300):
         return None
     return full
 
 
 def lasso_solve_batch(A, rhs, kappa, max_sweeps=20000, tol=1e-15):
-    """A: (K,K) shared or (G,K,K); rhs (G,K); kappa (G,).  Cyclic coordinate
-    descent from 0 (glmnet's start), then an exact active-set polish."""
+    """A: (K,K) shared or (G,K,K); rhs (G,K); kappa (G,) or (G,K) (per-coordinate
+    penalties, 0 = unpenalised).  Cyclic coordinate descent from 0 (glmnet's
+    start), then an exact active-set polish."""
     rhs = np.asarray(rhs, dtype=np.float64)
     G, K = rhs.shape
     shared = (A.ndim == 2)
-    kappa = np.broadcast_to(np.asarray(kappa, dtype=np.float64), (G,))
+    kappa = np.asarray(kappa, dtype=np.float64)
+    kappa = np.broadcast_to(kappa[:, None] if kappa.ndim == 1 else kappa, (G, K))
     beta = np.zeros((G, K))
     r = rhs.copy()
     live = np.arange(G)
@@ -191,7 +197,7 @@ def lasso_solve_batch(A, rhs, kappa, max_sweeps=20000, tol=1e-15):
         for k in range(K):
             akk = Al[k, k] if shared else Al[:, k, k]
             t = rl[:, k] + akk * bl[:, k]
-            bn = np.sign(t) * np.maximum(np.abs(t) - kl, 0.0) / akk
+            bn = np.sign(t) * np.maximum(np.abs(t) - kl[:, k], 0.0) / akk
             d = bn - bl[:, k]
             col = Al[:, k] if shared else Al[:, :, k]
             rl -= d[:, None] * col
@@ -219,7 +225,9 @@ def lasso_solve_batch(A, rhs, kappa, max_sweeps=20000, tol=1e-15):
 
 
 def lasso_solve(A, rhs, kappa):
-    return lasso_solve_batch(np.asarray(A), np.asarray(rhs)[None, :], np.array([kappa]))[0]
+    kap = np.asarray(kappa, dtype=np.float64)
+    kap = kap[None] if kap.ndim == 0 else kap[None, :]
+    return lasso_solve_batch(np.asarray(A), np.asarray(rhs)[None, :], kap)[0]
 
 
 # ----------------------------------------------------------------------------
@@ -787,3 +795,97 @@ def bic_ref(loglik_tot, n, G, K0, M0):
     bic = (-2 * loglik_tot + math.log(n) * (2 * G * M0 + G) + math.log(n * G) * K0 * (M0 - 1)
            + K0 * math.log((G * n) / (G + n)) * (G + n))
     return bic, bic0
+
+
+# ----------------------------------------------------------------------------
+# N1: low-quality-gene regression and imputation draw between the two EM calls
+# (R/SIMPLE.R:308-411, R/SIMPLE_B.R:335-419)
+# ----------------------------------------------------------------------------
+def lq_regress_ref(dat, resp, sigma, z, Ef, Varf, penl=1, resid_mode=0):
+    """Literal restatement.  dat / resp / sigma are the rows of the lq genes.
+    resp = regression response (dat, or init_imp when SIMPLE got one);
+    resid_mode 0 = residual term of sg dropped (SIMPLE with init_imp = NULL: the
+    inverted branch indexes NULL, quirk Q16, R/SIMPLE.R:354-359), 1 = residual
+    from dat (SIMPLE with init_imp, R/SIMPLE.R:360-364; SIMPLE_B, R/SIMPLE_B.R:370-374)."""
+    Gq, n = dat.shape
+    M0 = z.shape[1]
+    K0 = Ef[0].shape[1]
+    nz = z.sum(axis=0)
+    Vm = [Varf[m] * nz[m] for m in range(M0)]                               # R/SIMPLE.R:305-306
+    sq = np.sqrt(z)
+    mu = np.empty((Gq, M0))
+    beta = np.empty((Gq, K0))
+    sg_out = np.empty(Gq)
+    for g in range(Gq):                                                      # :312
+        V = sum(Vm[m] / sigma[g, m] for m in range(M0))                      # :314
+        rows, ys = [], []
+        for m in range(M0):                                                  # :318-330
+            ys.append(resp[g] * sq[:, m] / math.sqrt(sigma[g, m]))
+            Wb = Ef[m] * sq[:, m][:, None] / math.sqrt(sigma[g, m])
+            Wmu = np.zeros((n, M0))
+            Wmu[:, m] = sq[:, m] / math.sqrt(sigma[g, m])
+            rows.append(np.concatenate([Wmu, Wb], axis=1))
+        ML = np.concatenate([np.zeros((K0, M0)), np.linalg.cholesky(V).T], axis=1)   # :332
+        W_aug = np.concatenate(rows + [ML])                                  # :335
+        Y_aug = np.concatenate(ys + [np.zeros(K0)])                          # :337
+        # glmnet(lambda = penalty K0/(M0+K0), penalty.factor = c(0.., 1..)) with the internal rescale of the
+        # penalty factors to sum to M0 + K0  ==  kappa = penl / var(Y_aug) on the loadings, 0 on the intercepts
+        kappa = np.concatenate([np.zeros(M0), np.full(K0, penl / np.var(Y_aug, ddof=1))])   # :341-349
+        coef = lasso_solve(W_aug.T @ W_aug, W_aug.T @ Y_aug, kappa)
+        tempmu, coeff = coef[:M0], coef[M0:]                                 # :351-352
+        sg = 0.0
+        for m in range(M0):                                                  # :354-364
+            if resid_mode:
+                sg += np.sum((dat[g] - tempmu[m] - Ef[m] @ coeff) ** 2 * z[:, m])
+            sg += coeff @ Vm[m] @ coeff
+        mu[g], beta[g], sg_out[g] = tempmu, coeff, (sg + 1) / (n + 3)        # :365
+    sigma_new = np.repeat(np.clip(sg_out, 1e-4, 9.0)[:, None], M0, axis=1)   # :371-373
+    return mu, beta, sigma_new
+
+
+def lq_regress_fast(dat, resp, sigma, z, Ef, Varf, penl=1, resid_mode=0):
+    """Same result from cell-additive statistics; the M0 unpenalised intercepts are profiled out
+    (their block of the Gram matrix is diagonal), leaving a K0-dimensional lasso per gene."""
+    Gq, n = dat.shape
+    M0 = z.shape[1]
+    K0 = Ef[0].shape[1]
+    nz = z.sum(axis=0)
+    S = np.stack([(Ef[m] * z[:, m][:, None]).T @ Ef[m] for m in range(M0)])
+    a = np.stack([(Ef[m] * z[:, m][:, None]).sum(axis=0) for m in range(M0)])
+    D = np.stack([S[m] + nz[m] * Varf[m] - np.outer(a[m], a[m]) / nz[m] for m in range(M0)])
+
+    def stats(Yq):
+        return (np.stack([Yq @ (Ef[m] * z[:, m][:, None]) for m in range(M0)]), Yq @ z, Yq @ np.sqrt(z), (Yq * Yq) @ z)
+
+    T, U, Uh, U2 = stats(resp)
+    N = M0 * n + K0
+    sumY = np.sum(Uh / np.sqrt(sigma), axis=1)
+    sumY2 = np.sum(U2 / sigma, axis=1)
+    var = (sumY2 - sumY * sumY / N) / (N - 1)
+    A = np.einsum("mjk,gm->gjk", D, 1.0 / sigma)
+    rhs = np.einsum("mgk,gm->gk", T - U.T[:, :, None] * (a / nz[:, None])[:, None, :], 1.0 / sigma)
+    beta = lasso_solve_batch(A, rhs, penl / var)
+    mu = (U - beta @ a.T) / nz[None, :]
+    C = np.stack([nz[m] * Varf[m] for m in range(M0)])
+    sg = np.einsum("gj,mjk,gk->g", beta, C, beta)
+    if resid_mode:
+        Td, Ud, _, U2d = (T, U, Uh, U2) if resp is dat else stats(dat)
+        for m in range(M0):
+            bm = Td[m] - mu[:, m][:, None] * a[m][None, :]
+            sg += (U2d[:, m] - 2 * mu[:, m] * Ud[:, m] + mu[:, m] ** 2 * nz[m] - 2 * np.sum(beta * bm, axis=1)
+                   + np.einsum("gj,jk,gk->g", beta, S[m], beta))
+    sigma_new = np.repeat(np.clip((sg + 1) / (n + 3), 1e-4, 9.0)[:, None], M0, axis=1)
+    return mu, beta, sigma_new
+
+
+def lq_impute_ref(dat, mu, beta, sigma, pg, z, Ef, celltype, cutoff=0.1, seed=0, sweep=0, cell0=0):
+    """R/SIMPLE.R:376-411: one imputation draw of the lq genes' zero entries with the factor fixed at its posterior
+    mean Ef[[m]][i,] (no factor noise), membership sampled from z; uncentred output."""
+    Gq, n = dat.shape
+    M0 = z.shape[1]
+    K0 = beta.shape[1]
+    Y = np.array(dat, dtype=np.float64)
+    celltype0 = np.zeros(n, dtype=np.int64) if celltype is None else np.asarray(celltype, dtype=np.int64) - 1
+    sample_sweep(Y, dat <= cutoff, z, Ef, [np.zeros((K0, K0))] * M0, mu, beta, sigma, np.asarray(pg), celltype0,
+                 np.zeros(Gq), np.ones(Gq), cutoff, seed, sweep, cell0, draw_membership=(M0 > 1), clip=False)
+    return Y

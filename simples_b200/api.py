@@ -291,6 +291,50 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
             "varF": bufs["varF"], "consensus_cluster": bufs["consensus_cluster"]}
 
 
+def lq_fit(dat, sigma, pg, z, Ef, Varf, celltype=None, penl=1, cutoff=0.1, *, resp=None, resid_mode=0, impute=True,
+           seed=0, sweep=0, comm=None, stream=None):
+    """The low-quality-gene step between the two ``EM_impute`` calls of ``SIMPLE()`` / ``SIMPLE_B()``
+    (R/SIMPLE.R:305-411, R/SIMPLE_B.R:332-419) on B200: per gene M0 unpenalised intercepts + K0 lasso loadings,
+    the shared variance, and one imputation draw of the entries <= cutoff with the factor at its posterior mean.
+    All matrices hold the lq rows only.  ``resp`` = ``init_imp[lq_ind, ]`` when SIMPLE() got one; ``resid_mode``
+    0 = SIMPLE() with ``init_imp = NULL`` (residual term dropped), 1 = residual of ``dat`` (SIMPLE() with
+    ``init_imp``; SIMPLE_B()).  Returns mu, beta, sigma, Y."""
+    lib = _lib.load()
+    dat = _f(dat)
+    Gq, n = dat.shape
+    z = _f(z)
+    M0 = z.shape[1]
+    K0 = np.asarray(Ef[0]).shape[1]
+    ct = None if celltype is None else np.ascontiguousarray(np.asarray(celltype).astype(np.int32))
+    pg = _f(np.asarray(pg, dtype=np.float64).reshape(Gq, -1))
+    keep = dict(dat=dat, resp=None if resp is None else _f(resp, (Gq, n), "resp"), sigma=_f(sigma, (Gq, M0), "sigma"),
+                pg=pg, z=_f(z, (n, M0), "z"),
+                Ef=np.ascontiguousarray(np.stack([_f(e, (n, K0), "Ef").T for e in Ef])),       # M0 col-major n x K0 blocks
+                Varf=np.ascontiguousarray(np.stack([_f(v, (K0, K0), "Varf").T for v in Varf])),
+                celltype=ct)
+    a = _lib.LqArgs()
+    a.Gq, a.n, a.M0, a.K0, a.MB = Gq, n, M0, K0, pg.shape[1]
+    for k, v in keep.items():
+        setattr(a, k, _ptr(v))
+    a.penl, a.cutoff, a.resid_mode, a.impute = float(penl), float(cutoff), int(resid_mode), int(bool(impute))
+    a.seed, a.sweep = int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep)
+    cw = None
+    if comm is not None:
+        cw = _Comm(comm)
+        a.n_total, a.cell_offset, a.allreduce = int(comm.n_total), int(comm.cell_offset), cw.cb
+    a.stream = stream
+    bufs = dict(mu=np.zeros((Gq, M0), order="F"), beta=np.zeros((Gq, K0), order="F"), sigma=np.zeros((Gq, M0), order="F"),
+                Y=np.empty((Gq, n), order="F") if impute else None)
+    o = _lib.LqOut()
+    for k, v in bufs.items():
+        setattr(o, k, _ptr(v))
+    rc = lib.simples_lq_fit(C.byref(a), C.byref(o))
+    if rc < 0 and cw is not None and cw.error is not None:
+        raise cw.error
+    check(rc)
+    return bufs
+
+
 def bic(loglik_last, n, G, K0, M0):
     """(BIC, BIC0) of SIMPLE()/SIMPLE_B() (R/SIMPLE.R:429-430); ``n`` is the global number of cells."""
     b, b0 = C.c_double(), C.c_double()

@@ -1029,4 +1029,126 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     return SIMPLES_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// lq-gene fit between the two EM_impute calls (R/SIMPLE.R:305-411 = R/SIMPLE_B.R:332-419)
+int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
+    if (!a || !o) return fail(SIMPLES_EINVAL, "null argument");
+    CKR(check_common(a->Gq, a->n, a->M0, a->K0, a->MB));
+    if (!a->dat || !a->sigma || !a->pg || !a->z || !a->Ef || !a->Varf)
+        return fail(SIMPLES_EINVAL, "dat, sigma, pg, z, Ef and Varf are required");
+    if (a->resid_mode != 0 && a->resid_mode != 1) return fail(SIMPLES_EINVAL, "resid_mode must be 0 or 1");
+    if (a->n_total != 0 && a->n_total < a->n) return fail(SIMPLES_EINVAL, "n_total < n");
+    if (a->impute && !o->Y) return fail(SIMPLES_EINVAL, "impute = 1 needs out->Y");
+    CKR(ensure_device());
+
+    std::unique_ptr<simples_ctx> guard(new simples_ctx());
+    simples_ctx* c = guard.get();
+    c->kind = 2;
+    if (a->stream) {
+        c->stream = (cudaStream_t)a->stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->cutoff = a->cutoff;
+    c->seed = a->seed;
+    c->sweep = a->sweep;
+    c->allreduce = a->allreduce;
+    c->allreduce_user = a->allreduce_user;
+    const int Gq = a->Gq, n = a->n, M0 = a->M0, K0 = a->K0;
+    {
+        std::vector<double> b0(size_t(Gq) * K0, 0.0), l1(size_t(M0) * K0, 1.0), p1(M0, 1.0 / M0);
+        CKR(setup_common(c, Gq, n, M0, K0, a->MB, a->n_total, a->cell_offset, a->dat, a->dat, a->pg, b0.data(), a->sigma,
+                         l1.data(), p1.data(), a->celltype, a->cutoff, true));
+    }
+    DevState& s = c->s;
+    const Dims& d = s.d;
+    const int ldG = d.ldG;
+    const size_t na = c->n_alloc;
+    launch_fill(s.gsd, ldG, 1.0, c->stream);
+    CKR(upload_z(c, a->z));
+    double* varf = nullptr;
+    CKR(c->dalloc(&varf, size_t(M0) * K0 * K0));
+    CK(cudaMemcpyAsync(varf, a->Varf, size_t(M0) * K0 * K0 * 8, cudaMemcpyHostToDevice, c->stream));
+    {   // Ef: M0 col-major n x K0 blocks -> W [M0][n][K0]
+        double* tmp = nullptr;
+        CK(cudaMallocAsync(&tmp, size_t(M0) * n * K0 * 8, c->stream));
+        CK(cudaMemcpyAsync(tmp, a->Ef, size_t(M0) * n * K0 * 8, cudaMemcpyHostToDevice, c->stream));
+        for (int m = 0; m < M0; ++m)
+            launch_transpose(tmp + size_t(m) * n * K0, s.W + size_t(m) * n * K0, K0, n, n, K0, c->stream);
+        CK(cudaFreeAsync(tmp, c->stream));
+    }
+    const int ncg = K0 * M0 + 2 * M0;
+    CKR(c->dalloc(&s.Vg, na * ncg));
+    s.statsg_count = size_t(ldG) * ncg + size_t(ldG) * M0 + size_t(M0) * K0 * K0 + size_t(M0) * K0 + 2 * M0 + 1;
+    const size_t nC = size_t(ldG) * ncg, nU2 = size_t(ldG) * M0;
+    CKR(c->dalloc(&s.statsg, s.statsg_count));
+    c->nsplit_g = 8;
+    CKR(c->dalloc(&c->part_g, size_t(c->nsplit_g) * ldG * ncg));
+    s.nsplit_ss = std::max(1, (4 * NUM_SMS_B200) / M0);
+    CKR(c->dalloc(&s.part_ss, size_t(s.nsplit_ss) * M0 * (K0 * K0 + K0)));
+
+    // ---- cell operands + membership draw, then the statistics of the response ----
+    {
+        LqCellArgs la{d, s.z, s.W, s.Vg, s.Fh, s.im, c->seed, c->sweep, M0 > 1};
+        launch_lq_cell(la, c->stream);
+        launch_colsum(s.z, c->cellsum_last, n, M0, c->stream);
+    }
+    const bool own_resp = a->resp != nullptr && a->resp != a->dat;
+    double* R = s.Y;            // response matrix on the device, [n][ldG]
+    if (own_resp) {
+        CKR(c->dalloc(&R, na * ldG));
+        if (ldG == Gq) {
+            CK(cudaMemcpyAsync(R, a->resp, size_t(n) * Gq * 8, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            CK(cudaMemcpy2DAsync(R, size_t(ldG) * 8, a->resp, size_t(Gq) * 8, size_t(Gq) * 8, n, cudaMemcpyHostToDevice,
+                                 c->stream));
+        }
+    }
+    auto gene_stats = [&](const double* Ymat, double* out) {
+        launch_ygemm_simple(Ymat, s.Vg, c->part_g, n, ldG, ncg, ncg, 0, c->nsplit_g, c->stream);
+        launch_reduce_parts(c->part_g, out, nC, c->nsplit_g, c->stream);
+        launch_ygemm_simple(Ymat, s.Vg + size_t(K0) * M0, c->part_g, n, ldG, M0, ncg, 1, c->nsplit_g, c->stream);
+        launch_reduce_parts(c->part_g, out + nC, nU2, c->nsplit_g, c->stream);
+    };
+    gene_stats(R, s.statsg);
+    {
+        SstatsArgs sa{d, s.W, s.z, s.part_ss, s.nsplit_ss};
+        launch_sstats(sa, c->stream);
+        FinalizeArgs fa{d, nullptr, c->cellsum_last, s.part_ss, 0, 1, s.nsplit_ss, s.statsg, nC + nU2, 1};
+        launch_finalize_stats(fa, c->stream);
+    }
+    CKR(allreduce(c, s.statsg, s.statsg_count));
+    double* stats_d = s.statsg;
+    if (own_resp && a->resid_mode) {           // residual of dat, response init_imp (R/SIMPLE.R:360-364)
+        CKR(c->dalloc(&stats_d, nC + nU2 + 1));
+        gene_stats(s.Y, stats_d);
+        CKR(allreduce(c, stats_d, nC + nU2));
+    }
+    {
+        LqSolveArgs qa{d, s.statsg, stats_d, varf, s.beta, s.sigma, s.mu, a->penl, a->resid_mode};
+        launch_lq_solve(qa, c->stream);
+    }
+    CK(cudaGetLastError());
+    if (a->impute) {                            // R/SIMPLE.R:376-411
+        PrepArgs pa{d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.igs, s.cc, 0};
+        launch_prep(pa, c->stream, c->stream);
+        CKR(run_sweep(c, false, nullptr, nullptr));
+    }
+    if (o->mu) CKR(fetch_genemajor(c, s.mu, M0, o->mu));
+    if (o->beta) CKR(fetch_genemajor(c, s.beta, K0, o->beta));
+    if (o->sigma) CKR(fetch_genemajor(c, s.sigma, M0, o->sigma));
+    if (a->impute && o->Y) {
+        if (ldG == Gq) {
+            CK(cudaMemcpyAsync(o->Y, s.Y, size_t(n) * Gq * 8, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            CK(cudaMemcpy2DAsync(o->Y, size_t(Gq) * 8, s.Y, size_t(ldG) * 8, size_t(Gq) * 8, n, cudaMemcpyDeviceToHost,
+                                 c->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
 }  // extern "C"

@@ -2,6 +2,7 @@
 // gene means (R/EM_impute.R:82-90), centring, layout transposes, do_impute accumulators
 // (R/do_impute.R:139-148,156-159) and the optional n x n consensus matrix (R/do_impute.R:96).
 #include "ptx.cuh"
+#include "rng.cuh"
 #include "state.h"
 
 namespace sb {
@@ -179,6 +180,61 @@ inline int gs_grid(size_t total) {
     return int(g);
 }
 
+// lq-gene fit: regression operand Vg = [z_m Ef_m | z | sqrt z] and the sweep operand Fh = [Ef_{m_i}[i,] | onehot | 1]
+// with m_i drawn from z[i,] (R/SIMPLE.R:376-382; the factor is NOT sampled here, :386).
+__global__ void k_lq_cell(LqCellArgs a) {
+    const Dims& d = a.d;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const int K0 = d.K0, M0 = d.M0, ncg = K0 * M0 + 2 * M0;
+    double* vg = a.Vg + size_t(i) * ncg;
+    const double* zi = a.z + size_t(i) * M0;
+    int im = 0;
+    if (a.draw_membership) {
+        double u0, u1;
+        cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(d.cell_offset + i), 0u, u0, u1);
+        double cum = 0.0;
+        for (int m = 0; m < M0; ++m) {
+            cum += zi[m];
+            im += (u0 >= cum) ? 1 : 0;
+        }
+        im = min(im, M0 - 1);
+    }
+    a.im[i] = im;
+    double* fh = a.Fh + size_t(i) * d.FS;
+    for (int m = 0; m < M0; ++m) {
+        const double zm = zi[m];
+        const double* w = a.W + (size_t(m) * d.n + i) * K0;
+        for (int k = 0; k < K0; ++k) {
+            vg[m * K0 + k] = zm * w[k];
+            if (m == im) fh[k] = w[k];
+        }
+        vg[K0 * M0 + m] = zm;
+        vg[K0 * M0 + M0 + m] = sqrt(zm);
+        fh[K0 + m] = (m == im) ? 1.0 : 0.0;
+    }
+    fh[K0 + M0] = 1.0;
+    for (int c = K0 + M0 + 1; c < d.FS; ++c) fh[c] = 0.0;
+}
+
+// out[m] = sum_i z[i][m] in a fixed order (one CTA), out[M0 .. 2 M0] = 0
+__global__ void __launch_bounds__(256) k_colsum(const double* z, double* out, int n, int M0) {
+    __shared__ double red[256];
+    for (int m = 0; m < M0; ++m) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += 256) s += z[size_t(i) * M0 + m];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[m] = red[0];
+        __syncthreads();
+    }
+    if (threadIdx.x <= M0) out[M0 + threadIdx.x] = 0.0;
+}
+
 }  // namespace
 
 void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int cell0, int n_alloc, int G, int ldG,
@@ -225,5 +281,8 @@ void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t
     dim3 grid((n + 15) / 16, (n + 15) / 16), block(16, 16);
     k_consensus<<<grid, block, 0, st>>>(z, cons, n, M0);
 }
+
+void launch_lq_cell(const LqCellArgs& a, cudaStream_t st) { k_lq_cell<<<(a.d.n + 127) / 128, 128, 0, st>>>(a); }
+void launch_colsum(const double* z, double* out, int n, int M0, cudaStream_t st) { k_colsum<<<1, 256, 0, st>>>(z, out, n, M0); }
 
 }  // namespace sb

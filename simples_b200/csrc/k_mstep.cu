@@ -208,6 +208,101 @@ __global__ void __launch_bounds__(GW * 32) k_gene_solve(MstepArgs a) {
     }
 }
 
+// Low-quality-gene regression, R/SIMPLE.R:312-366 (= R/SIMPLE_B.R:335-378), from cell-additive statistics.  The
+// intercept block of the augmented Gram matrix is diagonal (nz_m / sigma_gm), so the M0 unpenalised intercepts are
+// profiled out exactly and a K0-dimensional lasso remains:
+//   A  = sum_m (S_m + nz_m Varf_m - a_m a_m'/nz_m) / sigma_gm,   rhs = sum_m (T_gm - a_m U_gm / nz_m) / sigma_gm,
+//   kappa = penl / var(Y_aug)   (lambda = penalty K0/(M0+K0) with glmnet's penalty.factor rescale, :341-349),
+//   mu_gm = (U_gm - a_m'b) / nz_m.
+// One warp per gene; lane k owns loading k, lane m owns cluster m.
+__global__ void __launch_bounds__(GW * 32) k_lq_solve(LqSolveArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const Dims& d = a.d;
+    const int K0 = d.K0, M0 = d.M0;
+    const StatView sv = stat_view(a.stats, d, 1), svd = stat_view(a.stats_d, d, 1);
+    const int KK = K0 * K0;
+    double* sAsum = sm;                       // [K0][K0]  sum_m nz_m Varf_m (+ S_m when the residual is kept)
+    double* sa = sAsum + KK;                  // [M0][K0]
+    double* sL = sa + M0 * K0;                // [GW][K0*K0]
+    double* sAl = sL + GW * KK;               // [GW][K0*K0]
+    double* sxs = sAl + GW * KK;              // [GW][K0]
+    int* sidx = reinterpret_cast<int*>(sxs + GW * K0);   // [GW][K0]
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        double s = 0.0;
+        for (int m = 0; m < M0; ++m)
+            s += sv.nz[m] * a.Varf[size_t(m) * KK + e] + (a.resid_mode ? sv.S[size_t(m) * KK + e] : 0.0);
+        sAsum[e] = s;
+    }
+    for (int e = threadIdx.x; e < M0 * K0; e += blockDim.x) sa[e] = sv.a[e];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool kl = lane < K0, ml = lane < M0;
+    const int g = blockIdx.x * GW + warp;
+    if (g >= d.G) return;
+    const double ntot = double(d.n_total);
+    const double N = double(M0) * ntot + K0;
+    const double* Cg = sv.C + size_t(g) * sv.ldc;
+    const double sgm = ml ? a.sigma[size_t(g) * M0 + lane] : 1.0;   // lane m
+    const double nzm = ml ? sv.nz[lane] : 0.0;
+    const double inz = nzm > 0.0 ? 1.0 / nzm : 0.0;
+    const double U = ml ? Cg[K0 * M0 + lane] : 0.0, Uh = ml ? Cg[K0 * M0 + M0 + lane] : 0.0;
+    const double U2 = ml ? sv.U2[size_t(g) * M0 + lane] : 0.0;
+    double* Al = sAl + warp * KK;
+    for (int e = lane; e < KK; e += 32) {
+        const int i = e / K0, j = e - i * K0;
+        double s = 0.0;
+        for (int m = 0; m < M0; ++m) {
+            const double nz = sv.nz[m];
+            const double t = sv.S[size_t(m) * KK + e] + nz * a.Varf[size_t(m) * KK + e] -
+                             (nz > 0.0 ? sa[m * K0 + i] * sa[m * K0 + j] / nz : 0.0);
+            s += t / a.sigma[size_t(g) * M0 + m];
+        }
+        Al[e] = s;
+    }
+    __syncwarp();
+    double rhs = 0.0;
+    for (int m = 0; m < M0; ++m) {
+        const double Um = __shfl_sync(0xffffffffu, U, m), sg_m = __shfl_sync(0xffffffffu, sgm, m),
+                     iz = __shfl_sync(0xffffffffu, inz, m);
+        if (kl) rhs += (Cg[m * K0 + lane] - sa[m * K0 + lane] * Um * iz) / sg_m;
+    }
+    const double sumY = warp_sum(ml ? Uh / sqrt(sgm) : 0.0);
+    const double sumY2 = warp_sum(ml ? U2 / sgm : 0.0);
+    const double var = (sumY2 - sumY * sumY / N) / (N - 1.0);
+    const double kappa = a.penl / var;
+    const double b = lasso_solve(Al, K0, rhs, kappa, sL + warp * KK, sxs + warp * K0, sidx + warp * K0, lane);
+    double ab_m = 0.0;                                 // lane m: a_m'b
+    for (int k = 0; k < K0; ++k) {
+        const double bk = __shfl_sync(0xffffffffu, b, k);
+        if (ml) ab_m = fma(sa[lane * K0 + k], bk, ab_m);
+    }
+    const double mu = ml ? (U - ab_m) * inz : 0.0;
+    double ab = 0.0;
+    for (int k = 0; k < K0; ++k) {
+        const double bk = __shfl_sync(0xffffffffu, b, k);
+        if (kl) ab = fma(sAsum[lane * K0 + k], bk, ab);
+    }
+    double sg = warp_sum(kl ? b * ab : 0.0);           // b'(sum_m Vm [+ S_m]) b
+    if (a.resid_mode) {
+        const double* Dg = svd.C + size_t(g) * svd.ldc;
+        const double Ud = ml ? Dg[K0 * M0 + lane] : 0.0, U2d = ml ? svd.U2[size_t(g) * M0 + lane] : 0.0;
+        sg += warp_sum(ml ? U2d - 2.0 * mu * Ud + mu * mu * nzm : 0.0);
+        double bt = 0.0;
+        for (int m = 0; m < M0; ++m) {
+            const double mum = __shfl_sync(0xffffffffu, mu, m);
+            if (kl) bt += Dg[m * K0 + lane] - mum * sa[m * K0 + lane];
+        }
+        sg -= 2.0 * warp_sum(kl ? b * bt : 0.0);
+    }
+    sg = (sg + 1.0) / (ntot + 3.0);
+    if (kl) a.beta[size_t(g) * K0 + lane] = b;
+    if (ml) {
+        a.mu[size_t(g) * M0 + lane] = mu;
+        a.sigma[size_t(g) * M0 + lane] = fmin(fmax(sg, 1e-4), 9.0);
+    }
+}
+
 // sum of v over lanes 0..mt-1 in ascending lane order (mirrors the oracle's sequential Python sums)
 __device__ __forceinline__ double ordered_sum(double v, int mt) {
     double s = 0.0;
@@ -417,6 +512,18 @@ void launch_mstep(const MstepArgs& a, cudaStream_t st) {
         }
         k_mu<<<M0, 256, smem, st>>>(a);
     }
+}
+
+void launch_lq_solve(const LqSolveArgs& a, cudaStream_t st) {
+    const int K0 = a.d.K0, M0 = a.d.M0;
+    const size_t KK = size_t(K0) * K0;
+    const size_t smem = sizeof(double) * (KK + size_t(M0) * K0 + 2 * GW * KK + GW * K0) + sizeof(int) * GW * K0;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(k_lq_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr = smem;
+    }
+    k_lq_solve<<<(a.d.G + GW - 1) / GW, GW * 32, smem, st>>>(a);
 }
 
 }  // namespace sb

@@ -166,6 +166,19 @@ struct MstepArgs {
 void launch_mstep(const MstepArgs& a, cudaStream_t st);
 int mstep_gene_ctas(int G);
 
+// low-quality-gene fit (R/SIMPLE.R:305-411)
+struct LqSolveArgs {
+    Dims d; const double *stats, *stats_d, *Varf;   // stats: response statistics (general layout); stats_d: those of dat
+    double *beta, *sigma, *mu; double penl; int resid_mode;
+};
+void launch_lq_solve(const LqSolveArgs& a, cudaStream_t st);
+struct LqCellArgs {
+    Dims d; const double *z, *W; double *Vg, *Fh; int32_t* im;
+    unsigned long long seed; unsigned sweep; int draw_membership;
+};
+void launch_lq_cell(const LqCellArgs& a, cudaStream_t st);
+void launch_colsum(const double* z, double* out, int n, int M0, cudaStream_t st);   // out [2 M0 + 1] = [colSums(z) | 0...]
+
 // misc
 void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int cell0, int n_alloc, int G, int ldG, double cutoff,
                        unsigned long long* nnz, cudaStream_t st);

@@ -41,6 +41,30 @@ def test_struct_layout_matches_header():
     assert _lib.MiArgs.dat.offset == 24
 
 
+def test_struct_layout_against_gcc(tmp_path):
+    """sizeof / offsetof of every struct as gcc lays out include/simples_b200.h == the ctypes mirrors."""
+    import os, subprocess
+    from simples_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [("simples_em_args", _lib.EmArgs), ("simples_em_out", _lib.EmOut), ("simples_mi_args", _lib.MiArgs),
+             ("simples_mi_out", _lib.MiOut), ("simples_lq_args", _lib.LqArgs), ("simples_lq_out", _lib.LqOut)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "simples_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname.rstrip("_")}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_argument_validation_without_gpu(built_lib):
     import simples_b200 as sb
     G, n, K0, M0 = 4, 3, 2, 1

@@ -276,3 +276,79 @@ def test_extreme_tails_and_degenerate_dropout_prior(sb):
     got = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
     assert np.all(np.isfinite(got["Y"])) and np.all(np.isfinite(ref["Y"]))
     assert_em_close(got, ref, M0)
+
+
+def _lq_case(K0, M0, n, G, seed, MB=None):
+    st = make_case(n, G, 3, 3, K0, M0, seed=seed, MB=MB)
+    em = O.em_impute_fast(*em_args(st, M0, K0, 3), celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=2)
+    rng = np.random.default_rng(seed)
+    G = st["Y"].shape[0]
+    lq = np.sort(rng.choice(G, size=G // 3, replace=False))
+    return st, em, lq, rng.uniform(0.4, 1.6, (len(lq), M0))
+
+
+@pytest.mark.parametrize("K0,M0,n,G,MB", [(4, 3, 150, 120, None), (1, 1, 90, 80, None), (7, 2, 333, 210, 2), (32, 4, 260, 150, None)])
+def test_lq_fit_matches_oracle(sb, K0, M0, n, G, MB):
+    """Row N1: lq-gene regression + imputation draw between the two EM calls (R/SIMPLE.R:305-411)."""
+    st, em, lq, sig = _lq_case(K0, M0, n, G, seed=31 + K0, MB=MB)
+    dat = np.asarray(st["Y0"])[lq]
+    init = np.asarray(st["Y"])[lq]
+    for mode, resp in ((0, None), (1, None), (1, init)):
+        got = sb.lq_fit(dat, sig, st["pg"][lq], em["z"], em["Ef"], em["Varf"], st["celltype"], penl=1, cutoff=0.1,
+                        resp=resp, resid_mode=mode, seed=17, sweep=1000)
+        ref = O.lq_regress_ref(dat, dat if resp is None else resp, sig, em["z"], em["Ef"], em["Varf"], 1, mode)
+        for k, r in zip(("mu", "beta", "sigma"), ref):
+            assert rel(got[k], r) <= 1e-8, (mode, k, rel(got[k], r))
+        assert np.array_equal(got["beta"] == 0, ref[1] == 0)
+        Yq = O.lq_impute_ref(dat, ref[0], ref[1], ref[2], st["pg"][lq], em["z"], em["Ef"], st["celltype"], 0.1, 17, 1000)
+        assert rel(got["Y"], Yq) <= 1e-6
+        obs = dat > 0.1
+        assert np.array_equal(got["Y"][obs], dat[obs])
+    only = sb.lq_fit(dat, sig, st["pg"][lq], em["z"], em["Ef"], em["Varf"], st["celltype"], impute=False)
+    assert only["Y"] is None and rel(only["beta"], O.lq_regress_ref(dat, dat, sig, em["z"], em["Ef"], em["Varf"], 1, 0)[1]) <= 1e-8
+
+
+def test_lq_fit_sharded_equals_single(sb):
+    """Cell shards passed one after another through a summing callback reproduce the unsharded call."""
+    import torch
+    K0, M0 = 4, 3
+    st, em, lq, sig = _lq_case(K0, M0, 200, 120, seed=77)
+    dat = np.asarray(st["Y0"])[lq]
+    full = sb.lq_fit(dat, sig, st["pg"][lq], em["z"], em["Ef"], em["Varf"], st["celltype"], resid_mode=1, seed=5, sweep=9)
+    n = dat.shape[1]
+    cuts = [0, 72, n]
+
+    class Rec:      # pass 1 records each shard's statistics; pass 2 replaces them by the global sum
+        def __init__(self, n_total, off):
+            self.n_total, self.cell_offset, self.seen, self.total = n_total, off, [], None
+        def allreduce_sum_(self, ptr, count, stream):
+            buf = _dev_view(ptr, count, stream)
+            if self.total is None:
+                self.seen.append(buf.clone())
+            else:
+                buf.copy_(self.total[len(self.seen)])
+                self.seen.append(None)
+            torch.cuda.synchronize()
+
+    def _dev_view(ptr, count, stream):
+        class W:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        torch.cuda.synchronize()
+        return torch.as_tensor(W(), device="cuda")
+
+    def run(comm, lo, hi):
+        return sb.lq_fit(dat[:, lo:hi], sig, st["pg"][lq], em["z"][lo:hi], [e[lo:hi] for e in em["Ef"]], em["Varf"],
+                         st["celltype"][lo:hi], resid_mode=1, seed=5, sweep=9, comm=comm)
+
+    recs = [Rec(n, cuts[r]) for r in range(2)]
+    for r in range(2):
+        run(recs[r], cuts[r], cuts[r + 1])
+    totals = [recs[0].seen[j] + recs[1].seen[j] for j in range(len(recs[0].seen))]
+    outs = []
+    for r in range(2):
+        c = Rec(n, cuts[r])
+        c.total = totals
+        outs.append(run(c, cuts[r], cuts[r + 1]))
+    for k in ("mu", "beta", "sigma"):
+        assert rel(outs[0][k], full[k]) <= 1e-10 and np.array_equal(outs[0][k], outs[1][k])
+    assert rel(np.concatenate([outs[0]["Y"], outs[1]["Y"]], axis=1), full["Y"]) <= 1e-9

@@ -256,3 +256,40 @@ def test_device_math_restatement():
     x = np.linspace(-12, 12, 240001)
     pf = 0.5 + 0.5 * np.tanh(0.7978845608 * (x + 0.044715 * x ** 3))
     assert np.abs(pf - special.ndtr(x)).max() < 2e-4                  # + MUFU.TANH 2^-11 rel => < 5e-4 < band 1.5e-3
+
+
+@pytest.mark.parametrize("K0,M0", [(4, 3), (1, 1), (6, 2)])
+def test_lq_regression_literal_vs_profiled(K0, M0):
+    """Row N1 oracle: the augmented-design restatement of R/SIMPLE.R:312-366 equals the sufficient-statistic form with
+    the unpenalised intercepts profiled out; unpenalised coordinates satisfy the normal equations exactly."""
+    st = make_case(150, 120, 3, 3, K0, M0, seed=5)
+    em = O.em_impute_fast(*em_args(st, M0, K0, 3), celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=2)
+    lq = np.arange(30, 70)
+    dat = np.asarray(st["Y0"])[lq]
+    sig = np.random.default_rng(0).uniform(0.5, 1.5, (len(lq), M0))
+    for mode, resp in ((0, dat), (1, dat), (1, np.asarray(st["Y"])[lq])):
+        a = O.lq_regress_ref(dat, resp, sig, em["z"], em["Ef"], em["Varf"], 1, mode)
+        b = O.lq_regress_fast(dat, resp, sig, em["z"], em["Ef"], em["Varf"], 1, mode)
+        for x, y in zip(a, b):
+            assert rel(x, y) <= 1e-11
+    # intercept normal equations: sum_i z_im (y_i - mu_m - Ef_m[i,] b) = 0
+    mu, beta, _ = a
+    resp = np.asarray(st["Y"])[lq]
+    for m in range(M0):
+        r = (resp - mu[:, m][:, None] - beta @ em["Ef"][m].T) @ em["z"][:, m]
+        assert np.abs(r).max() <= 1e-8 * max(1.0, np.abs(resp).sum(axis=1).max())
+    Yq = O.lq_impute_ref(dat, mu, beta, a[2], st["pg"][lq], em["z"], em["Ef"], st["celltype"], 0.1, 3, 0)
+    assert np.isfinite(Yq).all() and np.array_equal(Yq[dat > 0.1], dat[dat > 0.1]) and not np.array_equal(Yq, dat)
+
+
+def test_lasso_unpenalised_coordinates():
+    rng = np.random.default_rng(4)
+    X = rng.normal(size=(60, 6))
+    y = rng.normal(size=60)
+    A, rhs = X.T @ X, X.T @ y
+    kap = np.array([0, 0, 8.0, 8.0, 8.0, 8.0])
+    b = O.lasso_solve(A, rhs, kap)
+    g = rhs - A @ b
+    assert np.abs(g[:2]).max() <= 1e-9                      # unpenalised: exact stationarity
+    for k in range(2, 6):
+        assert abs(g[k] - kap[k] * np.sign(b[k])) <= 1e-9 if b[k] != 0 else abs(g[k]) <= kap[k] + 1e-9
