@@ -183,6 +183,31 @@ typedef struct simples_lq_out {
     double *Y;                      /* Gq x n  dat with the entries <= cutoff redrawn (NULL when impute = 0) */
 } simples_lq_out;
 
+/* ---- initial per-gene fit + imputation ------------------------------------
+ * init_impute (R/SIMPLE.R:15-73) when pg1 = NULL, init_impute_bulk
+ * (R/SIMPLE_B.R:23-114) when pg1 is given; both fit every gene within every
+ * cluster by ztruncnorm (R/fit_ztrunc.R:55-134: Brent on the profile
+ * likelihoods LL / LLwZ) and redraw the entries <= cutoff once. */
+typedef struct simples_init_args {
+    int32_t G, n, M0;
+    const double *Y2;               /* G x n                                            */
+    const int32_t *clus;            /* n, labels 1..M0                                  */
+    const double *pg1;              /* NULL, or G x M0 upper bounds of pg (bulk variant) */
+    double p_min, cutoff;           /* p_min is ignored (0.01) in the bulk variant      */
+    uint64_t seed;
+    uint32_t sweep;                 /* tape position of the draw                        */
+    int64_t n_total, cell_offset;
+    simples_allreduce_fn allreduce;
+    void *allreduce_user;
+    void *stream;
+} simples_init_args;
+
+typedef struct simples_init_out {
+    double *impute;                 /* G x n                                            */
+    double *pg;                     /* G x M0: init_impute's second return value; the per-cluster fitted pg in the bulk variant */
+    double *mu, *sd;                /* G x M0 fitted per-cluster mean / sd (optional, may be NULL) */
+} simples_init_out;
+
 /* ---- lifecycle / errors ------------------------------------------------ */
 SIMPLES_API int simples_abi_version(void);
 /* Select the device this process drives (ndev must be 1: one process per GPU). */
@@ -194,6 +219,7 @@ SIMPLES_API const char *simples_last_error(void);
 SIMPLES_API int simples_em_impute(const simples_em_args *args, simples_em_out *out);
 SIMPLES_API int simples_do_impute(const simples_mi_args *args, simples_mi_out *out);
 SIMPLES_API int simples_lq_fit(const simples_lq_args *args, simples_lq_out *out);
+SIMPLES_API int simples_init_impute(const simples_init_args *args, simples_init_out *out);
 
 /* ---- resident-context API (keeps Y/mask/state in HBM between calls; used
  *      by SIMPLE()-level drivers and by bench.py's device-resident timing) -- */

@@ -36,6 +36,7 @@ __all__ = [
     "em_impute_ref", "em_impute_fast", "do_impute_ref",
     "simulate", "bench_state", "expected_impute", "yimp0_ref", "bic_ref",
     "lq_regress_ref", "lq_regress_fast", "lq_impute_ref",
+    "brent_fmin", "ztruncnorm_ref", "init_impute_ref", "init_impute_bulk_ref",
 ]
 
 PI_REF = 3.14159265359          # R/EM_impute.R:80, R/do_impute.R:31  (Q2)
@@ -889,3 +890,207 @@ def lq_impute_ref(dat, mu, beta, sigma, pg, z, Ef, celltype, cutoff=0.1, seed=0,
     sample_sweep(Y, dat <= cutoff, z, Ef, [np.zeros((K0, K0))] * M0, mu, beta, sigma, np.asarray(pg), celltype0,
                  np.zeros(Gq), np.ones(Gq), cutoff, seed, sweep, cell0, draw_membership=(M0 > 1), clip=False)
     return Y
+
+
+# ----------------------------------------------------------------------------
+# N2: per-gene zero-inflated censored-normal fit and the initial imputation
+# (R/fit_ztrunc.R:2-134, R/SIMPLE.R:15-73, R/SIMPLE_B.R:23-114)
+# ----------------------------------------------------------------------------
+_DBL_MAX = float(np.finfo(np.float64).max)
+_BRENT_TOL = math.sqrt(np.finfo(np.float64).eps)        # optim(method="Brent") -> optimize(tol = con$reltol)
+
+
+def brent_fmin(f, ax, bx, tol=_BRENT_TOL):
+    """Brent's golden-section / parabolic-interpolation minimiser on [ax, bx] -- the published Netlib `fmin`
+    (Forsythe, Malcolm & Moler 1977; Brent 1973) that stats::optimize documents as its algorithm and that
+    optim(method = "Brent") calls (R/fit_ztrunc.R:80-83, 116-120).  Third-party arithmetic not in /root/reference:
+    base R `stats` (no pinned version).  Non-finite function values are replaced by DBL_MAX as optimize does."""
+    def fv_(x):
+        v = f(x)
+        return v if math.isfinite(v) else _DBL_MAX
+    c = (3.0 - math.sqrt(5.0)) * 0.5
+    eps = math.sqrt(np.finfo(np.float64).eps)              # ~ square root of the relative machine precision
+    a, b = ax, bx
+    v = a + c * (b - a)
+    w = x = v
+    d = e = 0.0
+    fx = fv_(x)
+    fv = fw = fx
+    tol3 = tol / 3.0
+    while True:
+        xm = (a + b) * 0.5
+        tol1 = eps * abs(x) + tol3
+        t2 = tol1 * 2.0
+        if abs(x - xm) <= t2 - (b - a) * 0.5:
+            break
+        p = q = r = 0.0
+        if abs(e) > tol1:                       # fit a parabola
+            r = (x - w) * (fx - fv)
+            q = (x - v) * (fx - fw)
+            p = (x - v) * q - (x - w) * r
+            q = (q - r) * 2.0
+            if q > 0.0:
+                p = -p
+            else:
+                q = -q
+            r = e
+            e = d
+        if abs(p) >= abs(q * 0.5 * r) or p <= q * (a - x) or p >= q * (b - x):
+            e = (b - x) if x < xm else (a - x)  # golden-section step
+            d = c * e
+        else:                                   # parabolic step
+            d = p / q
+            u = x + d
+            if u - a < t2 or b - u < t2:
+                d = tol1 if x < xm else -tol1
+        if abs(d) >= tol1:
+            u = x + d
+        elif d > 0.0:
+            u = x + tol1
+        else:
+            u = x - tol1
+        fu = fv_(u)
+        if fu <= fx:
+            if u < x:
+                b = x
+            else:
+                a = x
+            v, w, x = w, x, u
+            fv, fw, fx = fw, fx, fu
+        else:
+            if u < x:
+                a = u
+            else:
+                b = u
+            if fu <= fw or w == x:
+                v, fv = w, fw
+                w, fw = u, fu
+            elif fu <= fv or v == x or v == w:
+                v, fv = u, fu
+    return x
+
+
+def _LL(sigma, xbar, Sx, delta):                                             # R/fit_ztrunc.R:2-10
+    mu = xbar + (Sx - sigma * sigma) / (xbar - delta)
+    return math.log(sigma) + (Sx + (xbar - mu) ** 2) / 2 / (sigma * sigma) + float(special.log_ndtr((mu - delta) / sigma))
+
+
+def _LLwZ(sigma, xbar, Sx, r01, p, delta):                                   # R/fit_ztrunc.R:18-25
+    mu = xbar + (Sx - sigma * sigma) / (xbar - delta)
+    phi = float(special.ndtr((delta - mu) / sigma))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lg = float(np.log(np.float64(1 - p + p * phi)))
+        return math.log(sigma) + (Sx + (xbar - mu) ** 2) / 2 / (sigma * sigma) - float(np.float64(r01) * lg)
+
+
+def ztruncnorm_ref(dat, cutoff=0.1, s_upper=4.0, s_lower=0.1, p_min=0.6, p_max=1.0):
+    """R/fit_ztrunc.R:55-134.  NA is NaN.  Returns (param (G, 2), pg (G,))."""
+    dat = np.asarray(dat, dtype=np.float64)
+    G, n = dat.shape
+    pos = dat > cutoff
+    n1 = pos.sum(axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mu = np.where(pos, dat, 0.0).sum(axis=1) / n1                        # :59 rowMeans(na.rm = T)
+        dev = np.where(pos, dat - mu[:, None], 0.0)
+        var = (dev * dev).sum(axis=1) / (n1 - 1.0)                           # :60 rowVars (NA when n1 < 2)
+        var = np.where(n1 >= 2, var, np.nan) * (n1 - 1.0) / n1               # :62
+    p_max = np.broadcast_to(np.asarray(p_max, dtype=np.float64), (G,)).copy()   # :64-66
+    param = np.full((G, 2), np.nan)
+    for g in range(G):                                                       # :70-93
+        if n1[g] < 4:
+            continue
+        s = brent_fmin(lambda sg: _LL(sg, mu[g], var[g], cutoff), s_lower, s_upper)
+        param[g] = (mu[g] + (var[g] - s * s) / (mu[g] - cutoff), s)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        n0 = n - n1                                                          # :96
+        r01 = n0 / n1.astype(np.float64)
+        p1 = n1 / float(n)
+        p11 = special.ndtr((param[:, 0] - cutoff) / param[:, 1])             # :99
+        pg = p1 / p11
+        ind = np.nonzero((pg > p_max) | np.isnan(pg))[0]                     # :102
+    pg[ind] = p_max[ind]
+    ind2 = np.nonzero(pg < p_min)[0]                                         # :104
+    pg[ind2] = p_min
+    for g in np.concatenate([ind, ind2]):                                    # :106-131 (later rows win on duplicates)
+        if np.isnan(var[g]):
+            param[g] = (-1.0, 0.5)
+            continue
+        s = brent_fmin(lambda sg: _LLwZ(sg, mu[g], var[g], r01[g], pg[g], cutoff), s_lower, s_upper)
+        param[g] = (mu[g] + (var[g] - s * s) / (mu[g] - cutoff), s)
+    return param, pg
+
+
+def _init_cluster_fit(Y2, sel, cutoff, p_min, p_max):
+    res, pgc = ztruncnorm_ref(Y2[:, sel], cutoff=cutoff, p_min=p_min, p_max=p_max)
+    mu, sd = res[:, 0].copy(), res[:, 1].copy()
+    na = np.isnan(mu)
+    if na.any():
+        sub = Y2[np.ix_(na, sel)]
+        mu[na] = sub.mean(axis=1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sd[na] = sub.std(axis=1, ddof=1) if sub.shape[1] > 1 else np.nan
+    return mu, sd, pgc, na
+
+
+def init_impute_ref(Y2, M0, clus, p_min=0.6, cutoff=0.1, seed=0, sweep=0, cell0=0):
+    """R/SIMPLE.R:15-73 with the draws taken from the Philox tape (entry stream, gene = row of Y2).
+    Returns (impute, pg, mu (G, M0), sd (G, M0))."""
+    Y2 = np.asarray(Y2, dtype=np.float64)
+    G, n = Y2.shape
+    clus = np.asarray(clus)
+    impute = Y2.copy()
+    pg = np.zeros((G, M0))
+    mus, sds_ = np.zeros((G, M0)), np.zeros((G, M0))
+    for i in range(M0):
+        sel = clus == i + 1
+        mu, sd, pgc, na = _init_cluster_fit(Y2, sel, cutoff, p_min, 1.0)     # :22-26
+        pg[:, i] = pgc
+        pg[pg > 0.99] = 0.99                                                 # :28 (whole matrix, every pass)
+        pg[na, i] = 1.0                                                      # :36
+        mus[:, i], sds_[:, i] = mu, sd
+        cells = np.nonzero(sel)[0]
+        gi, cj = np.nonzero(Y2[:, cells] <= cutoff)                          # :43
+        ci = cells[cj]
+        ms, sds, p = mu[gi], sd[gi], pg[gi, i]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = (cutoff - ms) / sds
+            prob = special.ndtr(r)                                           # :49
+            prob_drop = (1 - p) / (prob * p + (1 - p))                       # :50
+            ua, ub = entry_uniforms(seed, sweep, ci.astype(np.uint64) + np.uint64(cell0), gi)
+            x = np.where(ua < prob_drop, ms + sds * special.ndtri(ub), ms + sds * trunc_z(ub, r))   # :51-66
+        impute[gi, ci] = x
+    impute[np.isnan(impute)] = 0.0                                           # :69
+    return impute, pg, mus, sds_
+
+
+def init_impute_bulk_ref(Y2, clus, pg1, cutoff=0.1, seed=0, sweep=0, cell0=0):
+    """R/SIMPLE_B.R:23-114 (the `bulk` argument only feeds the verbose plots).  Three-way draw per zero entry:
+    dropout of an expressed gene / structural zero ~ N(-1, 0.5) / censored."""
+    Y2 = np.asarray(Y2, dtype=np.float64)
+    pg1 = np.asarray(pg1, dtype=np.float64)
+    clus = np.asarray(clus)
+    impute0 = Y2.copy()
+    M0 = int(clus.max())                                                     # :28
+    for i in range(M0):
+        sel = clus == i + 1
+        mu, sd, pgc, na = _init_cluster_fit(Y2, sel, cutoff, 0.01, pg1[:, i])   # :34
+        pgc = pgc.copy()
+        pgc[na] = pg1[na, i]                                                 # :45
+        cells = np.nonzero(sel)[0]
+        gi, cj = np.nonzero(Y2[:, cells] <= cutoff)                          # :68
+        ci = cells[cj]
+        m_, s_, p, q1 = mu[gi], sd[gi], pgc[gi], pg1[gi, i]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = (cutoff - m_) / s_
+            prob = special.ndtr(r)                                           # :71
+            den = prob * p + (1 - p)
+            prob_drop = (p / q1 - p) / den                                   # :75
+            prob_zero = (1 - p / q1) / den                                   # :78
+            ua, ub = entry_uniforms(seed, sweep, ci.astype(np.uint64) + np.uint64(cell0), gi)
+            zq = special.ndtri(ub)
+            x = np.where(ua < prob_drop, m_ + s_ * zq,                       # :85-86
+                         np.where(ua < prob_drop + prob_zero, -1.0 + 0.5 * zq,   # :89-90
+                                  m_ + s_ * trunc_z(ub, r)))                 # :92-93
+        impute0[gi, ci] = x
+    impute0[np.isnan(impute0)] = 0.0                                         # :108
+    return impute0

@@ -335,6 +335,55 @@ def lq_fit(dat, sigma, pg, z, Ef, Varf, celltype=None, penl=1, cutoff=0.1, *, re
     return bufs
 
 
+def _init_call(Y2, M0, clus, pg1, p_min, cutoff, seed, sweep, comm, stream, details):
+    lib = _lib.load()
+    Y2 = _f(Y2)
+    G, n = Y2.shape
+    cl = np.ascontiguousarray(np.asarray(clus).astype(np.int32))
+    if cl.shape != (n,):
+        raise ValueError("clus must have length n")
+    keep = dict(Y2=Y2, clus=cl, pg1=None if pg1 is None else _f(pg1, (G, M0), "pg1"))
+    a = _lib.InitArgs()
+    a.G, a.n, a.M0 = G, n, int(M0)
+    for k, v in keep.items():
+        setattr(a, k, _ptr(v))
+    a.p_min, a.cutoff = float(p_min), float(cutoff)
+    a.seed, a.sweep = int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep)
+    cw = None
+    if comm is not None:
+        cw = _Comm(comm)
+        a.n_total, a.cell_offset, a.allreduce = int(comm.n_total), int(comm.cell_offset), cw.cb
+    a.stream = stream
+    bufs = dict(impute=np.empty((G, n), order="F"), pg=np.empty((G, M0), order="F"),
+                mu=np.empty((G, M0), order="F") if details else None, sd=np.empty((G, M0), order="F") if details else None)
+    o = _lib.InitOut()
+    for k, v in bufs.items():
+        setattr(o, k, _ptr(v))
+    rc = lib.simples_init_impute(C.byref(a), C.byref(o))
+    if rc < 0 and cw is not None and cw.error is not None:
+        raise cw.error
+    check(rc)
+    return bufs
+
+
+def init_impute(Y2, M0, clus, p_min=0.6, cutoff=0.1, verbose=False, *, seed=0, sweep=0, comm=None, stream=None,
+                details=False):
+    """``init_impute`` (R/SIMPLE.R:15-73) on B200: per cluster and gene the zero-inflated censored-normal fit of
+    ``ztruncnorm`` (R/fit_ztrunc.R:55-134), then one draw of every entry <= cutoff.  Returns ``[impute, pg]`` like the
+    reference (``details=True`` appends the fitted per-cluster mean and sd)."""
+    b = _init_call(Y2, M0, clus, None, p_min, cutoff, seed, sweep, comm, stream, details)
+    return [b["impute"], b["pg"]] + ([b["mu"], b["sd"]] if details else [])
+
+
+def init_impute_bulk(Y2, clus, bulk, pg1, cutoff=0.1, verbose=False, *, seed=0, sweep=0, comm=None, stream=None,
+                     details=False):
+    """``init_impute_bulk`` (R/SIMPLE_B.R:23-114) on B200; ``bulk`` only feeds the reference's verbose plots and is
+    ignored.  Returns the imputed matrix (``details=True``: ``[impute0, pg, mu, sd]``)."""
+    M0 = int(np.max(clus))
+    b = _init_call(Y2, M0, clus, pg1, 0.01, cutoff, seed, sweep, comm, stream, details)
+    return [b["impute"], b["pg"], b["mu"], b["sd"]] if details else b["impute"]
+
+
 def bic(loglik_last, n, G, K0, M0):
     """(BIC, BIC0) of SIMPLE()/SIMPLE_B() (R/SIMPLE.R:429-430); ``n`` is the global number of cells."""
     b, b0 = C.c_double(), C.c_double()

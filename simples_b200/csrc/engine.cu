@@ -1151,4 +1151,65 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     return SIMPLES_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// init_impute / init_impute_bulk (R/SIMPLE.R:15-73, R/SIMPLE_B.R:23-114)
+int simples_init_impute(const simples_init_args* a, simples_init_out* o) {
+    if (!a || !o) return fail(SIMPLES_EINVAL, "null argument");
+    if (a->G < 1 || a->n < 1) return fail(SIMPLES_EINVAL, "G and n must be >= 1");
+    if (a->M0 < 1 || a->M0 > MAXM) return fail(SIMPLES_EINVAL, "M0 must be in [1, 32]");
+    if (!a->Y2 || !a->clus || !o->impute) return fail(SIMPLES_EINVAL, "Y2, clus and out->impute are required");
+    if (a->n_total != 0 && a->n_total < a->n) return fail(SIMPLES_EINVAL, "n_total < n");
+    const int G = a->G, n = a->n, M0 = a->M0;
+    std::vector<int32_t> c0(n);
+    std::vector<double> cnt(M0, 0.0);
+    for (int i = 0; i < n; ++i) {
+        if (a->clus[i] < 1 || a->clus[i] > M0) return fail(SIMPLES_EINVAL, "clus must be in 1..M0");
+        c0[i] = a->clus[i] - 1;
+        cnt[c0[i]] += 1.0;
+    }
+    CKR(ensure_device());
+    std::unique_ptr<simples_ctx> guard(new simples_ctx());
+    simples_ctx* c = guard.get();
+    c->kind = 3;
+    if (a->stream) {
+        c->stream = (cudaStream_t)a->stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->allreduce = a->allreduce;
+    c->allreduce_user = a->allreduce_user;
+    const size_t GM = size_t(G) * M0, nst = 5 * GM;
+    double *Y2 = nullptr, *part = nullptr, *stats = nullptr, *pg1 = nullptr, *fit = nullptr;
+    int32_t* clus0 = nullptr;
+    const int nsplit = init_stats_splits(n);
+    CKR(c->dalloc(&Y2, size_t(n) * G, false));
+    CKR(c->dalloc(&clus0, size_t(n), false));
+    CKR(c->dalloc(&part, size_t(nsplit) * nst));
+    CKR(c->dalloc(&stats, nst + M0));
+    CKR(c->dalloc(&fit, 4 * GM));
+    CK(cudaMemcpyAsync(Y2, a->Y2, size_t(n) * G * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(clus0, c0.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(stats + nst, cnt.data(), size_t(M0) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (a->pg1) {
+        CKR(c->dalloc(&pg1, GM, false));
+        CK(cudaMemcpyAsync(pg1, a->pg1, GM * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    launch_init_stats(Y2, clus0, n, G, M0, a->cutoff, part, nsplit, c->stream);
+    launch_reduce_parts(part, stats, nst, nsplit, c->stream);
+    CKR(allreduce(c, stats, nst + M0));
+    InitFitArgs fa{stats, G, M0, a->cutoff, a->p_min, 0.1, 4.0, pg1, fit, fit + GM, fit + 2 * GM, fit + 3 * GM};
+    launch_ztrunc(fa, c->stream);
+    InitDrawArgs da{Y2, Y2, clus0, n, G, fit, fit + GM, fit + 2 * GM, pg1, a->cutoff, a->seed, a->sweep, a->cell_offset};
+    launch_init_draw(da, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(o->impute, Y2, size_t(n) * G * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (o->pg) CK(cudaMemcpyAsync(o->pg, fit + 3 * GM, GM * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (o->mu) CK(cudaMemcpyAsync(o->mu, fit, GM * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (o->sd) CK(cudaMemcpyAsync(o->sd, fit + GM, GM * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
 }  // extern "C"

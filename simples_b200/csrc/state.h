@@ -179,6 +179,24 @@ struct LqCellArgs {
 void launch_lq_cell(const LqCellArgs& a, cudaStream_t st);
 void launch_colsum(const double* z, double* out, int n, int M0, cudaStream_t st);   // out [2 M0 + 1] = [colSums(z) | 0...]
 
+// initial fit + imputation (R/fit_ztrunc.R, R/SIMPLE.R:15-73, R/SIMPLE_B.R:23-114); Y2 is [n][G] unpadded
+struct InitFitArgs {
+    const double* stats;      // [M0][5][G] moments | [M0] cluster sizes
+    int G, M0; double cutoff, p_min, s_lower, s_upper;
+    const double* pg1;        // [M0][G] or nullptr
+    double *mu, *sd, *pg_used, *pg_ret;   // [M0][G]
+};
+struct InitDrawArgs {
+    const double* Y2; double* out; const int32_t* clus0; int n, G;
+    const double *mu, *sd, *pg_used, *pg1; double cutoff;
+    unsigned long long seed; unsigned sweep; long long cell_offset;
+};
+int init_stats_splits(int n);
+void launch_init_stats(const double* Y2, const int32_t* clus0, int n, int G, int M0, double cutoff, double* part, int nsplit,
+                       cudaStream_t st);
+void launch_ztrunc(const InitFitArgs& a, cudaStream_t st);
+void launch_init_draw(const InitDrawArgs& a, cudaStream_t st);
+
 // misc
 void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int cell0, int n_alloc, int G, int ldG, double cutoff,
                        unsigned long long* nnz, cudaStream_t st);

@@ -293,3 +293,46 @@ def test_lasso_unpenalised_coordinates():
     assert np.abs(g[:2]).max() <= 1e-9                      # unpenalised: exact stationarity
     for k in range(2, 6):
         assert abs(g[k] - kap[k] * np.sign(b[k])) <= 1e-9 if b[k] != 0 else abs(g[k]) <= kap[k] + 1e-9
+
+
+def test_brent_fmin_against_derivative_root():
+    from scipy import optimize
+    f = lambda x: (x - 1.3) ** 2 + 0.1 * math.sin(5 * x)
+    root = optimize.brentq(lambda x: 2 * (x - 1.3) + 0.5 * math.cos(5 * x), 1.0, 1.2, xtol=1e-14)
+    assert abs(O.brent_fmin(f, 0.1, 4.0) - root) <= 3e-8 * root + 1e-8
+    assert O.brent_fmin(lambda x: x, 0.1, 4.0) - 0.1 <= 1e-7          # boundary minimum
+    assert O.brent_fmin(lambda x: float("nan"), 0.1, 4.0) > 0.1        # non-finite values -> DBL_MAX, still terminates
+
+
+def test_ztruncnorm_recovers_censored_normal():
+    """Row N2 oracle: ztruncnorm (R/fit_ztrunc.R:55-134) on exact zero-inflated censored-normal data."""
+    rng = np.random.default_rng(8)
+    G, n = 40, 4000
+    mu = rng.uniform(0.5, 3.0, G)
+    sd = rng.uniform(0.4, 1.2, G)
+    p = rng.uniform(0.65, 0.95, G)
+    x = mu[:, None] + sd[:, None] * rng.normal(size=(G, n))
+    x[rng.uniform(size=(G, n)) > p[:, None]] = 0.0
+    x[x <= 0.1] = 0.0
+    par, pg = O.ztruncnorm_ref(x, cutoff=0.1, p_min=0.6, p_max=1.0)
+    assert np.abs(par[:, 0] - mu).max() <= 0.25 and np.abs(par[:, 1] - sd).max() <= 0.15
+    assert np.abs(pg - p).max() <= 0.08
+    # NA / refit rules: < 2 positives -> (-1, 0.5) with pg = p_max; 2-3 positives are refitted by LLwZ
+    y = np.zeros((3, 50))
+    y[1, :3] = (1.0, 2.0, 1.5)
+    y[2, :1] = 2.0
+    par2, pg2 = O.ztruncnorm_ref(y, cutoff=0.1, p_min=0.6, p_max=1.0)
+    assert np.array_equal(par2[0], (-1.0, 0.5)) and np.array_equal(par2[2], (-1.0, 0.5)) and pg2[0] == 1.0
+    assert np.isfinite(par2[1]).all() and 0.1 <= par2[1, 1] <= 4.0
+
+
+def test_init_impute_oracle_quirks():
+    sim = O.simulate(n=240, G=150, K=3, MC=3, S0=10, seed=3)
+    Y2, clus = sim["Y2"], sim["Z"]
+    imp, pg, mu, sd = O.init_impute_ref(Y2, 3, clus, 0.4, 0.1, seed=1)
+    assert np.isfinite(imp).all() and np.array_equal(imp[Y2 > 0.1], Y2[Y2 > 0.1])
+    assert (imp[Y2 <= 0.1] != Y2[Y2 <= 0.1]).mean() > 0.99
+    assert pg.max() <= 1.0 and pg[:, :2].max() <= 0.99 and pg.min() >= 0.4      # R/SIMPLE.R:28 re-applied each pass
+    pg1 = np.clip(np.random.default_rng(0).uniform(0.05, 1.2, (Y2.shape[0], 3)), 0.1, 1.0)
+    impb = O.init_impute_bulk_ref(Y2, clus, pg1, 0.1, seed=2)
+    assert np.isfinite(impb).all() and np.array_equal(impb[Y2 > 0.1], Y2[Y2 > 0.1])
