@@ -37,6 +37,7 @@ __all__ = [
     "simulate", "bench_state", "expected_impute", "yimp0_ref", "bic_ref",
     "lq_regress_ref", "lq_regress_fast", "lq_impute_ref",
     "brent_fmin", "ztruncnorm_ref", "init_impute_ref", "init_impute_bulk_ref",
+    "simple_ref", "simple_b_ref", "select_km_ref",
 ]
 
 PI_REF = 3.14159265359          # R/EM_impute.R:80, R/do_impute.R:31  (Q2)
@@ -1094,3 +1095,145 @@ def init_impute_bulk_ref(Y2, clus, pg1, cutoff=0.1, seed=0, sweep=0, cell0=0):
         impute0[gi, ci] = x
     impute0[np.isnan(impute0)] = 0.0                                         # :108
     return impute0
+
+
+# ----------------------------------------------------------------------------
+# N3: the run-level drivers SIMPLE / SIMPLE_B / selectKM
+# (R/SIMPLE.R:200-455, R/SIMPLE_B.R:229-455, R/select_KM.R:126-189).
+# Each stage draws from its own Philox key seed + stage (same numbering as the product driver).
+# ----------------------------------------------------------------------------
+ST_PMIN, ST_INIT, ST_EM_HQ, ST_LQ, ST_EM_ALL, ST_MI, ST_CLUS, ST_BETA = range(8)
+
+
+def _hq_genes_ref(dat, cutoff, p_min, min_gene, fix_num):
+    n1 = (dat > cutoff).mean(axis=1)                                         # R/SIMPLE.R:246
+    if fix_num:
+        return np.argsort(-n1, kind="stable")[:min_gene]                     # :248
+    hq = np.nonzero(n1 >= p_min)[0]                                          # :250
+    if len(hq) < min_gene:
+        hq = np.argsort(-n1, kind="stable")[:min_gene]                       # :253
+    return hq
+
+
+def _driver_tail(dat, Y, pg, hq, em_hq, beta, sigma, mu, celltype, M0, K0, iter, penl, est_z, max_lambda, est_lam,
+                 sigma0, pi_alpha, num_mc, cutoff, seed, resp, resid_mode, mcmc, burnin, extra):
+    G, n = dat.shape
+    beta[hq], sigma[hq], mu[hq] = em_hq["beta"], em_hq["sigma"], em_hq["mu"]   # R/SIMPLE.R:298-300
+    Y[hq] = em_hq["Y"]                                                       # :301
+    lq = np.setdiff1d(np.arange(G), hq)                                      # :310
+    m_, b_, s_ = lq_regress_fast(dat[lq], dat[lq] if resp is None else resp[lq], sigma[lq], em_hq["z"], em_hq["Ef"],
+                                 em_hq["Varf"], penl, resid_mode)            # :312-366
+    mu[lq], beta[lq], sigma[lq] = m_, b_, s_                                 # :368-371
+    np.clip(sigma, 1e-4, 9.0, out=sigma)                                     # :372-373
+    Y[lq] = lq_impute_ref(dat[lq], m_, b_, sigma[lq], pg[lq], em_hq["z"], em_hq["Ef"], celltype, cutoff,
+                          seed + ST_LQ, 0)                                   # :376-411
+    em = em_impute_fast(Y, dat, pg, M0, K0, cutoff, iter, beta, sigma, em_hq["lambda"], em_hq["pi"], em_hq["z"],
+                        mu=None, celltype=celltype, penl=penl, est_z=est_z, max_lambda=max_lambda, est_lam=est_lam,
+                        impt_it=1, sigma0=sigma0, pi_alpha=pi_alpha, num_mc=num_mc, seed=seed + ST_EM_ALL)   # :414-419
+    bic, bic0 = bic_ref(em["loglik"][-1], n, G, K0, M0)                      # :427-430
+    out = dict(loglik_tot=em["loglik"], priorB=em["priorB"], loglik=None, BIC=bic, BIC0=bic0, pi=em["pi"], mu=em["mu"],
+               sigma=em["sigma"], beta=em["beta"], z=em["z"], Yimp0=yimp0_ref(em), pg=pg)
+    out["lambda"] = em["lambda"]
+    if mcmc > 0:                                                             # :431-446
+        mi = do_impute_ref(dat, em["Y"], em["beta"], em["lambda"], em["sigma"], em["mu"], em["pi"], em["geneM"],
+                           em["geneSd"], celltype, mcmc=mcmc, burnin=burnin, pg=pg, cutoff=cutoff, seed=seed + ST_MI)
+        out.update(loglik=mi["loglik"], impt=mi["impt"], impt_var=mi["impt_var"], Ef=mi["EF"], Varf=mi["varF"],
+                   consensus_cluster=mi["consensus_cluster"])
+    else:                                                                    # :447-453
+        out.update(impt=em["Y"], impt_var=None, Ef=em["Ef"], Varf=em["Varf"], consensus_cluster=None)
+    out.update(extra)
+    return out
+
+
+def _driver_defaults(G, K0, M0, beta, lam, sigma, mu, seed):
+    pi = np.full(M0, 1.0 / M0)                                               # R/SIMPLE.R:210
+    lam = np.full((M0, K0), 1.0 / M0) if lam is None else np.asarray(lam, dtype=np.float64)
+    mu = np.zeros((G, M0)) if mu is None else np.array(mu, dtype=np.float64)
+    sigma = np.ones((G, M0)) if sigma is None else np.array(sigma, dtype=np.float64)
+    if beta is None:
+        beta = np.random.default_rng(seed + ST_BETA).normal(size=(G, K0)) / math.sqrt(K0) * math.sqrt(M0)   # :224-226
+    return pi, lam, mu, sigma, np.array(beta, dtype=np.float64)
+
+
+def simple_ref(dat, K0=10, M0=1, iter=10, est_lam=1, impt_it=5, penl=1, init_imp=None, sigma0=100, pi_alpha=1,
+               beta=None, max_lambda=True, lam=None, sigma=None, mu=None, est_z=1, clus=None, p_min=0.4, cutoff=0.1,
+               K=20, min_gene=2000, num_mc=3, fix_num=False, mcmc=50, burnin=2, seed=0):
+    """R/SIMPLE.R:200-455 with `clus` given (the clustering start is row N4)."""
+    dat = np.asarray(dat, dtype=np.float64)
+    G, n = dat.shape
+    Y = dat.copy()
+    pi, lam, mu, sigma, beta = _driver_defaults(G, K0, M0, beta, lam, sigma, mu, seed)
+    clus = np.asarray(clus)
+    if p_min is None:                                                        # :229-242
+        p_min = float(np.quantile(init_impute_ref(dat, M0, clus, 0.4, cutoff, seed + ST_PMIN)[1].ravel(), 0.25))
+    pg = np.full((G, M0), float(p_min))                                      # :243
+    hq = _hq_genes_ref(dat, cutoff, p_min, min_gene, fix_num)
+    z = np.zeros((n, M0))
+    z[np.arange(n), clus - 1] = 1.0                                          # :268-269
+    imp, pg_hq = init_impute_ref(dat[hq], M0, clus, p_min, cutoff, seed + ST_INIT)[:2]   # :276
+    start = imp if init_imp is None else np.asarray(init_imp)[hq]
+    em_hq = em_impute_fast(start, dat[hq], pg_hq, M0, K0, cutoff, 20, beta[hq], sigma[hq], lam, pi, z, mu=None,
+                           celltype=clus, penl=penl, est_z=est_z, max_lambda=max_lambda, est_lam=est_lam,
+                           impt_it=impt_it, sigma0=sigma0, pi_alpha=pi_alpha, num_mc=num_mc, seed=seed + ST_EM_HQ)   # :281-296
+    pg[hq] = pg_hq                                                           # :297
+    return _driver_tail(dat, Y, pg, hq, em_hq, beta, sigma, mu, clus, M0, K0, iter, penl, est_z, max_lambda, est_lam,
+                        sigma0, pi_alpha, num_mc, cutoff, seed, None if init_imp is None else np.asarray(init_imp),
+                        0 if init_imp is None else 1, mcmc, burnin, dict(initclus=clus, p_min=p_min))
+
+
+def simple_b_ref(dat, K0, bulk, celltype, M0=1, clus=None, b=1, iter=10, est_z=1, impt_it=3, max_lambda=False,
+                 est_lam=1, penl=1, sigma0=100, pi_alpha=1, beta=None, lam=None, sigma=None, mu=None, p_min=0.8,
+                 min_gene=300, cutoff=0.1, num_mc=3, fix_num=False, mcmc=50, burnin=2, seed=0):
+    """R/SIMPLE_B.R:229-455 with `clus` given."""
+    dat = np.asarray(dat, dtype=np.float64)
+    G, n = dat.shape
+    Y = dat.copy()
+    bulk = np.asarray(bulk, dtype=np.float64).reshape(G, -1)
+    celltype = np.asarray(celltype)
+    pi, lam, mu, sigma, beta = _driver_defaults(G, K0, M0, beta, lam, sigma, mu, seed)
+    hq = _hq_genes_ref(dat, cutoff, p_min, min_gene, fix_num)                # :258-266
+    MB = int(celltype.max())
+    pg = np.zeros((G, MB))
+    for i in range(MB):                                                      # :270-282
+        rm = dat[:, celltype == i + 1].mean(axis=1)
+        if b is None:
+            x, w = bulk[hq, i], bulk[hq, i] ** 2
+            b1 = float(np.sum(w * x * rm[hq]) / np.sum(w * x * x))           # coef(lm(y ~ 0 + x, weights = x^2))
+        else:
+            b1 = float(b)
+        pg[:, i] = (rm + p_min) / (1.0 + b1 * bulk[:, i])
+    np.clip(pg, 0.1, 1.0, out=pg)                                            # :284-285
+    res = init_impute_bulk_ref(dat[hq], celltype, pg[hq], cutoff, seed + ST_INIT)   # :289-290
+    clus = np.asarray(clus)
+    z = np.zeros((n, M0))
+    z[np.arange(n), clus - 1] = 1.0
+    em_hq = em_impute_fast(res, dat[hq], pg[hq], M0, K0, cutoff, 30, beta[hq], sigma[hq], lam, pi, z, mu=None,
+                           celltype=celltype, penl=penl, est_z=est_z, max_lambda=max_lambda, est_lam=est_lam,
+                           impt_it=impt_it, sigma0=sigma0, pi_alpha=pi_alpha, num_mc=num_mc, seed=seed + ST_EM_HQ)   # :318-321
+    return _driver_tail(dat, Y, pg, hq, em_hq, beta, sigma, mu, celltype, M0, K0, iter, penl, est_z, max_lambda, est_lam,
+                        sigma0, pi_alpha, num_mc, cutoff, seed, None, 1, mcmc, burnin, {})
+
+
+def select_km_ref(dat, K0, M0, rel=0.01, **kw):
+    """R/select_KM.R:126-189 (always through SIMPLE, Q18)."""
+    n = np.asarray(dat).shape[1]
+    Ms = sorted(set(np.atleast_1d(M0).astype(int).tolist()) | {1})
+    Ks = sorted(np.atleast_1d(K0).astype(int).tolist())
+    BICs = {m: {k: math.nan for k in Ks} for m in Ms}
+    best, mBIC, mK, mM, init_imp = {}, math.inf, None, None, None
+    clus_of = kw.pop("clus_of")
+    for M1 in Ms:
+        prev = math.inf
+        for K1 in Ks:
+            r = simple_ref(dat, K1, M1, init_imp=init_imp, clus=clus_of(M1), **kw)
+            crit = r["BIC0"] if n < 1000 else r["BIC"]
+            if mBIC > crit:
+                mBIC, mK, mM = crit, K1, M1
+                best[M1] = r
+            BICs[M1][K1] = crit
+            if (crit - prev) > -abs(crit) * rel:
+                break
+            prev = crit
+        if M1 == 1:
+            init_imp = best[1]["impt"]
+    return dict(BICs=BICs, mK=mK, mM=mM, result=best[mM])

@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         //      argument ub * Phi(r) (the only place the FP64 pnorm runs) and re-file them by quantile region:
         //      central -> appended to the Dc list, tail -> compacted back list.  Stored value < 0 marks a
         //      truncated draw (clamped to the cutoff, R/EM_impute.R:191-192).
+        // Re-filing appends to the front list while back-list slots are still unread, which is only safe when the
+        // two lists cannot meet: in a block dense in zeros (nDc + 2 nS > 256) the arguments are written IN PLACE
+        // instead and the back list is drained entry by entry afterwards (3c'').
+        const bool inplace = nDc + 2 * nS > 256;
         int nTail = 0;
         {
             const int srounds = (nS + 31) >> 5;
@@ -285,6 +289,10 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
                         toC = fabs(q - 0.5) <= 0.425;
                         toTail = !toC;
                     }
+                }
+                if (inplace) {                       // warp-uniform
+                    if (valid) dub[255 - e] = (toC || toTail) ? arg : 0.0;      // 0 marks "already finished"
+                    continue;
                 }
                 __syncwarp();                        // every lane has read its slot before slots are rewritten
                 const unsigned bC = __ballot_sync(0xffffffffu, toC);
@@ -323,6 +331,17 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
             double x = fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_tail(fabs(v)), msW[r * MSS + gl]);
             if (v < 0.0) x = fmin(x, a.cutoff);
             finish(r, gl, x);
+        }
+        // ---- 3c''. dense block: the whole back list, arguments in place, either quantile region ----
+        if (inplace) {
+            __syncwarp();
+#pragma unroll 1
+            for (int e = lane; e < nS; e += 32) {
+                const int code = dcode[255 - e];
+                const double v = dub[255 - e];
+                const int r = code >> 5, gl = code & 31;
+                if (v != 0.0) finish(r, gl, quantile_draw(msW[r * MSS + gl], b.sds[gl * M0 + cellinfo[r * 2]], a.cutoff, v));
+            }
         }
         // ---- 3d. inside the screening band: exact FP64 Bernoulli test and draw ----
 #pragma unroll 1

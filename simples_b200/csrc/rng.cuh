@@ -104,25 +104,12 @@ static __device__ __noinline__ double sample_entry(double ms, double sds, double
 }
 
 
-// Entry with a CERTAIN Bernoulli outcome that needs the slow quantile code (k_sweep list S):
-//   v > 0: dropout with a tail quantile, x = ms + sds qnorm(v);
-//   v < 0: expressed-but-below-cutoff, x = ms + sds min(qnorm(|v| Phi(r)), r)   (R/EM_impute.R:191-192).
-static __device__ __noinline__ double sample_slow(double ms, double sds, double isd, double cutoff, double v) {
-    const bool isT = v < 0.0;
-    const double ub = fabs(v);
-    double arg = ub, rr = 0.0;
-    if (isT) {
-        rr = (cutoff - ms) * isd;
-        arg = ub * pnorm(rr);
-    }
-    double z;
-    if (isT && rr < -30.0) {
-        z = trunc_z_deep(ub, rr);
-    } else {
-        z = qnorm(arg);
-        if (isT) z = fmin(z, rr);
-    }
-    return fma(sds, z, ms);
+// x = ms + sds Phi^-1(|v|) for an entry whose quantile argument is already known (k_sweep, dense blocks);
+// v < 0 marks a truncated draw, clamped to the cutoff (R/EM_impute.R:191-192).
+static __device__ __noinline__ double quantile_draw(double ms, double sds, double cutoff, double v) {
+    double x = fma(sds, qnorm(fabs(v)), ms);
+    if (v < 0.0) x = fmin(x, cutoff);
+    return x;
 }
 
 }  // namespace sb

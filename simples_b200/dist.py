@@ -75,6 +75,22 @@ class CellShard:
             t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def _host_reduce(self, x, op):
+        import torch
+        dist = self._dist
+        t = torch.from_numpy(np.array(x, dtype=np.float64))
+        if dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=op, group=self.group)
+        return t.cpu().numpy()
+
+    def sum_host(self, x):
+        """Sum of a small host array over the ranks (driver bookkeeping: gene expression rates, cluster sizes)."""
+        return self._host_reduce(x, self._dist.ReduceOp.SUM)
+
+    def max_host(self, x):
+        return self._host_reduce(x, self._dist.ReduceOp.MAX)
+
     def gather_cols(self, A_local):
         """Gather a G x n_local matrix from every rank into G x n_total (all ranks)."""
         import torch
