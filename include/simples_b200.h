@@ -208,6 +208,32 @@ typedef struct simples_init_out {
     double *mu, *sd;                /* G x M0 fitted per-cluster mean / sd (optional, may be NULL) */
 } simples_init_out;
 
+/* ---- initial clustering of the cells -------------------------------------
+ * R/SIMPLE.R:258-266 (= R/SIMPLE_B.R:293-302): rows of X standardised
+ * (scale), rank-K truncated SVD (irlba), cellmat = V diag(d), k-means with
+ * `nstart` random starts, best total within-cluster sum of squares wins.
+ * The SVD is the eigen-problem of the G x G Gram matrix (subspace iteration);
+ * k-means is Lloyd's algorithm, all restarts advanced together.  The
+ * reference's irlba start vector and Hartigan-Wong restarts are random, so
+ * agreement with it is at the level of the partition (ARI), not of numbers. */
+typedef struct simples_clus_args {
+    int32_t G, n, K, M0;
+    const double *X;                /* G x n (hq genes x cells)                         */
+    int32_t nstart, iter_max;       /* kmeans(nstart = 300, iter.max = 80)              */
+    uint64_t seed;
+    int64_t n_total, cell_offset;
+    simples_allreduce_fn allreduce;
+    void *allreduce_user;
+    void *stream;
+} simples_clus_args;
+
+typedef struct simples_clus_out {
+    int32_t *clus;                  /* n labels in 1..M0                                */
+    double *cellmat;                /* n x K  (V diag(d); column signs arbitrary) or NULL */
+    double *d;                      /* K singular values or NULL                        */
+    double *tot_withinss;           /* 1, of the winning start, or NULL                 */
+} simples_clus_out;
+
 /* ---- lifecycle / errors ------------------------------------------------ */
 SIMPLES_API int simples_abi_version(void);
 /* Select the device this process drives (ndev must be 1: one process per GPU). */
@@ -220,6 +246,7 @@ SIMPLES_API int simples_em_impute(const simples_em_args *args, simples_em_out *o
 SIMPLES_API int simples_do_impute(const simples_mi_args *args, simples_mi_out *out);
 SIMPLES_API int simples_lq_fit(const simples_lq_args *args, simples_lq_out *out);
 SIMPLES_API int simples_init_impute(const simples_init_args *args, simples_init_out *out);
+SIMPLES_API int simples_init_cluster(const simples_clus_args *args, simples_clus_out *out);
 
 /* ---- resident-context API (keeps Y/mask/state in HBM between calls; used
  *      by SIMPLE()-level drivers and by bench.py's device-resident timing) -- */

@@ -37,7 +37,7 @@ __all__ = [
     "simulate", "bench_state", "expected_impute", "yimp0_ref", "bic_ref",
     "lq_regress_ref", "lq_regress_fast", "lq_impute_ref",
     "brent_fmin", "ztruncnorm_ref", "init_impute_ref", "init_impute_bulk_ref",
-    "simple_ref", "simple_b_ref", "select_km_ref",
+    "simple_ref", "simple_b_ref", "select_km_ref", "init_cluster_ref", "adjusted_rand_index",
 ]
 
 PI_REF = 3.14159265359          # R/EM_impute.R:80, R/do_impute.R:31  (Q2)
@@ -1237,3 +1237,59 @@ def select_km_ref(dat, K0, M0, rel=0.01, **kw):
         if M1 == 1:
             init_imp = best[1]["impt"]
     return dict(BICs=BICs, mK=mK, mM=mM, result=best[mM])
+
+
+# ----------------------------------------------------------------------------
+# N4: initial clustering (R/SIMPLE.R:258-266, R/SIMPLE_B.R:293-302)
+# ----------------------------------------------------------------------------
+def init_cluster_ref(X, K, M0, nstart=300, iter_max=80, seed=0):
+    """t(scale(t(X))) -> rank-K SVD -> cellmat = V diag(d) -> k-means.  The SVD is exact (LAPACK) instead of irlba's
+    Lanczos iteration; k-means is Lloyd's algorithm from `nstart` sets of M0 distinct random cells (drawn from the
+    Philox cell stream: sweep = restart, cell = centre index, block = retry) instead of Hartigan-Wong with R's RNG, so
+    only the partition is comparable with the reference.  Returns (clus 1-based, cellmat, d, wss)."""
+    X = np.asarray(X, dtype=np.float64)
+    G, n = X.shape
+    sd = X.std(axis=1, ddof=1)
+    Xs = (X - X.mean(axis=1, keepdims=True)) / np.where(sd > 0, sd, 1.0)[:, None]      # :259
+    _, sv, Vt = np.linalg.svd(Xs, full_matrices=False)                                   # :261
+    cm = Vt[:K].T * sv[:K]                                                               # :263
+    best = (np.inf, None)
+    for r in range(nstart):                                                              # :264 nstart
+        picks = []
+        for j in range(M0):
+            t = 0
+            while True:
+                u0 = cell_uniforms(seed, r, np.array([j], dtype=np.uint64), 2 * t + 1)[0, 2 * t]
+                c = min(int(u0 * n), n - 1)
+                if c not in picks or t >= 64 or n <= j:
+                    picks.append(c)
+                    break
+                t += 1
+        cen = cm[picks].copy()
+        for _ in range(iter_max):
+            d2 = ((cm[:, None, :] - cen[None, :, :]) ** 2).sum(axis=2)
+            lab = np.argmin(d2, axis=1)
+            for j in range(M0):
+                if np.any(lab == j):
+                    cen[j] = cm[lab == j].mean(axis=0)
+        d2 = ((cm[:, None, :] - cen[None, :, :]) ** 2).sum(axis=2)
+        lab = np.argmin(d2, axis=1)
+        wss = float(d2[np.arange(n), lab].sum())
+        if wss < best[0]:
+            best = (wss, lab + 1)
+    return best[1], cm, sv[:K], best[0]
+
+
+def adjusted_rand_index(a, b):
+    """mclust::adjustedRandIndex, the reference's own agreement metric (utils/simulation.R:71-80)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    _, ai = np.unique(a, return_inverse=True)
+    _, bi = np.unique(b, return_inverse=True)
+    ct = np.zeros((ai.max() + 1, bi.max() + 1))
+    np.add.at(ct, (ai, bi), 1)
+    comb = lambda x: x * (x - 1) / 2.0
+    sij, sa, sb_ = comb(ct).sum(), comb(ct.sum(axis=1)).sum(), comb(ct.sum(axis=0)).sum()
+    exp = sa * sb_ / comb(len(a))
+    mx = 0.5 * (sa + sb_)
+    return float((sij - exp) / (mx - exp)) if mx != exp else 1.0

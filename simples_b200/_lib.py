@@ -103,9 +103,22 @@ class InitOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("impute", "pg", "mu", "sd")]
 
 
+class ClusArgs(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("n", C.c_int32), ("K", C.c_int32), ("M0", C.c_int32),
+        ("X", C.c_void_p), ("nstart", C.c_int32), ("iter_max", C.c_int32),
+        ("seed", C.c_uint64), ("n_total", C.c_int64), ("cell_offset", C.c_int64),
+        ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+class ClusOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("clus", "cellmat", "d", "tot_withinss")]
+
+
 EXPORTS = [
     "simples_abi_version", "simples_init", "simples_shutdown", "simples_last_error",
-    "simples_em_impute", "simples_do_impute", "simples_lq_fit", "simples_init_impute", "simples_em_create", "simples_em_run", "simples_em_fetch",
+    "simples_em_impute", "simples_do_impute", "simples_lq_fit", "simples_init_impute", "simples_init_cluster", "simples_em_create", "simples_em_run", "simples_em_fetch",
     "simples_em_sync", "simples_em_iter_ms", "simples_em_set_profile", "simples_em_profile",
     "simples_kernel_name", "simples_kernel_count", "simples_em_nnz0", "simples_em_kernel_launches",
     "simples_em_yimp0", "simples_bic",
@@ -132,6 +145,7 @@ def load():
     lib.simples_do_impute.argtypes = [C.POINTER(MiArgs), C.POINTER(MiOut)]
     lib.simples_lq_fit.argtypes = [C.POINTER(LqArgs), C.POINTER(LqOut)]
     lib.simples_init_impute.argtypes = [C.POINTER(InitArgs), C.POINTER(InitOut)]
+    lib.simples_init_cluster.argtypes = [C.POINTER(ClusArgs), C.POINTER(ClusOut)]
     lib.simples_em_create.argtypes = [C.POINTER(EmArgs), C.POINTER(C.c_void_p)]
     lib.simples_em_run.argtypes = [C.c_void_p, C.c_int]
     lib.simples_em_fetch.argtypes = [C.c_void_p, C.POINTER(EmOut)]

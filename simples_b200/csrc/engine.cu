@@ -1212,4 +1212,143 @@ int simples_init_impute(const simples_init_args* a, simples_init_out* o) {
     return SIMPLES_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// initial clustering (R/SIMPLE.R:258-266, R/SIMPLE_B.R:293-302)
+int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
+    if (!a || !o) return fail(SIMPLES_EINVAL, "null argument");
+    if (a->G < 2 || a->n < 2) return fail(SIMPLES_EINVAL, "G and n must be >= 2");
+    if (a->M0 < 1 || a->M0 > MAXM) return fail(SIMPLES_EINVAL, "M0 must be in [1, 32]");
+    if (a->K < 1 || a->K > 32 || a->K >= a->G) return fail(SIMPLES_EINVAL, "K must be in [1, 32] and < G");
+    if (!a->X || !o->clus) return fail(SIMPLES_EINVAL, "X and out->clus are required");
+    if (a->nstart < 1 || a->iter_max < 1) return fail(SIMPLES_EINVAL, "nstart and iter_max must be >= 1");
+    if (a->n_total != 0 && a->n_total < a->n) return fail(SIMPLES_EINVAL, "n_total < n");
+    CKR(ensure_device());
+    std::unique_ptr<simples_ctx> guard(new simples_ctx());
+    simples_ctx* c = guard.get();
+    c->kind = 4;
+    if (a->stream) {
+        c->stream = (cudaStream_t)a->stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->allreduce = a->allreduce;
+    c->allreduce_user = a->allreduce_user;
+    cudaStream_t st = c->stream;
+    const int G = a->G, n = a->n, K = a->K, M0 = a->M0, R = a->nstart;
+    const int ldG = round_up(G, GPAD), na = round_up(n, 128);
+    const long long n_total = a->n_total > 0 ? a->n_total : n;
+    const int KP = std::min(32, std::min(K + 10, G));          // subspace width (oversampled)
+    const int NQP = round_up(K, 8), QS = NQP + 4;
+    const int NVP = std::min(96, round_up(G, 8)), VS = NVP + 4;
+
+    double *Y, *gmean, *gsd, *ones, *part, *V, *zs, *pms, *blk, *C, *Q, *Z, *A, *dv, *isg, *P, *S2;
+    CKR(c->dalloc(&Y, size_t(na) * ldG));
+    CUtensorMap tmapY;
+    CK(make_tmap_2d(&tmapY, Y, ldG, na, 16, 128));
+    CKR(c->dalloc(&gmean, size_t(ldG)));
+    CKR(c->dalloc(&gsd, size_t(ldG)));
+    CKR(c->dalloc(&ones, size_t(na)));
+    const int nsplit = 32;
+    CKR(c->dalloc(&part, size_t(nsplit) * ldG));
+    if (ldG == G) {
+        CK(cudaMemcpyAsync(Y, a->X, size_t(n) * G * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        CK(cudaMemcpy2DAsync(Y, size_t(ldG) * 8, a->X, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyHostToDevice, st));
+    }
+    // ---- t(scale(t(X))): centre by the row mean, divide by the row sd (n - 1) ----
+    launch_rowsum(Y, part, n, ldG, nsplit, st);
+    launch_reduce_parts(part, gmean, ldG, nsplit, st);
+    CKR(allreduce(c, gmean, ldG));
+    launch_scale(gmean, ldG, 1.0 / double(n_total), st);
+    launch_fill(gsd, ldG, 1.0, st);
+    launch_center(Y, gmean, gsd, n, ldG, 0, 0, st);
+    launch_fill(ones, size_t(n), 1.0, st);
+    launch_ygemm_simple(Y, ones, part, n, ldG, 1, 1, 1, nsplit, st);
+    launch_reduce_parts(part, gmean, ldG, nsplit, st);                      // gmean <- sum of squares (reused buffer)
+    CKR(allreduce(c, gmean, ldG));
+    launch_sd_from_ss(gmean, gsd, gmean, G, ldG, double(n_total - 1), st);  // gsd <- sd, gmean <- 0
+    launch_center(Y, gmean, gsd, n, ldG, 0, 0, st);
+    // ---- Gram matrix C = Ys Ys' in column blocks through the DMMA mstep_stats kernel ----
+    const int splitK = mstats_pick_splitk(ldG);
+    CKR(c->dalloc(&V, size_t(na) * VS));
+    CKR(c->dalloc(&zs, size_t(na)));
+    CKR(c->dalloc(&pms, size_t(splitK) * ldG * (NVP + 1)));
+    CKR(c->dalloc(&blk, size_t(ldG) * NVP));
+    CKR(c->dalloc(&C, size_t(ldG) * ldG));
+    for (int g0 = 0; g0 < G; g0 += NVP) {
+        const int ncol = std::min(NVP, ldG - g0);
+        launch_extract_cols(Y, V, n, ldG, G, g0, NVP, VS, st);
+        MstatsArgs ma{Y, V, zs, pms, n, ldG, NVP, VS, splitK};
+        launch_mstats(ma, st);
+        launch_reduce_parts(pms, blk, size_t(ldG) * NVP, splitK, st);
+        launch_scatter_block(blk, C, ldG, NVP, g0, ncol, st);
+    }
+    CKR(allreduce(c, C, size_t(ldG) * ldG));
+    // ---- leading K eigenvectors of C (= left singular vectors of Ys), d = sqrt(eigenvalues) ----
+    CKR(c->dalloc(&Q, size_t(ldG) * KP));
+    CKR(c->dalloc(&Z, size_t(ldG) * KP));
+    CKR(c->dalloc(&A, size_t(ldG) * QS));
+    CKR(c->dalloc(&dv, size_t(32)));
+    launch_subspace(C, Q, Z, A, dv, G, ldG, KP, K, QS, 300, a->seed, st);
+    // ---- cellmat = Ys' U = V diag(d)  (estep_project) ----
+    CKR(c->dalloc(&isg, size_t(ldG)));
+    CKR(c->dalloc(&P, size_t(na) * NQP));
+    CKR(c->dalloc(&S2, size_t(na)));
+    {
+        ProjArgs pa{Y, A, isg, P, S2, n, ldG, NQP, QS};
+        launch_proj(pa, tmapY, st);
+    }
+    CK(cudaGetLastError());
+    // ---- k-means: nstart restarts of Lloyd's algorithm advanced together ----
+    KmArgs km{};
+    km.X = P;
+    km.ldx = NQP;
+    km.n = n;
+    km.K = K;
+    km.M0 = M0;
+    km.R = R;
+    km.nsplit = std::max(1, std::min((n + 127) / 128, 64));
+    const int nw = km.nsplit * 4;
+    const size_t nsum = size_t(R) * M0 * (K + 1);
+    double* sums;
+    CKR(c->dalloc(&km.cent, size_t(R) * M0 * K));
+    CKR(c->dalloc(&km.part, size_t(nw) * nsum));
+    CKR(c->dalloc(&km.wss_part, size_t(nw) * R));
+    CKR(c->dalloc(&sums, nsum + R));
+    launch_km_init(km, a->seed, n_total, a->cell_offset, st);
+    CKR(allreduce(c, km.cent, size_t(R) * M0 * K));
+    for (int it = 0; it < a->iter_max; ++it) {
+        launch_km_pass(km, 0, 0, nullptr, st);
+        launch_reduce_parts(km.part, sums, nsum, nw, st);
+        CKR(allreduce(c, sums, nsum));
+        launch_km_update(km, sums, st);
+    }
+    launch_km_pass(km, 1, 0, nullptr, st);
+    launch_reduce_parts(km.wss_part, sums + nsum, size_t(R), nw, st);
+    CKR(allreduce(c, sums + nsum, size_t(R)));
+    std::vector<double> wss(R);
+    CK(cudaMemcpyAsync(wss.data(), sums + nsum, size_t(R) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int best = 0;
+    for (int r = 1; r < R; ++r)
+        if (wss[r] < wss[best]) best = r;
+    int32_t* labels;
+    CKR(c->dalloc(&labels, size_t(na)));
+    launch_km_pass(km, 2, best, labels, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(o->clus, labels, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+    if (o->tot_withinss) *o->tot_withinss = wss[best];
+    if (o->d) CK(cudaMemcpyAsync(o->d, dv, size_t(K) * 8, cudaMemcpyDeviceToHost, st));
+    if (o->cellmat) {
+        double* tmp;
+        CKR(c->dalloc(&tmp, size_t(n) * K, false));
+        launch_cellmat_out(P, tmp, n, K, NQP, st);
+        CK(cudaMemcpyAsync(o->cellmat, tmp, size_t(n) * K * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
 }  // extern "C"

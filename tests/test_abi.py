@@ -48,7 +48,8 @@ def test_struct_layout_against_gcc(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = [("simples_em_args", _lib.EmArgs), ("simples_em_out", _lib.EmOut), ("simples_mi_args", _lib.MiArgs),
              ("simples_mi_out", _lib.MiOut), ("simples_lq_args", _lib.LqArgs), ("simples_lq_out", _lib.LqOut),
-             ("simples_init_args", _lib.InitArgs), ("simples_init_out", _lib.InitOut)]
+             ("simples_init_args", _lib.InitArgs), ("simples_init_out", _lib.InitOut),
+             ("simples_clus_args", _lib.ClusArgs), ("simples_clus_out", _lib.ClusOut)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "simples_b200.h"', 'int main(void) {']
     for cname, cls in pairs:
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

@@ -514,3 +514,38 @@ def test_blocks_dense_in_zeros(sb, keep, pgv):
     mkw = dict(mcmc=3, burnin=1, pg=st["pg"], cutoff=0.1, seed=2)
     r2, g2 = O.do_impute_ref(*args, **mkw), sb.do_impute(*args, **mkw)
     assert rel(g2["impt"], r2["impt"]) <= 1e-6 and abs(g2["loglik"] - r2["loglik"]) <= 1e-8 * abs(r2["loglik"])
+
+
+def _cluster_data(seed, n=420, G=160, M=3, rank=4):
+    rng = np.random.default_rng(seed)
+    Z = np.sort(rng.integers(1, M + 1, n))
+    cen = rng.normal(size=(G, M)) * 1.5
+    B = rng.normal(size=(G, rank)) * np.array([0.6, 0.5, 0.4, 0.3])[:rank]
+    X = cen[:, Z - 1] + B @ rng.normal(size=(rank, n)) + 0.7 * rng.normal(size=(G, n))
+    X[5] = 2.0                                               # a constant gene: sd = 0
+    return X, Z
+
+
+def test_init_cluster_matches_oracle(sb):
+    """Row N4: scale -> truncated SVD -> k-means (R/SIMPLE.R:258-266).  Singular values and the K-dimensional cell
+    embedding agree with LAPACK's SVD; Lloyd's restarts from the same Philox-drawn centres give the same partition."""
+    X, Z = _cluster_data(4)
+    K, M0 = 6, 3
+    got = sb.init_cluster(X, K, M0, seed=11, nstart=12, iter_max=25, details=True)
+    lab, cm, d, wss = O.init_cluster_ref(X, K, M0, nstart=12, iter_max=25, seed=11)
+    assert rel(got["d"], d) <= 1e-8
+    # the embedding is defined up to an orthogonal map of the columns: compare the n x n Gram matrices
+    assert rel(got["cellmat"] @ got["cellmat"].T, cm @ cm.T) <= 1e-6
+    assert O.adjusted_rand_index(got["clus"], lab) >= 0.99 and abs(got["tot_withinss"] - wss) <= 1e-6 * wss
+    assert O.adjusted_rand_index(got["clus"], Z) >= 0.95
+    assert set(np.unique(got["clus"])) <= set(range(1, M0 + 1))
+    one = sb.init_cluster(X, 3, 1, seed=1, nstart=2, iter_max=3)
+    assert np.array_equal(one, np.ones(X.shape[1], dtype=np.int32))
+
+
+def test_simple_driver_with_clustering_start(sb):
+    """SIMPLE(clus = NULL): the whole pipeline including the clustering start recovers the simulated cell types."""
+    sim = O.simulate(n=300, G=260, K=3, MC=3, S0=12, seed=9)
+    res = sb.SIMPLE(sim["Y2"], K0=3, M0=3, iter=3, clus=None, K=5, min_gene=120, mcmc=2, burnin=1, seed=3)
+    assert res["initclus"].shape == (300,) and O.adjusted_rand_index(np.argmax(res["z"], axis=1), sim["Z"]) >= 0.8
+    assert np.isfinite(res["impt"]).all() and np.isfinite(res["BIC"])

@@ -336,3 +336,16 @@ def test_init_impute_oracle_quirks():
     pg1 = np.clip(np.random.default_rng(0).uniform(0.05, 1.2, (Y2.shape[0], 3)), 0.1, 1.0)
     impb = O.init_impute_bulk_ref(Y2, clus, pg1, 0.1, seed=2)
     assert np.isfinite(impb).all() and np.array_equal(impb[Y2 > 0.1], Y2[Y2 > 0.1])
+
+
+def test_init_cluster_oracle_and_ari():
+    rng = np.random.default_rng(4)
+    n, G = 240, 90
+    Z = np.sort(rng.integers(1, 4, n))
+    X = (rng.normal(size=(G, 3)) * 1.5)[:, Z - 1] + 0.7 * rng.normal(size=(G, n))
+    lab, cm, d, wss = O.init_cluster_ref(X, 4, 3, nstart=6, iter_max=20, seed=2)
+    assert O.adjusted_rand_index(lab, Z) >= 0.98 and cm.shape == (n, 4) and np.all(np.diff(d) <= 0)
+    Xs = (X - X.mean(axis=1, keepdims=True)) / X.std(axis=1, ddof=1, keepdims=True)
+    assert abs(np.linalg.norm(cm, axis=0)[0] - np.linalg.svd(Xs, compute_uv=False)[0]) <= 1e-9 * d[0]   # |V d| = d
+    assert O.adjusted_rand_index([1, 1, 2, 2], [2, 2, 1, 1]) == 1.0
+    assert abs(O.adjusted_rand_index([1, 1, 2, 2], [1, 2, 1, 2]) + 0.5) < 1e-12
