@@ -81,3 +81,46 @@ def test_two_rank_allreduce_reproduces_single_rank_mstep():
     for a, b in zip(got[:5], ref[:5]):
         assert np.allclose(a, b, rtol=1e-9, atol=1e-12)
     assert got[5] == 1 and got[6] == 8 * (G * K0 + 2 * G * M0 + G + M0 * K0 * K0 + M0 * K0 + 2 * M0)
+
+
+def _driver_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simples_b200 import CellShard
+    from simples_b200.driver import _hq_genes, _n_total, _sum_over_ranks
+    rng = np.random.default_rng(5)
+    dat = rng.uniform(size=(40, 31)) * (rng.uniform(size=(40, 31)) < rng.uniform(0.1, 0.9, size=(40, 1)))
+    sh = CellShard(31)
+    loc = sh.cols(dat)
+    hq_a = _hq_genes(loc, 0.1, 0.5, 12, False, sh)            # expression rates summed over the ranks
+    hq_b = _hq_genes(loc, 0.1, 0.99, 12, False, sh)           # too few pass -> top-up branch
+    tot = _sum_over_ranks(np.array([loc.shape[1]]), sh)[0]
+    mx = sh.max_host(np.array([float(rank + 1)]))[0]
+    if rank == 0:
+        q.put((hq_a, hq_b, tot, mx, _n_total(loc.shape[1], sh)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_driver_host_logic_sharded():
+    """SIMPLE()'s gene selection on sharded cells (R/SIMPLE.R:246-255) equals the unsharded selection."""
+    import torch.multiprocessing as mp
+    from simples_b200.driver import _hq_genes
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7
+    ps = [ctx.Process(target=_driver_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in ps:
+        p_.start()
+    hq_a, hq_b, tot, mx, nt = q.get(timeout=120)
+    for p_ in ps:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    rng = np.random.default_rng(5)
+    dat = rng.uniform(size=(40, 31)) * (rng.uniform(size=(40, 31)) < rng.uniform(0.1, 0.9, size=(40, 1)))
+    assert np.array_equal(hq_a, _hq_genes(dat, 0.1, 0.5, 12, False, None))
+    assert np.array_equal(hq_b, _hq_genes(dat, 0.1, 0.99, 12, False, None)) and len(hq_b) == 12
+    assert tot == 31 and mx == 2.0 and nt == 31

@@ -35,5 +35,24 @@ if rank == 0:
     e = abs(mi["loglik"] - fmi["loglik"]) / abs(fmi["loglik"]); msgs.append(f"mi.loglik={e:.1e}"); ok &= e <= 1e-9
     e = rel(mi["impt"], fmi["impt"][:, a:b]); msgs.append(f"mi.impt[shard0]={e:.1e}"); ok &= e <= 1e-8
     print(json.dumps({"world": world, "ok": bool(ok), "allreduces_em+mi": sh.n_allreduce, "errs": msgs}), flush=True)
+# ---- run-level driver, cells sharded: init fit, hq EM, lq fit, all-gene EM, MI and the clustering start ----
+import oracle as O
+sim = O.simulate(n=1201, G=400, K=3, MC=3, S0=12, seed=9)
+shd = sb.CellShard(sim["Y2"].shape[1])
+dkw = dict(K0=4, M0=3, iter=3, K=5, min_gene=150, mcmc=2, burnin=1, seed=3)
+for clus in (sim["Z"], None):
+    pr = sb.SIMPLE(shd.cols(sim["Y2"]), clus=None if clus is None else shd.rows(clus), comm=shd, **dkw)
+    if rank == 0:
+        fr = sb.SIMPLE(sim["Y2"], clus=clus, consensus=False, **dkw)
+        a, b = shd.bounds[0], shd.bounds[1]
+        tag = "clus" if clus is not None else "kmeans"
+        for k in ("loglik_tot", "beta", "sigma", "mu", "pi", "lambda"):
+            e = rel(pr[k], fr[k]); msgs.append(f"SIMPLE[{tag}].{k}={e:.1e}"); ok &= e <= 1e-7
+        for k, sl in (("impt", fr["impt"][:, a:b]), ("Yimp0", fr["Yimp0"][:, a:b]), ("z", fr["z"][a:b])):
+            e = rel(pr[k], sl); msgs.append(f"SIMPLE[{tag}].{k}[shard0]={e:.1e}"); ok &= e <= 1e-6
+        ok &= bool(np.array_equal(pr["initclus"], fr["initclus"][a:b]))
+        e = abs(pr["BIC"] - fr["BIC"]) / abs(fr["BIC"]); msgs.append(f"SIMPLE[{tag}].BIC={e:.1e}"); ok &= e <= 1e-9
+if rank == 0:
+    print(json.dumps({"world": world, "ok": bool(ok), "driver": msgs[-20:]}), flush=True)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
