@@ -182,7 +182,14 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-iter", type=int, default=10)
+    ap.add_argument("--K0", type=int, default=None, help="override the number of factors (non-headline runs, e.g. C5)")
+    ap.add_argument("--M0", type=int, default=None, help="override the number of clusters (non-headline runs)")
     args = ap.parse_args()
+    if args.K0 is not None or args.M0 is not None:
+        CFG["K0"] = args.K0 or CFG["K0"]
+        CFG["M0"] = args.M0 or CFG["M0"]
+        CFG["K"], CFG["MC"] = CFG["K0"], CFG["M0"]
+        CFG["override"] = True
     if args.impl == "reference":
         run_reference(args)
         return
@@ -319,7 +326,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C3: synthetic zero-inflated log-counts 100k cells x 2k genes per GPU, K0=M0=10, "
+                "config": {"workload": ("NON-HEADLINE override (--K0/--M0/--cells): " if CFG.get("override") or n != CFG["n"] else "")
+                                       + f"C3: synthetic zero-inflated log-counts {n // 1000}k cells x 2k genes per GPU, K0={K0}, M0={M0}, "
                                        "impt_it=1, num_mc=3 (steady-state EM iteration)",
                            "cells_per_gpu": n, "genes": G, "K0": K0, "M0": M0, "zero_fraction": rho,
                            "l2": "inputs (1.6 GB Y per GPU) exceed L2; no flush needed",

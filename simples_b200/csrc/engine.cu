@@ -202,6 +202,33 @@ int allreduce(simples_ctx* c, double* buf, size_t count) {
     return SIMPLES_OK;
 }
 
+// SIMPLES_TRACE=1: wall-clock phases of the one-shot entry points (each mark synchronises the stream)
+struct Tracer {
+    const char* name;
+    cudaStream_t st;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string msg;
+    Tracer(const char* n, cudaStream_t s) : name(n), st(s), on(getenv("SIMPLES_TRACE") != nullptr) {
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, " %s %.1f ms,", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        msg += buf;
+        t0 = t1;
+    }
+    ~Tracer() {
+        if (on && !msg.empty()) {
+            msg.pop_back();
+            fprintf(stderr, "[simples_b200] %s:%s\n", name, msg.c_str());
+        }
+    }
+};
+
 // host col-major (rows x cols, ld = rows) -> gene-major padded [ldrows][cols]
 std::vector<double> to_rowmajor(const double* src, int rows, int cols, int ldrows, double padval) {
     std::vector<double> out(size_t(ldrows) * cols, padval);
@@ -221,9 +248,9 @@ void set_dims(Dims& d, int G, int n, int M0, int K0, int MB, long long n_total, 
     d.NQ = K0 + M0;
     d.NQP = round_up(d.NQ, 8);
     d.QS = d.NQP + 4;
-    d.NF = K0 + M0 + 1;
-    d.NFP = round_up(d.NF, 8);
-    d.FS = d.NFP + 4;
+    d.NF = K0;
+    d.NFP = round_up(K0, 4);
+    d.FS = round_up(K0, 8) + 4;
     d.NV = K0 + M0 + 1;
     d.NVP = round_up(d.NV, 8);
     d.VS = d.NVP + 4;
@@ -270,6 +297,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.Qs, size_t(ldG) * d.FS));
     CKR(c->dalloc(&s.sdsA, size_t(ldG) * M0));
     CKR(c->dalloc(&s.isdA, size_t(ldG) * M0));
+    CKR(c->dalloc(&s.musdA, size_t(ldG) * M0));
     CKR(c->dalloc(&s.igs, size_t(ldG)));
     s.n_alloc = c->n_alloc;
     CKR(c->dalloc(&s.P, size_t(c->NS_max) * na * d.NQP));
@@ -405,7 +433,7 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
 int run_prep(simples_ctx* c) {
     DevState& s = c->s;
     P p(c, KC_PREP, 2);
-    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.igs, s.cc, 0};
+    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.igs, s.cc, 0};
     if (c->profile) {                      // serial on the main stream so the per-class events mean something
         launch_prep(pa, c->stream, c->stream);
     } else {
@@ -435,6 +463,7 @@ int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2) {
     sa.Fh = s.Fh;
     sa.sdsA = s.sdsA;
     sa.isdA = s.isdA;
+    sa.musdA = s.musdA;
     sa.pg = s.pg;
     sa.gmean = s.gmean;
     sa.igs = s.igs;
@@ -1065,6 +1094,8 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     const Dims& d = s.d;
     const int ldG = d.ldG;
     const size_t na = c->n_alloc;
+    Tracer tr("lq_fit", c->stream);
+    tr.mark("H2D(dat)+mask");
     launch_fill(s.gsd, ldG, 1.0, c->stream);
     CKR(upload_z(c, a->z));
     double* varf = nullptr;
@@ -1088,6 +1119,7 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     s.nsplit_ss = std::max(1, (4 * NUM_SMS_B200) / M0);
     CKR(c->dalloc(&s.part_ss, size_t(s.nsplit_ss) * M0 * (K0 * K0 + K0)));
 
+    tr.mark("H2D(z, Ef)");
     // ---- cell operands + membership draw, then the statistics of the response ----
     {
         LqCellArgs la{d, s.z, s.W, s.Vg, s.Fh, s.im, c->seed, c->sweep, M0 > 1};
@@ -1130,11 +1162,13 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
         launch_lq_solve(qa, c->stream);
     }
     CK(cudaGetLastError());
+    tr.mark("statistics+regression");
     if (a->impute) {                            // R/SIMPLE.R:376-411
-        PrepArgs pa{d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.igs, s.cc, 0};
+        PrepArgs pa{d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.igs, s.cc, 0};
         launch_prep(pa, c->stream, c->stream);
         CKR(run_sweep(c, false, nullptr, nullptr));
     }
+    tr.mark("draw");
     if (o->mu) CKR(fetch_genemajor(c, s.mu, M0, o->mu));
     if (o->beta) CKR(fetch_genemajor(c, s.beta, K0, o->beta));
     if (o->sigma) CKR(fetch_genemajor(c, s.sigma, M0, o->sigma));
@@ -1146,6 +1180,7 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
                                  c->stream));
         }
     }
+    tr.mark("D2H");
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return SIMPLES_OK;
@@ -1195,18 +1230,24 @@ int simples_init_impute(const simples_init_args* a, simples_init_out* o) {
         CKR(c->dalloc(&pg1, GM, false));
         CK(cudaMemcpyAsync(pg1, a->pg1, GM * 8, cudaMemcpyHostToDevice, c->stream));
     }
+    Tracer tr("init_impute", c->stream);
+    tr.mark("H2D");
     launch_init_stats(Y2, clus0, n, G, M0, a->cutoff, part, nsplit, c->stream);
     launch_reduce_parts(part, stats, nst, nsplit, c->stream);
     CKR(allreduce(c, stats, nst + M0));
     InitFitArgs fa{stats, G, M0, a->cutoff, a->p_min, 0.1, 4.0, pg1, fit, fit + GM, fit + 2 * GM, fit + 3 * GM};
+    tr.mark("moments");
     launch_ztrunc(fa, c->stream);
+    tr.mark("fit(Brent)");
     InitDrawArgs da{Y2, Y2, clus0, n, G, fit, fit + GM, fit + 2 * GM, pg1, a->cutoff, a->seed, a->sweep, a->cell_offset};
     launch_init_draw(da, c->stream);
     CK(cudaGetLastError());
+    tr.mark("draw");
     CK(cudaMemcpyAsync(o->impute, Y2, size_t(n) * G * 8, cudaMemcpyDeviceToHost, c->stream));
     if (o->pg) CK(cudaMemcpyAsync(o->pg, fit + 3 * GM, GM * 8, cudaMemcpyDeviceToHost, c->stream));
     if (o->mu) CK(cudaMemcpyAsync(o->mu, fit, GM * 8, cudaMemcpyDeviceToHost, c->stream));
     if (o->sd) CK(cudaMemcpyAsync(o->sd, fit + GM, GM * 8, cudaMemcpyDeviceToHost, c->stream));
+    tr.mark("D2H");
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return SIMPLES_OK;
@@ -1256,6 +1297,8 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     } else {
         CK(cudaMemcpy2DAsync(Y, size_t(ldG) * 8, a->X, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyHostToDevice, st));
     }
+    Tracer tr("init_cluster", st);
+    tr.mark("H2D");
     // ---- t(scale(t(X))): centre by the row mean, divide by the row sd (n - 1) ----
     launch_rowsum(Y, part, n, ldG, nsplit, st);
     launch_reduce_parts(part, gmean, ldG, nsplit, st);
@@ -1269,6 +1312,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     CKR(allreduce(c, gmean, ldG));
     launch_sd_from_ss(gmean, gsd, gmean, G, ldG, double(n_total - 1), st);  // gsd <- sd, gmean <- 0
     launch_center(Y, gmean, gsd, n, ldG, 0, 0, st);
+    tr.mark("scale");
     // ---- Gram matrix C = Ys Ys' in column blocks through the DMMA mstep_stats kernel ----
     const int splitK = mstats_pick_splitk(ldG);
     CKR(c->dalloc(&V, size_t(na) * VS));
@@ -1285,12 +1329,14 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
         launch_scatter_block(blk, C, ldG, NVP, g0, ncol, st);
     }
     CKR(allreduce(c, C, size_t(ldG) * ldG));
+    tr.mark("gram");
     // ---- leading K eigenvectors of C (= left singular vectors of Ys), d = sqrt(eigenvalues) ----
     CKR(c->dalloc(&Q, size_t(ldG) * KP));
     CKR(c->dalloc(&Z, size_t(ldG) * KP));
     CKR(c->dalloc(&A, size_t(ldG) * QS));
     CKR(c->dalloc(&dv, size_t(32)));
     launch_subspace(C, Q, Z, A, dv, G, ldG, KP, K, QS, 300, a->seed, st);
+    tr.mark("subspace");
     // ---- cellmat = Ys' U = V diag(d)  (estep_project) ----
     CKR(c->dalloc(&isg, size_t(ldG)));
     CKR(c->dalloc(&P, size_t(na) * NQP));
@@ -1300,6 +1346,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
         launch_proj(pa, tmapY, st);
     }
     CK(cudaGetLastError());
+    tr.mark("cellmat");
     // ---- k-means: nstart restarts of Lloyd's algorithm advanced together ----
     KmArgs km{};
     km.X = P;
@@ -1333,6 +1380,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     int best = 0;
     for (int r = 1; r < R; ++r)
         if (wss[r] < wss[best]) best = r;
+    tr.mark("kmeans");
     int32_t* labels;
     CKR(c->dalloc(&labels, size_t(na)));
     launch_km_pass(km, 2, best, labels, st);

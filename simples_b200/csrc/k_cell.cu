@@ -294,10 +294,6 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
                     a.Fh[size_t(cell0 + r) * a.d.FS + k] = f;
                 }
             }
-            for (int id = lane; id < 8 * (M0 + 1); id += 32) {
-                const int r = id / (M0 + 1), m = id - r * (M0 + 1);
-                if (cell0 + r < n) a.Fh[size_t(cell0 + r) * a.d.FS + K0 + m] = (m == M0 || m == imw[r]) ? 1.0 : 0.0;
-            }
         }
         __syncwarp();
     }

@@ -180,7 +180,7 @@ inline int gs_grid(size_t total) {
     return int(g);
 }
 
-// lq-gene fit: regression operand Vg = [z_m Ef_m | z | sqrt z] and the sweep operand Fh = [Ef_{m_i}[i,] | onehot | 1]
+// lq-gene fit: regression operand Vg = [z_m Ef_m | z | sqrt z] and the sweep operand Fh = Ef_{m_i}[i,]
 // with m_i drawn from z[i,] (R/SIMPLE.R:376-382; the factor is NOT sampled here, :386).
 __global__ void k_lq_cell(LqCellArgs a) {
     const Dims& d = a.d;
@@ -211,10 +211,8 @@ __global__ void k_lq_cell(LqCellArgs a) {
         }
         vg[K0 * M0 + m] = zm;
         vg[K0 * M0 + M0 + m] = sqrt(zm);
-        fh[K0 + m] = (m == im) ? 1.0 : 0.0;
     }
-    fh[K0 + M0] = 1.0;
-    for (int c = K0 + M0 + 1; c < d.FS; ++c) fh[c] = 0.0;
+    for (int c = K0; c < d.FS; ++c) fh[c] = 0.0;
 }
 
 // out[m] = sum_i z[i][m] in a fixed order (one CTA), out[M0 .. 2 M0] = 0

@@ -27,13 +27,12 @@ __global__ void k_build_ops(PrepArgs a) {
         const double sdv = sqrt(a.sigma[size_t(g) * M0 + m]) * sd;
         a.sdsA[size_t(g) * M0 + m] = sdv;
         a.isdA[size_t(g) * M0 + m] = 1.0 / sdv;
+        a.musdA[size_t(g) * M0 + m] = a.mu[size_t(g) * M0 + m] * sd;
     }
     a.igs[g] = 1.0 / sd;
     double* qs = a.Qs + size_t(g) * d.FS;
     for (int k = 0; k < K0; ++k) qs[k] = a.beta[size_t(g) * K0 + k] * sd;
-    for (int m = 0; m < M0; ++m) qs[K0 + m] = a.mu[size_t(g) * M0 + m] * sd;
-    qs[K0 + M0] = (g < d.G) ? mean : 0.0;
-    for (int c = K0 + M0 + 1; c < d.FS; ++c) qs[c] = 0.0;
+    for (int c = K0; c < d.FS; ++c) qs[c] = 0.0;
 }
 
 constexpr int GT = 256;  // genes per smem tile

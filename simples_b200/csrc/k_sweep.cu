@@ -2,8 +2,8 @@
 // (R/EM_impute.R:168-199, R/do_impute.R:109-136).
 //
 // A warp owns 8 cells and walks the genes in 32-gene chunks (= one mask word per cell):
-//   1. ms(8 cells x 32 genes) = Fh * Qs^T by FP64 DMMA  (Fh_i = [f_i | onehot(m_i) | 1],
-//      Qs_g = [B_g sd_g | mu_g. sd_g | mean_g]) -> per-warp shared-memory tile; no per-cell gathers.
+//   1. ms(8 cells x 32 genes) = Fh * Qs^T by FP64 DMMA (Fh_i = f_i, Qs_g = B_g sd_g; depth K0, A-fragments in
+//      registers) + mu_g,m(i) sd_g + mean_g gathered from the chunk parameters -> per-warp shared-memory tile;
 //   2. the set bits of the 8 mask words are compacted (ballot + popc) into a dense work list, so
 //      the expensive per-entry sampler runs with full lanes instead of ~44 % (the zero fraction);
 //   3. each list entry draws from the Philox tape and writes the centred value to Y.
@@ -30,7 +30,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct ChunkBuf {
-    double *Q, *sds, *isd, *pg, *gm, *igs;
+    double *Q, *sds, *isd, *musd, *pg, *gm, *igs;
 };
 
 __device__ __forceinline__ ChunkBuf chunk_buf(double* base, int FS, int M0, int MB) {
@@ -38,27 +38,13 @@ __device__ __forceinline__ ChunkBuf chunk_buf(double* base, int FS, int M0, int 
     b.Q = base;
     b.sds = b.Q + SG * FS;
     b.isd = b.sds + SG * M0;
-    b.pg = b.isd + SG * M0;
+    b.musd = b.isd + SG * M0;
+    b.pg = b.musd + SG * M0;
     b.gm = b.pg + SG * MB;
     b.igs = b.gm + SG;
     return b;
 }
-__host__ __device__ inline int chunk_doubles(int FS, int M0, int MB) { return SG * FS + 2 * SG * M0 + SG * MB + 2 * SG; }
-
-__device__ __forceinline__ void copy_span(double* dst, const double* src, int ndbl, int tid, int nthr) {
-    for (int i = tid * 2; i < ndbl; i += nthr * 2) cp_async16(dst + i, src + i);   // ndbl is even, 16-B aligned spans
-}
-
-__device__ __forceinline__ void load_chunk(const SweepArgs& a, const ChunkBuf& b, int chunk, int tid, int nthr) {
-    const int g0 = chunk * SG, FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB;
-    copy_span(b.Q, a.Qs + size_t(g0) * FS, SG * FS, tid, nthr);
-    copy_span(b.sds, a.sdsA + size_t(g0) * M0, SG * M0, tid, nthr);
-    copy_span(b.isd, a.isdA + size_t(g0) * M0, SG * M0, tid, nthr);
-    copy_span(b.pg, a.pg + size_t(g0) * MB, SG * MB, tid, nthr);
-    copy_span(b.gm, a.gmean + g0, SG, tid, nthr);
-    copy_span(b.igs, a.igs + g0, SG, tid, nthr);
-    cp_async_commit();
-}
+__host__ __device__ inline int chunk_doubles(int FS, int M0, int MB) { return SG * FS + 3 * SG * M0 + SG * MB + 2 * SG; }
 
 // one thread: TMA bulk copies of the six parameter spans of gene chunk `chunk`, completing on `bar`
 __device__ __forceinline__ void load_chunk_bulk(const SweepArgs& a, const ChunkBuf& b, int chunk, uint64_t* bar) {
@@ -67,13 +53,15 @@ __device__ __forceinline__ void load_chunk_bulk(const SweepArgs& a, const ChunkB
     bulk_g2s(b.Q, a.Qs + size_t(g0) * FS, SG * FS * 8, bar);
     bulk_g2s(b.sds, a.sdsA + size_t(g0) * M0, SG * M0 * 8, bar);
     bulk_g2s(b.isd, a.isdA + size_t(g0) * M0, SG * M0 * 8, bar);
+    bulk_g2s(b.musd, a.musdA + size_t(g0) * M0, SG * M0 * 8, bar);
     bulk_g2s(b.pg, a.pg + size_t(g0) * MB, SG * MB * 8, bar);
     bulk_g2s(b.gm, a.gmean + g0, SG * 8, bar);
     bulk_g2s(b.igs, a.igs + g0, SG * 8, bar);
 }
 
-template <bool FREG>
-__global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
+// NKS = number of K-steps of 4 held as register A-fragments (K0 <= 4 NKS); MINB = resident CTAs per SM aimed at
+template <int NKS, int MINB>
+__global__ void __launch_bounds__(SW * 32, MINB) k_sweep(SweepArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB, ldG = a.d.ldG, n = a.d.n;
     const int KST = a.d.NFP / 4;
@@ -85,20 +73,14 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smb);                            // full[2], empty[2]
     unsigned char* wblk = smb + 64 + (threadIdx.x >> 5) * WBLK;
     double* sBuf = reinterpret_cast<double*>(smb + 64 + SW * WBLK);               // [2][CD] parameter chunks
-    double* sF = sBuf + 2 * CD;                                                    // [SC][FS] (only when !FREG)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cell0 = blockIdx.x * SC;
     const int wc0 = cell0 + warp * 8;           // first cell of this warp
-    double fr[6];                                     // FREG: A-fragments Fh[cell g][4 ks + t], NFP <= 24
-    if (FREG) {
+    double fr[NKS];                             // A-fragments f[cell g][4 ks + t] of the warp's 8 cells
+    {
         const int cell = wc0 + g;
 #pragma unroll
-        for (int ks = 0; ks < 6; ++ks) fr[ks] = (ks < KST && cell < n) ? a.Fh[size_t(cell) * FS + ks * 4 + t] : 0.0;
-    } else {
-        for (int idx = tid; idx < SC * FS; idx += blockDim.x) {
-            const int r = idx / FS, c = idx - r * FS;
-            sF[idx] = (cell0 + r < n) ? a.Fh[size_t(cell0 + r) * FS + c] : 0.0;
-        }
+        for (int ks = 0; ks < NKS; ++ks) fr[ks] = (ks < KST && cell < n) ? a.Fh[size_t(cell) * FS + ks * 4 + t] : 0.0;
     }
     if (lane < 8) {
         const int cell = wc0 + lane;
@@ -130,7 +112,6 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
     unsigned char* dcode = list + 256;                                 // [256] Dc (front) / back list codes
     unsigned char* xcode = list + 512;                                 // [256] uncertain entries
     int* cellinfo = reinterpret_cast<int*>(list + 768);                // [8][2] (im, celltype)
-    const double* fa = sF + (warp * 8 + g) * FS + t;
 
     for (int ci = 0; ci < nchunks; ++ci) {
         const int chunk = cbeg + ci;                   // absolute gene-chunk index
@@ -155,19 +136,20 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
         double acc[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-        if (FREG) {
 #pragma unroll
-            for (int ks = 0; ks < 6; ++ks) {
-                if (ks < KST) {
+        for (int ks = 0; ks < NKS; ++ks) {
+            if (ks < KST) {
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], fr[ks], b.Q[(nt * 8 + g) * FS + ks * 4 + t]);
-                }
+                for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], fr[ks], b.Q[(nt * 8 + g) * FS + ks * 4 + t]);
             }
-        } else {
-            for (int ks = 0; ks < KST; ++ks) {
-                const double av = fa[ks * 4];
+        }
+        {   // + mu_{g, m(i)} sd_g + mean_g for the lane's cell g and its genes nt*8 + 2t, +1
+            const int img = cellinfo[g * 2];
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], av, b.Q[(nt * 8 + g) * FS + ks * 4 + t]);
+            for (int nt = 0; nt < 4; ++nt) {
+                const int g0 = nt * 8 + 2 * t;
+                acc[nt][0] += b.musd[g0 * M0 + img] + b.gm[g0];
+                acc[nt][1] += b.musd[(g0 + 1) * M0 + img] + b.gm[g0 + 1];
             }
         }
 #pragma unroll
@@ -361,16 +343,25 @@ __global__ void __launch_bounds__(SW * 32, 3) k_sweep(SweepArgs a) {
 
 }  // namespace
 
+template <int NKS, int MINB>
+static void launch_variant(const SweepArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(k_sweep<NKS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr = smem;
+    }
+    k_sweep<NKS, MINB><<<grid, SW * 32, smem, st>>>(a);
+}
+
 void launch_sweep(const SweepArgs& a, cudaStream_t st) {
-    const bool freg = a.d.NFP <= 24;
-    const size_t smem = sizeof(double) * ((freg ? 0 : size_t(SC) * a.d.FS) + size_t(SW) * 8 * MSS +
-                                          2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
+    const size_t smem = sizeof(double) * (size_t(SW) * 8 * MSS + 2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
                         SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int) + 64;
     const int tiles = (a.d.n + SC - 1) / SC;
-    // pick the gene split (1..4) that minimises wave quantisation for ~3 resident CTAs per SM
+    const int resident = smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1);
+    // pick the gene split (1..4) that minimises wave quantisation for the resident CTAs per SM
     int gsplit = 1;
     {
-        const double slots = 3.0 * NUM_SMS_B200;
+        const double slots = double(resident) * NUM_SMS_B200;
         double best = 1e30;
         for (int gsp = 1; gsp <= 4; ++gsp) {
             if ((a.d.ldG / SG) / gsp < 8) break;
@@ -380,20 +371,11 @@ void launch_sweep(const SweepArgs& a, cudaStream_t st) {
         }
     }
     const dim3 grid(tiles, gsplit);
-    static size_t attr[2] = {0, 0};
-    if (freg) {
-        if (smem > 48 * 1024 && smem > attr[0]) {
-            cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr[0] = smem;
-        }
-        k_sweep<true><<<grid, SW * 32, smem, st>>>(a);
-    } else {
-        if (smem > 48 * 1024 && smem > attr[1]) {
-            cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr[1] = smem;
-        }
-        k_sweep<false><<<grid, SW * 32, smem, st>>>(a);
-    }
+    const int kst = a.d.NFP / 4;
+    if (kst <= 3) launch_variant<3, 3>(a, grid, smem, st);
+    else if (kst <= 6 && resident == 3) launch_variant<6, 3>(a, grid, smem, st);
+    else if (kst <= 6) launch_variant<6, 2>(a, grid, smem, st);
+    else launch_variant<8, 2>(a, grid, smem, st);
 }
 
 }  // namespace sb

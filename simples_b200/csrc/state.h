@@ -6,11 +6,11 @@
 //   lam    [M0][K0]   pi [M0]   z [n][M0]
 //   Q      [NS][ldG][QS]   projection operand  [B/sigma_s | mu_m/sigma_cs(m) | 0-pad]
 //   isg    [NS][ldG]       1/sigma_s
-//   Qs     [ldG][FS]       sweep operand       [B*sd | mu*sd | mean | 0-pad]
-//   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  igs [ldG] = 1/sd
+//   Qs     [ldG][FS]       sweep operand       [B*sd | 0-pad]
+//   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  musdA = mu*sd,  igs [ldG] = 1/sd
 //   P      [NS][n][NQP]    Y^T Q          S2 [NS][n]   sum_g Y^2/sigma_s
 //   V      [n][VS]         M-step operand [Wbar (K0) | z (M0) | sum_m sqrt z_m (1) | 0-pad],  zsum [n]
-//   Fh     [n][FS]         sweep operand  [f_i (K0) | onehot(m_i) (M0) | 1 | 0-pad]
+//   Fh     [n][FS]         sweep operand  [f_i (K0) | 0-pad]   (the membership m_i is in im[n])
 //   W      [M0][n][K0]     factor posterior means (Ef)
 // ldG = G rounded up to 64; padded genes have Y = 0, mask = 0, beta = mu = 0, sigma = 1.
 #pragma once
@@ -44,7 +44,7 @@ struct Dims {
     int G, ldG, n, M0, K0, MB;
     int NS;            // distinct sigma columns in use: 1 (cluster-shared) or M0
     int NQ, NQP, QS;   // projection cols: NQ = K0 + M0 (per sigma column), padded to 8; row stride QS = NQP + 4
-    int NF, NFP, FS;   // sweep GEMM depth: NF = K0 + M0 + 1 padded to 4 (NFP); row stride FS = NFP + 4 (== 4 mod 8)
+    int NF, NFP, FS;   // sweep GEMM depth: NF = K0 padded to 4 (NFP); row stride FS = roundup(K0, 8) + 4 (== 4 mod 8)
     int NV, NVP, VS;   // M-step cols: NV = K0 + M0 + 1, padded to 8; row stride VS = NVP + 4
     long long n_total, cell_offset;
 };
@@ -65,7 +65,7 @@ struct DevState {
     double *Y, *beta, *sigma, *mu, *pg, *gmean, *gsd, *lam, *pi, *z;
     uint32_t* mask;
     int32_t* celltype0;
-    double *Q, *isg, *Qs, *sdsA, *isdA, *igs, *P, *S2, *V, *zsum, *Fh, *W;
+    double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs, *P, *S2, *V, *zsum, *Fh, *W;
     int n_alloc;
     int32_t* im;
     ClusterConsts cc;
@@ -112,7 +112,7 @@ void launch_cell(const CellArgs& a, cudaStream_t st);
 
 struct SweepArgs {
     Dims d;
-    double* Y; const uint32_t* mask; const double *Qs, *Fh, *sdsA, *isdA, *pg, *gmean, *igs;
+    double* Y; const uint32_t* mask; const double *Qs, *Fh, *sdsA, *isdA, *musdA, *pg, *gmean, *igs;
     int n_alloc;
     const int32_t *im, *celltype0;
     double cutoff, lower, upper;
@@ -147,7 +147,7 @@ void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out
 
 struct PrepArgs {
     Dims d; const double *beta, *sigma, *mu, *lam, *pi, *gmean, *gsd;
-    double *Q, *isg, *Qs, *sdsA, *isdA, *igs; ClusterConsts cc; int stale_q;
+    double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs; ClusterConsts cc; int stale_q;
 };
 void launch_prep(const PrepArgs& a, cudaStream_t st, cudaStream_t st_cluster);
 
