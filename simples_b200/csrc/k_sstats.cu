@@ -8,43 +8,70 @@
 namespace sb {
 namespace {
 
-constexpr int CH = 256;  // cells per smem chunk
+constexpr int SSW = 4;    // warps per CTA, each with its own cell range and partial slot
+constexpr int SCH = 32;   // cells per staged chunk
 
-__global__ void __launch_bounds__(256) k_sstats(SstatsArgs a, int cps) {
-    extern __shared__ __align__(16) double sm[];
+// One warp owns a contiguous cell range of cluster m and accumulates S_m = (z W)^T W as KT x KT DMMA tiles
+// (m8n8k4: A = (z W)^T, B = W; both fragments are the same shared-memory load, A scaled by z) plus a_m = sum z W.
+template <int KT>
+__global__ void __launch_bounds__(SSW * 32) k_sstats(SstatsArgs a, int cells_per_warp) {
+    constexpr int KS = KT * 8 + 4;                 // row stride == 4 (mod 8): conflict-free fragment loads
+    __shared__ __align__(16) double sWall[SSW][SCH * KS];
+    __shared__ double sZall[SSW][SCH];
     const int K0 = a.d.K0, M0 = a.d.M0, n = a.d.n;
-    double* sW = sm;               // [CH][K0]
-    double* sZ = sW + CH * K0;     // [CH]
-    const int m = blockIdx.x, sp = blockIdx.y;
-    const int cbeg = sp * cps, cend = min(n, cbeg + cps);
-    const int NE = K0 * K0 + K0;
-    double acc[5] = {0, 0, 0, 0, 0};   // NE <= 1056 <= 5 * 256
-    for (int i0 = cbeg; i0 < cend; i0 += CH) {
-        const int lim = min(CH, cend - i0);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < lim * K0; idx += blockDim.x) sW[idx] = a.W[(size_t(m) * n + i0) * K0 + idx];
-        for (int idx = threadIdx.x; idx < lim; idx += blockDim.x) sZ[idx] = a.z[size_t(i0 + idx) * M0 + m];
-        __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int m = blockIdx.x, slot = blockIdx.y * SSW + warp;
+    if (slot >= a.nsplit) return;
+    double* sW = sWall[warp];
+    double* sZ = sZall[warp];
+    const int cbeg = slot * cells_per_warp, cend = min(n, cbeg + cells_per_warp);
+    double acc[KT][KT][2], sa[KT];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const int e = threadIdx.x + q * 256;
-            if (e < NE) {
-                double s = acc[q];
-                if (e < K0 * K0) {
-                    const int j = e / K0, k = e - j * K0;
-                    for (int r = 0; r < lim; ++r) s = fma(sZ[r] * sW[r * K0 + j], sW[r * K0 + k], s);
-                } else {
-                    const int k = e - K0 * K0;
-                    for (int r = 0; r < lim; ++r) s = fma(sZ[r], sW[r * K0 + k], s);
-                }
-                acc[q] = s;
+    for (int i = 0; i < KT; ++i) {
+        sa[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    for (int i0 = cbeg; i0 < cend; i0 += SCH) {
+        const int lim = min(SCH, cend - i0);
+        __syncwarp();
+        for (int idx = lane; idx < SCH * KT * 8; idx += 32) {
+            const int r = idx / (KT * 8), k = idx - r * (KT * 8);
+            sW[r * KS + k] = (r < lim && k < K0) ? a.W[(size_t(m) * n + i0 + r) * K0 + k] : 0.0;
+        }
+        sZ[lane] = lane < lim ? a.z[size_t(i0 + lane) * M0 + m] : 0.0;
+        __syncwarp();
+#pragma unroll 2
+        for (int c = 0; c < SCH; c += 4) {
+            const double zc = sZ[c + t];
+            double w[KT], zw[KT];
+#pragma unroll
+            for (int i = 0; i < KT; ++i) {
+                w[i] = sW[(c + t) * KS + i * 8 + g];
+                zw[i] = zc * w[i];
+                sa[i] += zw[i];
             }
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+#pragma unroll
+                for (int j = 0; j < KT; ++j) dmma(acc[i][j][0], acc[i][j][1], zw[i], w[j]);
         }
     }
+    const int NE = K0 * K0 + K0;
+    double* out = a.part + (size_t(slot) * M0 + m) * NE;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int e = threadIdx.x + q * 256;
-        if (e < NE) a.part[(size_t(sp) * M0 + m) * NE + e] = acc[q];
+    for (int i = 0; i < KT; ++i) {
+        const int row = i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            const int col = j * 8 + 2 * t;
+            if (row < K0 && col < K0) out[row * K0 + col] = acc[i][j][0];
+            if (row < K0 && col + 1 < K0) out[row * K0 + col + 1] = acc[i][j][1];
+        }
+        double s = sa[i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (t == 0 && row < K0) out[K0 * K0 + row] = s;
     }
 }
 
@@ -80,16 +107,20 @@ __global__ void k_finalize_stats(FinalizeArgs a, size_t count) {
 
 }  // namespace
 
+template <int KT>
+static void launch_sstats_kt(const SstatsArgs& a, cudaStream_t st) {
+    const int cpw = ((a.d.n + a.nsplit - 1) / a.nsplit + SCH - 1) / SCH * SCH;
+    dim3 grid(a.d.M0, (a.nsplit + SSW - 1) / SSW);
+    k_sstats<KT><<<grid, SSW * 32, 0, st>>>(a, cpw);
+}
+
 void launch_sstats(const SstatsArgs& a, cudaStream_t st) {
-    const int cps = ((a.d.n + a.nsplit - 1) / a.nsplit + CH - 1) / CH * CH;
-    const size_t smem = sizeof(double) * (size_t(CH) * a.d.K0 + CH);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_sstats, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
+    switch ((a.d.K0 + 7) / 8) {
+        case 1: launch_sstats_kt<1>(a, st); break;
+        case 2: launch_sstats_kt<2>(a, st); break;
+        case 3: launch_sstats_kt<3>(a, st); break;
+        default: launch_sstats_kt<4>(a, st); break;
     }
-    dim3 grid(a.d.M0, a.nsplit);
-    k_sstats<<<grid, 256, smem, st>>>(a, cps);
 }
 
 void launch_finalize_stats(const FinalizeArgs& a, cudaStream_t st) {
