@@ -20,8 +20,35 @@ from . import _lib
 from ._lib import COMPAT_DEFAULT, EmArgs, EmOut, MiArgs, MiOut, SimplesError, check  # noqa: F401
 
 
+def _is_dev(a):
+    """A torch CUDA tensor: the big matrices (Y, Y0, dat, X ... and their outputs) may live in HBM already; the
+    library copies with cudaMemcpyDefault, so a device pointer is as good as a host pointer."""
+    return bool(getattr(a, "is_cuda", False))
+
+
+def dev_matrix(a):
+    """Host matrix (R orientation, rows x cols) -> column-major float64 matrix on the current CUDA device."""
+    import torch
+    a = np.asarray(a, dtype=np.float64)
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().T
+
+
+def dev_empty(rows, cols):
+    """Uninitialised column-major float64 rows x cols matrix on the current CUDA device (for ``out=`` buffers)."""
+    import torch
+    return torch.empty((cols, rows), dtype=torch.float64, device="cuda").T
+
+
 def _f(a, shape=None, name=""):
-    """float64, column-major (R layout) view/copy."""
+    """float64, column-major (R layout) view/copy; device matrices pass through after a layout check."""
+    if _is_dev(a):
+        import torch
+        if a.dtype != torch.float64 or a.dim() != 2 or not a.T.is_contiguous():
+            raise ValueError(f"{name}: a device matrix must be float64 and column-major (see simples_b200.dev_matrix)")
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+        torch.cuda.current_stream().synchronize()       # producers on torch's stream are done before the library reads
+        return a
     a = np.asarray(a, dtype=np.float64)
     if shape is not None and tuple(a.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
@@ -29,7 +56,22 @@ def _f(a, shape=None, name=""):
 
 
 def _ptr(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    if a is None:
+        return None
+    if _is_dev(a):
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check_out(b, shape, order, name):
+    if _is_dev(b):
+        import torch
+        ok = b.dtype == torch.float64 and tuple(b.shape) == tuple(shape) and (b.T.is_contiguous() if order == "F" else b.is_contiguous())
+    else:
+        ok = b.dtype == np.float64 and tuple(b.shape) == tuple(shape) and (b.flags.f_contiguous if order == "F" else b.flags.c_contiguous)
+    if not ok:
+        raise ValueError(f"out[{name!r}] must be float64 {tuple(shape)} in {order} order")
+    return b
 
 
 class _Comm:
@@ -108,9 +150,7 @@ def _em_out(G, n, M0, K0, iter, out=None):
         if b is None:
             b = np.empty(shape, order=order)
         else:
-            ok = b.dtype == np.float64 and tuple(b.shape) == tuple(shape) and (b.flags.f_contiguous if order == "F" else b.flags.c_contiguous)
-            if not ok:
-                raise ValueError(f"out[{k!r}] must be float64 {shape} in {order} order")
+            _check_out(b, shape, order, k)
         bufs[k] = b
     o = EmOut()
     for k, v in bufs.items():
@@ -200,8 +240,8 @@ class EMContext:
     def kernel_launches(self):
         return int(self._lib.simples_em_kernel_launches(self._h))
 
-    def fetch(self, big=True):
-        o, bufs = _em_out(self.G, self.n, self.M0, self.K0, self.iters_done)
+    def fetch(self, big=True, out=None):
+        o, bufs = _em_out(self.G, self.n, self.M0, self.K0, self.iters_done, out)
         if not big:
             o.Y = None
             o.Ef = None
@@ -278,8 +318,7 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
                 EF=np.zeros((n, K0), order="F"), varF=np.zeros((n, K0), order="F"),
                 consensus_cluster=np.zeros((n, n), order="F") if want_cons else None)
     for k in ("impt", "impt_var"):
-        if bufs[k].shape != (G, n) or not bufs[k].flags.f_contiguous or bufs[k].dtype != np.float64:
-            raise ValueError(f"out[{k!r}] must be a float64 F-ordered {G} x {n} array")
+        _check_out(bufs[k], (G, n), "F", k)
     o = MiOut()
     for k, v in bufs.items():
         setattr(o, k, _ptr(v))
@@ -292,7 +331,7 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
 
 
 def lq_fit(dat, sigma, pg, z, Ef, Varf, celltype=None, penl=1, cutoff=0.1, *, resp=None, resid_mode=0, impute=True,
-           seed=0, sweep=0, comm=None, stream=None):
+           seed=0, sweep=0, comm=None, stream=None, out_Y=None):
     """The low-quality-gene step between the two ``EM_impute`` calls of ``SIMPLE()`` / ``SIMPLE_B()``
     (R/SIMPLE.R:305-411, R/SIMPLE_B.R:332-419) on B200: per gene M0 unpenalised intercepts + K0 lasso loadings,
     the shared variance, and one imputation draw of the entries <= cutoff with the factor at its posterior mean.
@@ -324,7 +363,7 @@ def lq_fit(dat, sigma, pg, z, Ef, Varf, celltype=None, penl=1, cutoff=0.1, *, re
         a.n_total, a.cell_offset, a.allreduce = int(comm.n_total), int(comm.cell_offset), cw.cb
     a.stream = stream
     bufs = dict(mu=np.zeros((Gq, M0), order="F"), beta=np.zeros((Gq, K0), order="F"), sigma=np.zeros((Gq, M0), order="F"),
-                Y=np.empty((Gq, n), order="F") if impute else None)
+                Y=(np.empty((Gq, n), order="F") if out_Y is None else _check_out(out_Y, (Gq, n), "F", "Y")) if impute else None)
     o = _lib.LqOut()
     for k, v in bufs.items():
         setattr(o, k, _ptr(v))
@@ -335,7 +374,7 @@ def lq_fit(dat, sigma, pg, z, Ef, Varf, celltype=None, penl=1, cutoff=0.1, *, re
     return bufs
 
 
-def _init_call(Y2, M0, clus, pg1, p_min, cutoff, seed, sweep, comm, stream, details):
+def _init_call(Y2, M0, clus, pg1, p_min, cutoff, seed, sweep, comm, stream, details, out=None):
     lib = _lib.load()
     Y2 = _f(Y2)
     G, n = Y2.shape
@@ -354,7 +393,8 @@ def _init_call(Y2, M0, clus, pg1, p_min, cutoff, seed, sweep, comm, stream, deta
         cw = _Comm(comm)
         a.n_total, a.cell_offset, a.allreduce = int(comm.n_total), int(comm.cell_offset), cw.cb
     a.stream = stream
-    bufs = dict(impute=np.empty((G, n), order="F"), pg=np.empty((G, M0), order="F"),
+    bufs = dict(impute=np.empty((G, n), order="F") if out is None else _check_out(out, (G, n), "F", "impute"),
+                pg=np.empty((G, M0), order="F"),
                 mu=np.empty((G, M0), order="F") if details else None, sd=np.empty((G, M0), order="F") if details else None)
     o = _lib.InitOut()
     for k, v in bufs.items():
@@ -367,20 +407,20 @@ def _init_call(Y2, M0, clus, pg1, p_min, cutoff, seed, sweep, comm, stream, deta
 
 
 def init_impute(Y2, M0, clus, p_min=0.6, cutoff=0.1, verbose=False, *, seed=0, sweep=0, comm=None, stream=None,
-                details=False):
+                details=False, out=None):
     """``init_impute`` (R/SIMPLE.R:15-73) on B200: per cluster and gene the zero-inflated censored-normal fit of
     ``ztruncnorm`` (R/fit_ztrunc.R:55-134), then one draw of every entry <= cutoff.  Returns ``[impute, pg]`` like the
     reference (``details=True`` appends the fitted per-cluster mean and sd)."""
-    b = _init_call(Y2, M0, clus, None, p_min, cutoff, seed, sweep, comm, stream, details)
+    b = _init_call(Y2, M0, clus, None, p_min, cutoff, seed, sweep, comm, stream, details, out)
     return [b["impute"], b["pg"]] + ([b["mu"], b["sd"]] if details else [])
 
 
 def init_impute_bulk(Y2, clus, bulk, pg1, cutoff=0.1, verbose=False, *, seed=0, sweep=0, comm=None, stream=None,
-                     details=False):
+                     details=False, out=None):
     """``init_impute_bulk`` (R/SIMPLE_B.R:23-114) on B200; ``bulk`` only feeds the reference's verbose plots and is
     ignored.  Returns the imputed matrix (``details=True``: ``[impute0, pg, mu, sd]``)."""
     M0 = int(np.max(clus))
-    b = _init_call(Y2, M0, clus, pg1, 0.01, cutoff, seed, sweep, comm, stream, details)
+    b = _init_call(Y2, M0, clus, pg1, 0.01, cutoff, seed, sweep, comm, stream, details, out)
     return [b["impute"], b["pg"], b["mu"], b["sd"]] if details else b["impute"]
 
 

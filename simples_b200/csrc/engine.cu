@@ -329,13 +329,13 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
 
     // ---- uploads ----
     if (ldG == G) {
-        CK(cudaMemcpyAsync(s.Y, Y, size_t(n) * G * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.Y, Y, size_t(n) * G * 8, cudaMemcpyDefault, c->stream));
     } else {
-        CK(cudaMemcpy2DAsync(s.Y, size_t(ldG) * 8, Y, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpy2DAsync(s.Y, size_t(ldG) * 8, Y, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyDefault, c->stream));
     }
     for (size_t c0 = 0; c0 < size_t(n); c0 += cells_per_chunk) {
         const size_t nc = std::min(cells_per_chunk, size_t(n) - c0);
-        CK(cudaMemcpyAsync(c->stage, Y0 + c0 * G, nc * G * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->stage, Y0 + c0 * G, nc * G * 8, cudaMemcpyDefault, c->stream));
         launch_build_mask(c->stage, s.mask, int(nc), int(c0), c->n_alloc, G, ldG, cutoff, c->d_nnz, c->stream);
     }
     {
@@ -350,16 +350,16 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
                 ct[i] = celltype[i] - 1;
             }
         }
-        CK(cudaMemcpyAsync(s.beta, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.sigma, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.pg, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.lam, hl.data(), hl.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.pi, pi, size_t(M0) * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.celltype0, ct.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.beta, hb.data(), hb.size() * 8, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(s.sigma, hs.data(), hs.size() * 8, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(s.pg, hp.data(), hp.size() * 8, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(s.lam, hl.data(), hl.size() * 8, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(s.pi, pi, size_t(M0) * 8, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(s.celltype0, ct.data(), size_t(n) * 4, cudaMemcpyDefault, c->stream));
         CK(cudaStreamSynchronize(c->stream));   // host vectors go out of scope
     }
     unsigned long long h_nnz = 0;
-    CK(cudaMemcpy(&h_nnz, c->d_nnz, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&h_nnz, c->d_nnz, 8, cudaMemcpyDefault));
     c->nnz0 = (long long)h_nnz;
     return SIMPLES_OK;
 }
@@ -377,7 +377,7 @@ int upload_z(simples_ctx* c, const double* z) {
     const int n = s.d.n, M0 = s.d.M0;
     double* tmp = nullptr;
     CK(cudaMallocAsync(&tmp, size_t(n) * M0 * 8, c->stream));
-    CK(cudaMemcpyAsync(tmp, z, size_t(n) * M0 * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(tmp, z, size_t(n) * M0 * 8, cudaMemcpyDefault, c->stream));
     launch_transpose(tmp, s.z, M0, n, n, M0, c->stream);
     CK(cudaFreeAsync(tmp, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -621,7 +621,7 @@ int fetch_big(simples_ctx* c, double* host_out, F fill) {
         fill(buf, c0, nc);
         CK(cudaEventRecord(filled[h], c->stream));
         CK(cudaStreamWaitEvent(cs, filled[h], 0));
-        CK(cudaMemcpyAsync(host_out + c0 * d.G, buf, nc * d.G * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(host_out + c0 * d.G, buf, nc * d.G * 8, cudaMemcpyDefault, cs));
         CK(cudaEventRecord(copied[h], cs));
     }
     CK(cudaStreamSynchronize(cs));
@@ -638,7 +638,7 @@ int fetch_big(simples_ctx* c, double* host_out, F fill) {
 int fetch_genemajor(simples_ctx* c, const double* dev, int cols, double* host) {
     const Dims& d = c->s.d;
     std::vector<double> tmp(size_t(d.ldG) * cols);
-    CK(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * 8, cudaMemcpyDefault, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int cidx = 0; cidx < cols; ++cidx)
         for (int g = 0; g < d.G; ++g) host[size_t(cidx) * d.G + g] = tmp[size_t(g) * cols + cidx];
@@ -650,7 +650,7 @@ int fetch_transposed(simples_ctx* c, const double* dev, int rows, int cols, int 
     double* tmp = nullptr;
     CK(cudaMallocAsync(&tmp, size_t(rows) * cols * 8, c->stream));
     launch_transpose(dev, tmp, rows, cols, ld, rows, c->stream);
-    CK(cudaMemcpyAsync(host, tmp, size_t(rows) * cols * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(host, tmp, size_t(rows) * cols * 8, cudaMemcpyDefault, c->stream));
     CK(cudaFreeAsync(tmp, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SIMPLES_OK;
@@ -766,7 +766,7 @@ int simples_em_create(const simples_em_args* a, simples_ctx** out) {
     if (a->z) CKR(upload_z(c, a->z));
     if (a->mu) {
         std::vector<double> hm = to_rowmajor(a->mu, d.G, M0, ldG, 0.0);
-        CK(cudaMemcpyAsync(s.mu, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.mu, hm.data(), hm.size() * 8, cudaMemcpyDefault, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     } else if (M0 > 1 && a->z) {
         // mu <- Y %*% z / n   (R/EM_impute.R:95, Q3)
@@ -870,14 +870,14 @@ int simples_em_fetch(simples_ctx* c, simples_em_out* o) {
     DevState& s = c->s;
     const Dims& d = s.d;
     const int M0 = d.M0, K0 = d.K0;
-    if (o->loglik && c->it > 0) CK(cudaMemcpy(o->loglik, s.loglik, size_t(c->it) * 8, cudaMemcpyDeviceToHost));
-    if (o->pi) CK(cudaMemcpy(o->pi, s.pi, size_t(M0) * 8, cudaMemcpyDeviceToHost));
+    if (o->loglik && c->it > 0) CK(cudaMemcpy(o->loglik, s.loglik, size_t(c->it) * 8, cudaMemcpyDefault));
+    if (o->pi) CK(cudaMemcpy(o->pi, s.pi, size_t(M0) * 8, cudaMemcpyDefault));
     if (o->mu) CKR(fetch_genemajor(c, s.mu, M0, o->mu));
     if (o->sigma) CKR(fetch_genemajor(c, s.sigma, M0, o->sigma));
     if (o->beta) CKR(fetch_genemajor(c, s.beta, K0, o->beta));
     if (o->lambda) {
         std::vector<double> t(size_t(M0) * K0);
-        CK(cudaMemcpy(t.data(), s.lam, t.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(t.data(), s.lam, t.size() * 8, cudaMemcpyDefault));
         for (int k = 0; k < K0; ++k)
             for (int m = 0; m < M0; ++m) o->lambda[size_t(k) * M0 + m] = t[size_t(m) * K0 + k];
     }
@@ -885,14 +885,14 @@ int simples_em_fetch(simples_ctx* c, simples_em_out* o) {
     if (o->Ef)
         for (int m = 0; m < M0; ++m)
             CKR(fetch_transposed(c, s.W + size_t(m) * d.n * K0, d.n, K0, K0, o->Ef + size_t(m) * d.n * K0));
-    if (o->Varf) CK(cudaMemcpy(o->Varf, s.cc.Mm, size_t(M0) * K0 * K0 * 8, cudaMemcpyDeviceToHost));   // symmetric
+    if (o->Varf) CK(cudaMemcpy(o->Varf, s.cc.Mm, size_t(M0) * K0 * K0 * 8, cudaMemcpyDefault));   // symmetric
     if (o->Y)
         CKR(fetch_big(c, o->Y, [&](double* dst, size_t c0, size_t nc) {
             launch_uncenter(s.Y + c0 * d.ldG, dst, s.gmean, s.gsd, int(nc), d.G, d.ldG, c->stream);   // :335
         }));
-    if (o->geneM) CK(cudaMemcpy(o->geneM, s.gmean, size_t(d.G) * 8, cudaMemcpyDeviceToHost));
-    if (o->geneSd) CK(cudaMemcpy(o->geneSd, s.gsd, size_t(d.G) * 8, cudaMemcpyDeviceToHost));
-    if (o->priorB) CK(cudaMemcpy(o->priorB, s.priorB, 8, cudaMemcpyDeviceToHost));
+    if (o->geneM) CK(cudaMemcpy(o->geneM, s.gmean, size_t(d.G) * 8, cudaMemcpyDefault));
+    if (o->geneSd) CK(cudaMemcpy(o->geneSd, s.gsd, size_t(d.G) * 8, cudaMemcpyDefault));
+    if (o->priorB) CK(cudaMemcpy(o->priorB, s.priorB, 8, cudaMemcpyDefault));
     return SIMPLES_OK;
 }
 
@@ -978,9 +978,9 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
         std::vector<double> pm(ldG, 0.0), ps(ldG, 1.0);
         if (a->pos_mean) std::copy(a->pos_mean, a->pos_mean + G, pm.begin());
         if (a->pos_sd) std::copy(a->pos_sd, a->pos_sd + G, ps.begin());
-        CK(cudaMemcpyAsync(s.mu, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.gmean, pm.data(), size_t(ldG) * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(s.gsd, ps.data(), size_t(ldG) * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(s.mu, hm.data(), hm.size() * 8, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(s.gmean, pm.data(), size_t(ldG) * 8, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(s.gsd, ps.data(), size_t(ldG) * 8, cudaMemcpyDefault, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     launch_center(s.Y, s.gmean, s.gsd, n, ldG, 0, 1, c->stream);   // Y <- (Y - pos_mean) / pos_sd  (:50)
@@ -1019,7 +1019,7 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     // ---- outputs (R/do_impute.R:156-159) ----
     if (o->loglik) {
         std::vector<double> t(size_t(nit) * (2 * M0 + 1));
-        CK(cudaMemcpy(t.data(), c->tot_mi, t.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(t.data(), c->tot_mi, t.size() * 8, cudaMemcpyDefault));
         double sacc = 0.0;
         for (int it = a->burnin; it < nit; ++it) sacc += t[size_t(it) * (2 * M0 + 1) + 2 * M0];
         *o->loglik = sacc / a->mcmc;
@@ -1036,9 +1036,9 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
         }));
     if (o->EF || o->varF) {
         std::vector<double> ef(size_t(n) * K0), f2(size_t(n) * K0), vf(size_t(n) * K0);
-        CK(cudaMemcpy(ef.data(), c->rEF, ef.size() * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(f2.data(), c->rF2, f2.size() * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(vf.data(), c->rVF, vf.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ef.data(), c->rEF, ef.size() * 8, cudaMemcpyDefault));
+        CK(cudaMemcpy(f2.data(), c->rF2, f2.size() * 8, cudaMemcpyDefault));
+        CK(cudaMemcpy(vf.data(), c->rVF, vf.size() * 8, cudaMemcpyDefault));
         const double mc = a->mcmc;
         for (int i = 0; i < n; ++i)
             for (int k = 0; k < K0; ++k) {
@@ -1050,7 +1050,7 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     }
     if (o->consensus_cluster && c->cons) {
         launch_scale(c->cons, size_t(n) * n, 1.0 / a->mcmc, c->stream);
-        CK(cudaMemcpyAsync(o->consensus_cluster, c->cons, size_t(n) * n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(o->consensus_cluster, c->cons, size_t(n) * n * 8, cudaMemcpyDefault, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -1100,11 +1100,11 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     CKR(upload_z(c, a->z));
     double* varf = nullptr;
     CKR(c->dalloc(&varf, size_t(M0) * K0 * K0));
-    CK(cudaMemcpyAsync(varf, a->Varf, size_t(M0) * K0 * K0 * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(varf, a->Varf, size_t(M0) * K0 * K0 * 8, cudaMemcpyDefault, c->stream));
     {   // Ef: M0 col-major n x K0 blocks -> W [M0][n][K0]
         double* tmp = nullptr;
         CK(cudaMallocAsync(&tmp, size_t(M0) * n * K0 * 8, c->stream));
-        CK(cudaMemcpyAsync(tmp, a->Ef, size_t(M0) * n * K0 * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(tmp, a->Ef, size_t(M0) * n * K0 * 8, cudaMemcpyDefault, c->stream));
         for (int m = 0; m < M0; ++m)
             launch_transpose(tmp + size_t(m) * n * K0, s.W + size_t(m) * n * K0, K0, n, n, K0, c->stream);
         CK(cudaFreeAsync(tmp, c->stream));
@@ -1131,9 +1131,9 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     if (own_resp) {
         CKR(c->dalloc(&R, na * ldG));
         if (ldG == Gq) {
-            CK(cudaMemcpyAsync(R, a->resp, size_t(n) * Gq * 8, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(R, a->resp, size_t(n) * Gq * 8, cudaMemcpyDefault, c->stream));
         } else {
-            CK(cudaMemcpy2DAsync(R, size_t(ldG) * 8, a->resp, size_t(Gq) * 8, size_t(Gq) * 8, n, cudaMemcpyHostToDevice,
+            CK(cudaMemcpy2DAsync(R, size_t(ldG) * 8, a->resp, size_t(Gq) * 8, size_t(Gq) * 8, n, cudaMemcpyDefault,
                                  c->stream));
         }
     }
@@ -1174,9 +1174,9 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     if (o->sigma) CKR(fetch_genemajor(c, s.sigma, M0, o->sigma));
     if (a->impute && o->Y) {
         if (ldG == Gq) {
-            CK(cudaMemcpyAsync(o->Y, s.Y, size_t(n) * Gq * 8, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(o->Y, s.Y, size_t(n) * Gq * 8, cudaMemcpyDefault, c->stream));
         } else {
-            CK(cudaMemcpy2DAsync(o->Y, size_t(Gq) * 8, s.Y, size_t(ldG) * 8, size_t(Gq) * 8, n, cudaMemcpyDeviceToHost,
+            CK(cudaMemcpy2DAsync(o->Y, size_t(Gq) * 8, s.Y, size_t(ldG) * 8, size_t(Gq) * 8, n, cudaMemcpyDefault,
                                  c->stream));
         }
     }
@@ -1223,12 +1223,12 @@ int simples_init_impute(const simples_init_args* a, simples_init_out* o) {
     CKR(c->dalloc(&part, size_t(nsplit) * nst));
     CKR(c->dalloc(&stats, nst + M0));
     CKR(c->dalloc(&fit, 4 * GM));
-    CK(cudaMemcpyAsync(Y2, a->Y2, size_t(n) * G * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(clus0, c0.data(), size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(stats + nst, cnt.data(), size_t(M0) * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(Y2, a->Y2, size_t(n) * G * 8, cudaMemcpyDefault, c->stream));
+    CK(cudaMemcpyAsync(clus0, c0.data(), size_t(n) * 4, cudaMemcpyDefault, c->stream));
+    CK(cudaMemcpyAsync(stats + nst, cnt.data(), size_t(M0) * 8, cudaMemcpyDefault, c->stream));
     if (a->pg1) {
         CKR(c->dalloc(&pg1, GM, false));
-        CK(cudaMemcpyAsync(pg1, a->pg1, GM * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(pg1, a->pg1, GM * 8, cudaMemcpyDefault, c->stream));
     }
     Tracer tr("init_impute", c->stream);
     tr.mark("H2D");
@@ -1243,10 +1243,10 @@ int simples_init_impute(const simples_init_args* a, simples_init_out* o) {
     launch_init_draw(da, c->stream);
     CK(cudaGetLastError());
     tr.mark("draw");
-    CK(cudaMemcpyAsync(o->impute, Y2, size_t(n) * G * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (o->pg) CK(cudaMemcpyAsync(o->pg, fit + 3 * GM, GM * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (o->mu) CK(cudaMemcpyAsync(o->mu, fit, GM * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (o->sd) CK(cudaMemcpyAsync(o->sd, fit + GM, GM * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(o->impute, Y2, size_t(n) * G * 8, cudaMemcpyDefault, c->stream));
+    if (o->pg) CK(cudaMemcpyAsync(o->pg, fit + 3 * GM, GM * 8, cudaMemcpyDefault, c->stream));
+    if (o->mu) CK(cudaMemcpyAsync(o->mu, fit, GM * 8, cudaMemcpyDefault, c->stream));
+    if (o->sd) CK(cudaMemcpyAsync(o->sd, fit + GM, GM * 8, cudaMemcpyDefault, c->stream));
     tr.mark("D2H");
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
@@ -1293,9 +1293,9 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     const int nsplit = 32;
     CKR(c->dalloc(&part, size_t(nsplit) * ldG));
     if (ldG == G) {
-        CK(cudaMemcpyAsync(Y, a->X, size_t(n) * G * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(Y, a->X, size_t(n) * G * 8, cudaMemcpyDefault, st));
     } else {
-        CK(cudaMemcpy2DAsync(Y, size_t(ldG) * 8, a->X, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpy2DAsync(Y, size_t(ldG) * 8, a->X, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyDefault, st));
     }
     Tracer tr("init_cluster", st);
     tr.mark("H2D");
@@ -1375,7 +1375,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     launch_reduce_parts(km.wss_part, sums + nsum, size_t(R), nw, st);
     CKR(allreduce(c, sums + nsum, size_t(R)));
     std::vector<double> wss(R);
-    CK(cudaMemcpyAsync(wss.data(), sums + nsum, size_t(R) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(wss.data(), sums + nsum, size_t(R) * 8, cudaMemcpyDefault, st));
     CK(cudaStreamSynchronize(st));
     int best = 0;
     for (int r = 1; r < R; ++r)
@@ -1385,14 +1385,14 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     CKR(c->dalloc(&labels, size_t(na)));
     launch_km_pass(km, 2, best, labels, st);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(o->clus, labels, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o->clus, labels, size_t(n) * 4, cudaMemcpyDefault, st));
     if (o->tot_withinss) *o->tot_withinss = wss[best];
-    if (o->d) CK(cudaMemcpyAsync(o->d, dv, size_t(K) * 8, cudaMemcpyDeviceToHost, st));
+    if (o->d) CK(cudaMemcpyAsync(o->d, dv, size_t(K) * 8, cudaMemcpyDefault, st));
     if (o->cellmat) {
         double* tmp;
         CKR(c->dalloc(&tmp, size_t(n) * K, false));
         launch_cellmat_out(P, tmp, n, K, NQP, st);
-        CK(cudaMemcpyAsync(o->cellmat, tmp, size_t(n) * K * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(o->cellmat, tmp, size_t(n) * K * 8, cudaMemcpyDefault, st));
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());

@@ -30,6 +30,9 @@ import oracle as O
 out["init_cluster_ari_vs_truth"] = O.adjusted_rand_index(cl["clus"], Z)
 out["init_cluster_wss"] = cl["tot_withinss"]
 full = timed("SIMPLE_total", lambda: sb.SIMPLE(Y2, K0=10, M0=10, iter=10, clus=clus, p_min=0.4, min_gene=1000, mcmc=10, burnin=2, seed=1, consensus=False))
+resd = timed("SIMPLE_resident_total", lambda: sb.SIMPLE(Y2, K0=10, M0=10, iter=10, clus=clus, p_min=0.4, min_gene=1000, mcmc=10, burnin=2, seed=1, consensus=False, resident=True))
+torch.cuda.synchronize()
+out["resident_equals_host"] = bool(np.array_equal(full["beta"], resd["beta"]))
 out["SIMPLE_ari_vs_truth"] = O.adjusted_rand_index(np.argmax(full["z"], axis=1), Z)
 out["SIMPLE_mse_zero_entries"] = None
 # CPU oracle on bounded samples (same code path as the parity tests)
