@@ -15,6 +15,7 @@
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
 #include <stdint.h>
+#include <string.h>
 #include "simples_b200.h"
 
 static const double *opt_real(SEXP x) { return Rf_isNull(x) ? NULL : REAL(x); }
@@ -140,8 +141,96 @@ SEXP C_simples_do_impute(SEXP dat, SEXP Y, SEXP beta, SEXP lambda, SEXP sigma, S
     return res;
 }
 
+/* init_impute (R/SIMPLE.R:15-73) when pg1 is NULL, init_impute_bulk (R/SIMPLE_B.R:23-114) otherwise.
+ * Returns list(impute, pg). */
+SEXP C_simples_init_impute(SEXP Y2, SEXP M0, SEXP clus, SEXP pg1, SEXP p_min, SEXP cutoff, SEXP seed) {
+    simples_init_args a;
+    simples_init_out o;
+    memset(&a, 0, sizeof a);
+    memset(&o, 0, sizeof o);
+    a.G = Rf_nrows(Y2); a.n = Rf_ncols(Y2); a.M0 = Rf_asInteger(M0);
+    a.Y2 = REAL(Y2); a.clus = (const int32_t *)INTEGER(clus); a.pg1 = opt_real(pg1);
+    a.p_min = Rf_asReal(p_min); a.cutoff = Rf_asReal(cutoff); a.seed = (uint64_t)Rf_asReal(seed);
+    const char *names[] = {"impute", "pg", ""};
+    SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+    SEXP s_im = PROTECT(Rf_allocMatrix(REALSXP, a.G, a.n));
+    SEXP s_pg = PROTECT(Rf_allocMatrix(REALSXP, a.G, a.M0));
+    o.impute = REAL(s_im); o.pg = REAL(s_pg);
+    const int rc = simples_init_impute(&a, &o);
+    if (rc != SIMPLES_OK) {
+        UNPROTECT(3);
+        Rf_error("simples_b200: %s (status %d)", simples_last_error(), rc);
+    }
+    SET_VECTOR_ELT(res, 0, s_im); SET_VECTOR_ELT(res, 1, s_pg);
+    UNPROTECT(3);
+    return res;
+}
+
+/* kmeans(irlba(t(scale(t(X))), nv = K)$v %*% diag(d), M0, iter.max, nstart)$cluster (R/SIMPLE.R:258-266) */
+SEXP C_simples_init_cluster(SEXP X, SEXP K, SEXP M0, SEXP nstart, SEXP iter_max, SEXP seed) {
+    simples_clus_args a;
+    simples_clus_out o;
+    memset(&a, 0, sizeof a);
+    memset(&o, 0, sizeof o);
+    a.G = Rf_nrows(X); a.n = Rf_ncols(X); a.K = Rf_asInteger(K); a.M0 = Rf_asInteger(M0);
+    a.X = REAL(X); a.nstart = Rf_asInteger(nstart); a.iter_max = Rf_asInteger(iter_max);
+    a.seed = (uint64_t)Rf_asReal(seed);
+    SEXP s_cl = PROTECT(Rf_allocVector(INTSXP, a.n));
+    o.clus = (int32_t *)INTEGER(s_cl);
+    const int rc = simples_init_cluster(&a, &o);
+    if (rc != SIMPLES_OK) {
+        UNPROTECT(1);
+        Rf_error("simples_b200: %s (status %d)", simples_last_error(), rc);
+    }
+    UNPROTECT(1);
+    return s_cl;
+}
+
+/* The foreach(g = lq_ind) regression and the for (i in 1:n) draw of R/SIMPLE.R:312-411 (= R/SIMPLE_B.R:335-419).
+ * Ef / Varf are the R lists of impute_hq; they are packed back to back here.  Returns list(mu, beta, sigma, Y). */
+SEXP C_simples_lq_fit(SEXP dat, SEXP resp, SEXP sigma, SEXP pg, SEXP z, SEXP Ef, SEXP Varf, SEXP celltype, SEXP penl,
+                      SEXP cutoff, SEXP resid_mode, SEXP seed) {
+    simples_lq_args a;
+    simples_lq_out o;
+    memset(&a, 0, sizeof a);
+    memset(&o, 0, sizeof o);
+    a.Gq = Rf_nrows(dat); a.n = Rf_ncols(dat); a.M0 = Rf_ncols(z); a.MB = Rf_ncols(pg);
+    a.K0 = Rf_ncols(VECTOR_ELT(Ef, 0));
+    const int Gq = a.Gq, n = a.n, M = a.M0, K = a.K0;
+    double *ef = (double *)R_alloc((size_t)M * n * K, sizeof(double));
+    double *vf = (double *)R_alloc((size_t)M * K * K, sizeof(double));
+    for (int m = 0; m < M; ++m) {
+        memcpy(ef + (size_t)m * n * K, REAL(VECTOR_ELT(Ef, m)), sizeof(double) * (size_t)n * K);
+        memcpy(vf + (size_t)m * K * K, REAL(VECTOR_ELT(Varf, m)), sizeof(double) * (size_t)K * K);
+    }
+    a.dat = REAL(dat); a.resp = opt_real(resp); a.sigma = REAL(sigma); a.pg = REAL(pg); a.z = REAL(z);
+    a.Ef = ef; a.Varf = vf;
+    a.celltype = Rf_isNull(celltype) ? NULL : (const int32_t *)INTEGER(celltype);
+    a.penl = Rf_asReal(penl); a.cutoff = Rf_asReal(cutoff); a.resid_mode = Rf_asInteger(resid_mode); a.impute = 1;
+    a.seed = (uint64_t)Rf_asReal(seed);
+    const char *names[] = {"mu", "beta", "sigma", "Y", ""};
+    SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+    SEXP s_mu = PROTECT(Rf_allocMatrix(REALSXP, Gq, M));
+    SEXP s_be = PROTECT(Rf_allocMatrix(REALSXP, Gq, K));
+    SEXP s_sg = PROTECT(Rf_allocMatrix(REALSXP, Gq, M));
+    SEXP s_y = PROTECT(Rf_allocMatrix(REALSXP, Gq, n));
+    o.mu = REAL(s_mu); o.beta = REAL(s_be); o.sigma = REAL(s_sg); o.Y = REAL(s_y);
+    const int rc = simples_lq_fit(&a, &o);
+    if (rc != SIMPLES_OK) {
+        UNPROTECT(5);
+        Rf_error("simples_b200: %s (status %d)", simples_last_error(), rc);
+    }
+    SEXP parts[] = {s_mu, s_be, s_sg, s_y};
+    for (int i = 0; i < 4; ++i) SET_VECTOR_ELT(res, i, parts[i]);
+    UNPROTECT(5);
+    return res;
+}
+
 static const R_CallMethodDef call_methods[] = {{"C_simples_em_impute", (DL_FUNC)&C_simples_em_impute, 25},
                                                {"C_simples_do_impute", (DL_FUNC)&C_simples_do_impute, 16},
+                                               {"C_simples_init_impute", (DL_FUNC)&C_simples_init_impute, 7},
+                                               {"C_simples_init_cluster", (DL_FUNC)&C_simples_init_cluster, 6},
+                                               {"C_simples_lq_fit", (DL_FUNC)&C_simples_lq_fit, 12},
                                                {NULL, NULL, 0}};
 
 void R_init_SIMPLEs(DllInfo *dll) {
