@@ -734,7 +734,7 @@ int simples_em_create(const simples_em_args* a, simples_ctx** out) {
     s.stats_count = size_t(ldG) * d.NVP + ldG + size_t(M0) * K0 * K0 + size_t(M0) * K0 + 2 * M0 + 1;
     CKR(c->dalloc(&s.stats, s.stats_count));
     CKR(c->dalloc(&s.part_ms, size_t(s.splitK) * ldG * (d.NVP + 1)));
-    s.nsplit_ss = std::max(1, (16 * NUM_SMS_B200) / M0);   // warp-level partial slots of k_sstats
+    s.nsplit_ss = std::max(1, (8 * NUM_SMS_B200) / M0);   // warp-level partial slots of k_sstats
     CKR(c->dalloc(&s.part_ss, size_t(s.nsplit_ss) * M0 * (K0 * K0 + K0)));
     s.ncta_gene = mstep_gene_ctas(d.G);
     CKR(c->dalloc(&s.part_gene, size_t(s.ncta_gene)));
@@ -1116,7 +1116,7 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     CKR(c->dalloc(&s.statsg, s.statsg_count));
     c->nsplit_g = 8;
     CKR(c->dalloc(&c->part_g, size_t(c->nsplit_g) * ldG * ncg));
-    s.nsplit_ss = std::max(1, (16 * NUM_SMS_B200) / M0);   // warp-level partial slots of k_sstats
+    s.nsplit_ss = std::max(1, (8 * NUM_SMS_B200) / M0);   // warp-level partial slots of k_sstats
     CKR(c->dalloc(&s.part_ss, size_t(s.nsplit_ss) * M0 * (K0 * K0 + K0)));
 
     tr.mark("H2D(z, Ef)");
