@@ -151,7 +151,7 @@ def run_reference(args):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "R is not installed in this image or on the GPU box; this is the CPU restatement (oracle) of the "
                     "reference algorithm with a sufficient-statistic M-step, i.e. faster than the R package would be"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def cpu_baseline_sample():
@@ -172,7 +172,26 @@ def cpu_baseline_sample():
             "sample": f"{ncell} cells x {CFG['G']} genes of the same workload, 2 steady-state EM iterations, NumPy/OpenBLAS oracle"}
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print to fd 1 (e.g. NCCL's version banner under
+    NCCL_DEBUG=VERSION) are sent to stderr; the result line goes to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -335,7 +354,7 @@ def main():
                 "em_iters_per_sec": 1e3 / ms_per_step, "wall_ms_per_step": wall * 1e3 / K,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern,
                 "cpu_baseline": cpu, "e2e": e2e, "loglik_last": float(ll[-1]) if len(ll) else None}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
