@@ -1137,9 +1137,22 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
                                  c->stream));
         }
     }
+    // T = Y (z_m Ef_m), U = Y z, Uh = Y sqrt z: the DMMA mstep_stats kernel in blocks of <= 96 operand columns;
+    // U2 = Y.^2 z through the generic kernel (M0 columns)
+    const int NVPq = std::min(96, round_up(ncg, 8)), VSq = NVPq + 4, splitKq = mstats_pick_splitk(ldG);
+    double *Vblk, *zs0, *pmsq, *blkq;
+    CKR(c->dalloc(&Vblk, na * VSq));
+    CKR(c->dalloc(&zs0, na));
+    CKR(c->dalloc(&pmsq, size_t(splitKq) * ldG * (NVPq + 1)));
+    CKR(c->dalloc(&blkq, size_t(ldG) * NVPq));
     auto gene_stats = [&](const double* Ymat, double* out) {
-        launch_ygemm_simple(Ymat, s.Vg, c->part_g, n, ldG, ncg, ncg, 0, c->nsplit_g, c->stream);
-        launch_reduce_parts(c->part_g, out, nC, c->nsplit_g, c->stream);
+        for (int c0 = 0; c0 < ncg; c0 += NVPq) {
+            launch_extract_cols(s.Vg, Vblk, n, ncg, ncg, c0, NVPq, VSq, c->stream);
+            MstatsArgs ma{Ymat, Vblk, zs0, pmsq, n, ldG, NVPq, VSq, splitKq};
+            launch_mstats(ma, c->stream);
+            launch_reduce_parts(pmsq, blkq, size_t(ldG) * NVPq, splitKq, c->stream);
+            launch_scatter_block(blkq, out, ldG, ncg, NVPq, c0, std::min(NVPq, ncg - c0), c->stream);
+        }
         launch_ygemm_simple(Ymat, s.Vg + size_t(K0) * M0, c->part_g, n, ldG, M0, ncg, 1, c->nsplit_g, c->stream);
         launch_reduce_parts(c->part_g, out + nC, nU2, c->nsplit_g, c->stream);
     };
@@ -1326,7 +1339,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
         MstatsArgs ma{Y, V, zs, pms, n, ldG, NVP, VS, splitK};
         launch_mstats(ma, st);
         launch_reduce_parts(pms, blk, size_t(ldG) * NVP, splitK, st);
-        launch_scatter_block(blk, C, ldG, NVP, g0, ncol, st);
+        launch_scatter_block(blk, C, ldG, ldG, NVP, g0, ncol, st);
     }
     CKR(allreduce(c, C, size_t(ldG) * ldG));
     tr.mark("gram");
@@ -1335,7 +1348,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     CKR(c->dalloc(&Z, size_t(ldG) * KP));
     CKR(c->dalloc(&A, size_t(ldG) * QS));
     CKR(c->dalloc(&dv, size_t(32)));
-    launch_subspace(C, Q, Z, A, dv, G, ldG, KP, K, QS, 300, a->seed, st);
+    launch_subspace(C, Q, Z, A, dv, G, ldG, KP, K, QS, 150, a->seed, st);
     tr.mark("subspace");
     // ---- cellmat = Ys' U = V diag(d)  (estep_project) ----
     CKR(c->dalloc(&isg, size_t(ldG)));
@@ -1363,13 +1376,29 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     CKR(c->dalloc(&km.part, size_t(nw) * nsum));
     CKR(c->dalloc(&km.wss_part, size_t(nw) * R));
     CKR(c->dalloc(&sums, nsum + R));
+    int* nlive;                                    // [iter_max] restarts still moving after each update
+    CKR(c->dalloc(&km.moved, size_t(R), false));
+    CKR(c->dalloc(&nlive, size_t(a->iter_max)));
+    {
+        std::vector<int> ones_i(R, 1);
+        CK(cudaMemcpyAsync(km.moved, ones_i.data(), size_t(R) * 4, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+    }
     launch_km_init(km, a->seed, n_total, a->cell_offset, st);
     CKR(allreduce(c, km.cent, size_t(R) * M0 * K));
+    int km_iters = 0;
     for (int it = 0; it < a->iter_max; ++it) {
-        launch_km_pass(km, 0, 0, nullptr, st);
+        ++km_iters;
+        launch_km_pass(km, 0, 0, nullptr, st);     // converged restarts are skipped (their sums stay valid)
         launch_reduce_parts(km.part, sums, nsum, nw, st);
         CKR(allreduce(c, sums, nsum));
-        launch_km_update(km, sums, st);
+        launch_km_update(km, sums, nlive + it, st);
+        if ((it & 3) == 3) {                       // every 4 iterations: stop once no restart moves (Lloyd fixed point)
+            int h = 1;
+            CK(cudaMemcpyAsync(&h, nlive + it, 4, cudaMemcpyDefault, st));
+            CK(cudaStreamSynchronize(st));
+            if (h == 0) break;
+        }
     }
     launch_km_pass(km, 1, 0, nullptr, st);
     launch_reduce_parts(km.wss_part, sums + nsum, size_t(R), nw, st);
@@ -1381,6 +1410,13 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     for (int r = 1; r < R; ++r)
         if (wss[r] < wss[best]) best = r;
     tr.mark("kmeans");
+    if (tr.on) {
+        std::vector<int> nl(a->iter_max, 0);
+        cudaMemcpy(nl.data(), nlive, size_t(a->iter_max) * 4, cudaMemcpyDefault);
+        std::string t = " [" + std::to_string(km_iters) + " Lloyd iterations; restarts still moving:";
+        for (int it = 0; it < km_iters; it += 4) t += " " + std::to_string(nl[it]);
+        tr.msg += t + "],";
+    }
     int32_t* labels;
     CKR(c->dalloc(&labels, size_t(na)));
     launch_km_pass(km, 2, best, labels, st);

@@ -19,12 +19,12 @@ __global__ void k_extract_cols(const double* Y, double* V, int n, int ldG, int G
     V[e] = (c < ncol && g0 + c < G) ? Y[size_t(i) * ldG + g0 + c] : 0.0;
 }
 
-// C[g][g0 + c] = blk[g][c]
-__global__ void k_scatter_block(const double* blk, double* C, int ldG, int NVP, int g0, int ncol) {
+// C[g][g0 + c] = blk[g][c]   (C has `rows` rows of stride ldc)
+__global__ void k_scatter_block(const double* blk, double* C, int rows, int ldc, int NVP, int g0, int ncol) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ldG * ncol) return;
+    if (e >= rows * ncol) return;
     const int g = e / ncol, c = e - g * ncol;
-    if (g0 + c < ldG) C[size_t(g) * ldG + g0 + c] = blk[size_t(g) * NVP + c];
+    if (g0 + c < ldc) C[size_t(g) * ldc + g0 + c] = blk[size_t(g) * NVP + c];
 }
 
 // sd_g = sqrt(ss_g / (n - 1)) (0 -> 1 so that constant genes scale to 0 instead of NaN), mean <- 0 for the 2nd centring pass
@@ -222,6 +222,11 @@ __global__ void __launch_bounds__(KMW * 32) k_km_pass(KmArgs a, int RG, int cell
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = (mode == 2) ? rsel : blockIdx.y * RG;
     const int nr = (mode == 2) ? 1 : min(RG, a.R - r0);
+    if (mode == 0) {      // a restart whose centres did not move in the last update is converged: its sums stay valid
+        bool live = false;
+        for (int rr = 0; rr < nr; ++rr) live |= a.moved[r0 + rr] != 0;
+        if (!live) return;
+    }
     double* cen = sm;                                   // [RG][M0][K]
     double* xt = cen + size_t(RG) * M0 * K + size_t(warp) * 32 * KS;          // per warp [32][K+1] cell tile
     double* acc = sm + size_t(RG) * M0 * K + size_t(KMW) * 32 * KS + size_t(warp) * RG * M0 * KS;   // per warp [RG][M0][K+1]
@@ -247,17 +252,28 @@ __global__ void __launch_bounds__(KMW * 32) k_km_pass(KmArgs a, int RG, int cell
             double bd = 1.0e308;
             if (lane < nb) {
                 const double* x = xt + lane * KS;
-                for (int j = 0; j < M0; ++j) {
-                    const double* c = cen + (size_t(rr) * M0 + j) * K;
-                    double d = 0.0;
+                int j = 0;
+                for (; j + 1 < M0; j += 2) {                       // two centres at a time: independent FMA chains
+                    const double* c0 = cen + (size_t(rr) * M0 + j) * K;
+                    const double* c1 = c0 + K;
+                    double d0 = 0.0, d1 = 0.0;
                     for (int k = 0; k < K; ++k) {
-                        const double t = x[k] - c[k];
-                        d = fma(t, t, d);
+                        const double xk = x[k];
+                        const double t0 = xk - c0[k], t1 = xk - c1[k];
+                        d0 = fma(t0, t0, d0);
+                        d1 = fma(t1, t1, d1);
                     }
-                    if (d < bd) {
-                        bd = d;
-                        best = j;
+                    if (d0 < bd) { bd = d0; best = j; }
+                    if (d1 < bd) { bd = d1; best = j + 1; }
+                }
+                if (j < M0) {
+                    const double* c0 = cen + (size_t(rr) * M0 + j) * K;
+                    double d0 = 0.0;
+                    for (int k = 0; k < K; ++k) {
+                        const double t0 = x[k] - c0[k];
+                        d0 = fma(t0, t0, d0);
                     }
+                    if (d0 < bd) { bd = d0; best = j; }
                 }
             }
             if (mode == 0) {
@@ -285,13 +301,33 @@ __global__ void __launch_bounds__(KMW * 32) k_km_pass(KmArgs a, int RG, int cell
     }
 }
 
-// centres <- sums / counts (an empty cluster keeps its centre)
-__global__ void k_km_update(KmArgs a, const double* sums) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.R * a.M0 * a.K) return;
-    const int rj = e / a.K, k = e - rj * a.K;
-    const double cnt = sums[size_t(rj) * (a.K + 1) + a.K];
-    if (cnt > 0.0) a.cent[e] = sums[size_t(rj) * (a.K + 1) + k] / cnt;
+// centres <- sums / counts (an empty cluster keeps its centre); moved[r] = any centre of restart r changed;
+// *nlive counts the restarts still moving (read by the host every few iterations to stop early)
+__global__ void k_km_update(KmArgs a, const double* sums, int* nlive) {
+    const int r = blockIdx.x;
+    __shared__ int changed;
+    if (threadIdx.x == 0) changed = 0;
+    __syncthreads();
+    if (a.moved[r]) {
+        int ch = 0;
+        for (int e = threadIdx.x; e < a.M0 * a.K; e += blockDim.x) {
+            const int j = e / a.K, k = e - j * a.K;
+            const size_t rj = size_t(r) * a.M0 + j;
+            const double cnt = sums[rj * (a.K + 1) + a.K];
+            if (cnt > 0.0) {
+                const double v = sums[rj * (a.K + 1) + k] / cnt;
+                double* c = a.cent + rj * a.K + k;
+                ch |= (v != *c);
+                *c = v;
+            }
+        }
+        if (ch) atomicOr(&changed, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.moved[r] = changed;
+        if (changed) atomicAdd(nlive, 1);
+    }
 }
 
 // cellmat (n x K col-major, host layout) from P [n][ldx]
@@ -308,8 +344,8 @@ void launch_extract_cols(const double* Y, double* V, int n, int ldG, int G, int 
     const size_t tot = size_t(n) * VS;
     k_extract_cols<<<unsigned((tot + 255) / 256), 256, 0, st>>>(Y, V, n, ldG, G, g0, ncol, VS);
 }
-void launch_scatter_block(const double* blk, double* C, int ldG, int NVP, int g0, int ncol, cudaStream_t st) {
-    k_scatter_block<<<(ldG * ncol + 255) / 256, 256, 0, st>>>(blk, C, ldG, NVP, g0, ncol);
+void launch_scatter_block(const double* blk, double* C, int rows, int ldc, int NVP, int g0, int ncol, cudaStream_t st) {
+    k_scatter_block<<<(rows * ncol + 255) / 256, 256, 0, st>>>(blk, C, rows, ldc, NVP, g0, ncol);
 }
 void launch_sd_from_ss(const double* ss, double* sd, double* zero, int G, int ldG, double nm1, cudaStream_t st) {
     k_sd_from_ss<<<(ldG + 127) / 128, 128, 0, st>>>(ss, sd, zero, G, ldG, nm1);
@@ -327,7 +363,7 @@ void launch_subspace(const double* C, double* Q, double* Z, double* A, double* d
 
 int km_restart_group(int M0, int K) {
     const size_t per = size_t(M0) * K * 8 + size_t(KMW) * M0 * (K + 1) * 8;
-    int rg = int((56 * 1024 - size_t(KMW) * 32 * (K + 1) * 8) / per);
+    int rg = int((40 * 1024 - size_t(KMW) * 32 * (K + 1) * 8) / per);   // ~40 KB per CTA => 5 CTAs (20 warps) per SM
     return rg < 1 ? 1 : (rg > 8 ? 8 : rg);
 }
 void launch_km_init(const KmArgs& a, unsigned long long seed, long long n_total, long long cell_offset, cudaStream_t st) {
@@ -347,8 +383,8 @@ void launch_km_pass(const KmArgs& a, int mode, int rsel, int32_t* labels, cudaSt
     dim3 grid(a.nsplit, mode == 2 ? 1 : (a.R + RG - 1) / RG);
     k_km_pass<<<grid, KMW * 32, smem, st>>>(a, RG, cpw, mode, rsel, labels);
 }
-void launch_km_update(const KmArgs& a, const double* sums, cudaStream_t st) {
-    k_km_update<<<(a.R * a.M0 * a.K + 255) / 256, 256, 0, st>>>(a, sums);
+void launch_km_update(const KmArgs& a, const double* sums, int* nlive, cudaStream_t st) {
+    k_km_update<<<a.R, 128, 0, st>>>(a, sums, nlive);
 }
 void launch_cellmat_out(const double* P, double* out, int n, int K, int ldx, cudaStream_t st) {
     const size_t tot = size_t(n) * K;

@@ -203,16 +203,17 @@ struct KmArgs {
     double* cent;       // [R][M0][K]
     double* part;       // [nsplit * 4][R][M0][K + 1] per-warp sums | counts
     double* wss_part;   // [nsplit * 4][R]
+    int* moved;         // [R] 1 while the restart's centres still move
     int nsplit;
 };
 void launch_extract_cols(const double* Y, double* V, int n, int ldG, int G, int g0, int ncol, int VS, cudaStream_t st);
-void launch_scatter_block(const double* blk, double* C, int ldG, int NVP, int g0, int ncol, cudaStream_t st);
+void launch_scatter_block(const double* blk, double* C, int rows, int ldc, int NVP, int g0, int ncol, cudaStream_t st);
 void launch_sd_from_ss(const double* ss, double* sd, double* zero, int G, int ldG, double nm1, cudaStream_t st);
 void launch_subspace(const double* C, double* Q, double* Z, double* A, double* dvals, int G, int ldG, int KP, int K, int QS,
                      int iters, unsigned long long seed, cudaStream_t st);
 void launch_km_init(const KmArgs& a, unsigned long long seed, long long n_total, long long cell_offset, cudaStream_t st);
 void launch_km_pass(const KmArgs& a, int mode, int rsel, int32_t* labels, cudaStream_t st);
-void launch_km_update(const KmArgs& a, const double* sums, cudaStream_t st);
+void launch_km_update(const KmArgs& a, const double* sums, int* nlive, cudaStream_t st);
 void launch_cellmat_out(const double* P, double* out, int n, int K, int ldx, cudaStream_t st);
 
 // misc
