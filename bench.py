@@ -203,7 +203,11 @@ def main():
     ap.add_argument("--e2e-iter", type=int, default=10)
     ap.add_argument("--K0", type=int, default=None, help="override the number of factors (non-headline runs, e.g. C5)")
     ap.add_argument("--M0", type=int, default=None, help="override the number of clusters (non-headline runs)")
+    ap.add_argument("--genes", type=int, default=None, help="override the number of genes (non-headline runs, e.g. a C4 shard)")
     args = ap.parse_args()
+    if args.genes is not None:
+        CFG["G"] = args.genes
+        CFG["override"] = True
     if args.K0 is not None or args.M0 is not None:
         CFG["K0"] = args.K0 or CFG["K0"]
         CFG["M0"] = args.M0 or CFG["M0"]
@@ -346,7 +350,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": ("NON-HEADLINE override (--K0/--M0/--cells): " if CFG.get("override") or n != CFG["n"] else "")
-                                       + f"C3: synthetic zero-inflated log-counts {n // 1000}k cells x 2k genes per GPU, K0={K0}, M0={M0}, "
+                                       + f"C3: synthetic zero-inflated log-counts {n // 1000}k cells x {G / 1000:g}k genes per GPU, K0={K0}, M0={M0}, "
                                        "impt_it=1, num_mc=3 (steady-state EM iteration)",
                            "cells_per_gpu": n, "genes": G, "K0": K0, "M0": M0, "zero_fraction": rho,
                            "l2": "inputs (1.6 GB Y per GPU) exceed L2; no flush needed",

@@ -361,6 +361,15 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     unsigned long long h_nnz = 0;
     CK(cudaMemcpy(&h_nnz, c->d_nnz, 8, cudaMemcpyDefault));
     c->nnz0 = (long long)h_nnz;
+    {   // NA/NaN/Inf in Y would poison every statistic silently (the reference's glmnet call stops on them)
+        unsigned long long* d_bad = nullptr;
+        CKR(c->dalloc(&d_bad, 1));
+        launch_count_nonfinite(s.Y, na * ldG, d_bad, c->stream);
+        unsigned long long h_bad = 0;
+        CK(cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDefault, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (h_bad) return fail(SIMPLES_EINVAL, "Y contains " + std::to_string(h_bad) + " non-finite value(s)");
+    }
     return SIMPLES_OK;
 }
 

@@ -215,6 +215,15 @@ __global__ void k_lq_cell(LqCellArgs a) {
     for (int c = K0; c < d.FS; ++c) fh[c] = 0.0;
 }
 
+// number of non-finite entries of a buffer (input validation)
+__global__ void k_count_nonfinite(const double* p, size_t count, unsigned long long* out) {
+    unsigned long long c = 0;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
+        c += isfinite(p[i]) ? 0ull : 1ull;
+    c = __reduce_add_sync(0xffffffffu, (unsigned)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // out[m] = sum_i z[i][m] in a fixed order (one CTA), out[M0 .. 2 M0] = 0
 __global__ void __launch_bounds__(256) k_colsum(const double* z, double* out, int n, int M0) {
     __shared__ double red[256];
@@ -280,6 +289,9 @@ void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t
     k_consensus<<<grid, block, 0, st>>>(z, cons, n, M0);
 }
 
+void launch_count_nonfinite(const double* p, size_t count, unsigned long long* out, cudaStream_t st) {
+    k_count_nonfinite<<<gs_grid(count), 256, 0, st>>>(p, count, out);
+}
 void launch_lq_cell(const LqCellArgs& a, cudaStream_t st) { k_lq_cell<<<(a.d.n + 127) / 128, 128, 0, st>>>(a); }
 void launch_colsum(const double* z, double* out, int n, int M0, cudaStream_t st) { k_colsum<<<1, 256, 0, st>>>(z, out, n, M0); }
 

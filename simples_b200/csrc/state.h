@@ -219,6 +219,7 @@ void launch_cellmat_out(const double* P, double* out, int n, int K, int ldx, cud
 // misc
 void launch_build_mask(const double* Y0chunk, uint32_t* mask, int ncell, int cell0, int n_alloc, int G, int ldG, double cutoff,
                        unsigned long long* nnz, cudaStream_t st);
+void launch_count_nonfinite(const double* p, size_t count, unsigned long long* out, cudaStream_t st);
 void launch_clip(double* Y, int n, int G, int ldG, double lower, double upper, cudaStream_t st);
 void launch_rowsum(const double* Y, double* part, int n, int ldG, int nsplit, cudaStream_t st);
 void launch_center(double* Y, const double* gmean, const double* gsd, int n, int ldG, double scale_n, int mode, cudaStream_t st);

@@ -73,6 +73,8 @@ def init_state(gp, Y2, Z, K0, M0, cutoff=0.1, pgv=0.6, seed=1):
         blk = Yt[a:b]
         msk = blk <= cutoff
         u = rngc.random(blk.shape) * 0.998 + 0.001
-        draw = gm[None, :] + gs[None, :] * special.ndtri(u * pr[None, :])
+        zq = special.ndtri(u * pr[None, :])
+        zq = np.where(np.isfinite(zq), zq, r[None, :] - 0.05)        # Phi(r) underflows for genes far above the cutoff
+        draw = gm[None, :] + gs[None, :] * zq
         blk[msk] = draw[msk]
     return dict(Y=Yt.T, Y0=Y2, pg=pg, beta=beta, sigma=sigma, lam=lam, pi=pi, z=z, celltype=clus.astype(np.int32))

@@ -159,6 +159,15 @@ def test_golden_fixture(sb):
     assert rel(mi["impt"], g["mi_impt"]) <= 1e-6 and abs(mi["loglik"] - float(g["mi_loglik"])) <= 1e-8 * abs(float(g["mi_loglik"]))
 
 
+def test_non_finite_input_is_rejected(sb):
+    K0, M0 = 3, 2
+    st = make_case(80, 60, 2, 2, K0, M0, seed=3)
+    Y = np.array(st["Y"]); Y[7, 11] = np.nan
+    with pytest.raises(sb.SimplesError) as e:
+        sb.EM_impute(Y, st["Y0"], st["pg"], M0, K0, 0.1, 1, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"])
+    assert e.value.code == -1 and "non-finite" in str(e.value)
+
+
 def test_error_paths(sb):
     K0, M0 = 3, 2
     st = make_case(64, 40, 1, 2, K0, M0, seed=1)
@@ -577,3 +586,25 @@ def test_resident_pipeline_equals_host_pipeline(sb):
     a = sb.init_impute(Yd, 2, sim["Z"], 0.4, 0.1, seed=1, out=sb.dev_empty(*sim["Y2"].shape))
     b = sb.init_impute(sim["Y2"], 2, sim["Z"], 0.4, 0.1, seed=1)
     assert np.array_equal(a[0].cpu().numpy(), b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_golden_stages(sb):
+    """CUDA path against the committed fixtures of the stages around the hot path (oracle-generated)."""
+    g = np.load(os.path.join(GOLD, "stages_small.npz"))
+    Y2, Z = g["Y2"], g["Z"]
+    imp, pg, mu, sd = sb.init_impute(Y2, 2, Z, 0.4, 0.1, seed=3, sweep=1, details=True)
+    assert rel(sd, g["init_sd"]) <= 1e-6 and rel(pg, g["init_pg"]) <= 1e-6 and _draw_mismatch(imp, g["init_impute"], 1e-5) <= 3
+    impb = sb.init_impute_bulk(Y2, Z, None, g["pg1"], 0.1, seed=4, sweep=2)
+    assert _draw_mismatch(impb, g["init_bulk"], 1e-5) <= 3
+    cl = sb.init_cluster(Y2[:60], 4, 2, seed=6, nstart=5, iter_max=15, details=True)
+    assert rel(cl["d"], g["d"]) <= 1e-8 and O.adjusted_rand_index(cl["clus"], g["clus"]) >= 0.99
+    lq = np.arange(40, 90)
+    fit = sb.lq_fit(Y2[lq], g["lq_sigma_in"], g["lq_pg"], g["em_z"], list(g["em_Ef"]), list(g["em_Varf"]), g["celltype"],
+                    resid_mode=1, seed=9, sweep=3)
+    for k in ("mu", "beta", "sigma"):
+        assert rel(fit[k], g["lq_" + k]) <= 1e-8, k
+    assert rel(fit["Y"], g["lq_Y"]) <= 1e-6
+    run = sb.SIMPLE(Y2, K0=3, M0=2, iter=3, clus=Z, min_gene=45, mcmc=2, burnin=1, seed=5)
+    for k in ("loglik_tot", "beta", "sigma", "mu", "pi", "lambda", "z", "impt", "Yimp0", "pg"):
+        assert rel(run[k], g["run_" + k]) <= 1e-5, k
+    assert abs(run["BIC"] - float(g["run_BIC"])) <= 1e-6 * abs(float(g["run_BIC"]))

@@ -349,3 +349,19 @@ def test_init_cluster_oracle_and_ari():
     assert abs(np.linalg.norm(cm, axis=0)[0] - np.linalg.svd(Xs, compute_uv=False)[0]) <= 1e-9 * d[0]   # |V d| = d
     assert O.adjusted_rand_index([1, 1, 2, 2], [2, 2, 1, 1]) == 1.0
     assert abs(O.adjusted_rand_index([1, 1, 2, 2], [1, 2, 1, 2]) + 0.5) < 1e-12
+
+
+def test_golden_stages_regression():
+    """Committed oracle fixtures of the stages around the hot path (tests/golden/make_golden.py::stages)."""
+    g = np.load(os.path.join(GOLD, "stages_small.npz"))
+    Y2, Z = g["Y2"], g["Z"]
+    imp, pg, mu, sd = O.init_impute_ref(Y2, 2, Z, 0.4, 0.1, seed=3, sweep=1)
+    assert rel(imp, g["init_impute"]) <= 1e-12 and rel(pg, g["init_pg"]) <= 1e-12 and rel(sd, g["init_sd"]) <= 1e-12
+    par, pgz = O.ztruncnorm_ref(Y2, cutoff=0.1, p_min=0.6, p_max=1.0)
+    assert np.array_equal(np.isnan(par), np.isnan(g["zt_param"])) and rel(np.nan_to_num(par), np.nan_to_num(g["zt_param"])) <= 1e-12
+    clus, cm, d, wss = O.init_cluster_ref(Y2[:60], 4, 2, nstart=5, iter_max=15, seed=6)
+    assert np.array_equal(clus, g["clus"]) and rel(d, g["d"]) <= 1e-10
+    Ef, Varf = list(g["em_Ef"]), list(g["em_Varf"])
+    lq = np.arange(40, 90)
+    m_, b_, s_ = O.lq_regress_fast(Y2[lq], Y2[lq], g["lq_sigma_in"], g["em_z"], Ef, Varf, 1, 1)
+    assert rel(m_, g["lq_mu"]) <= 1e-10 and rel(b_, g["lq_beta"]) <= 1e-10 and rel(s_, g["lq_sigma"]) <= 1e-10
