@@ -849,6 +849,13 @@ int simples_em_sync(simples_ctx* c) {
         }
     }
     c->prof_collect();
+    if (getenv("SIMPLES_TRACE")) {
+        int d[4];
+        lasso_debug_fetch(d, true);
+        if (d[0])
+            fprintf(stderr, "[simples_b200] lasso: %d solves, %.1f coordinate-descent sweeps on average, max %d, %d at the cap\n",
+                    d[0], double(d[1]) / d[0], d[2], d[3]);
+    }
     return SIMPLES_OK;
 }
 

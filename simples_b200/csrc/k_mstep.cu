@@ -64,7 +64,21 @@ __device__ bool lasso_polish(const double* A, int K, double rhs, double kappa, d
     bool bad = false;
     for (int i = 0; i < ns; ++i) bad |= !(L[i * ns + i] > 0.0);
     if (bad) return false;
-    warp_chol_solve(L, xs, ns, lane);
+    // (L L') x = xs: forward / backward substitution, each row a warp-wide dot product (ns <= 32)
+    for (int i = 0; i < ns; ++i) {
+        const double part = (lane < i) ? L[i * ns + lane] * xs[lane] : 0.0;
+        const double sdot = warp_sum(part);
+        __syncwarp();
+        if (lane == 0) xs[i] = (xs[i] - sdot) / L[i * ns + i];
+        __syncwarp();
+    }
+    for (int i = ns - 1; i >= 0; --i) {
+        const double part = (lane > i && lane < ns) ? L[lane * ns + i] * xs[lane] : 0.0;
+        const double sdot = warp_sum(part);
+        __syncwarp();
+        if (lane == 0) xs[i] = (xs[i] - sdot) / L[i * ns + i];
+        __syncwarp();
+    }
     const double xm = mine ? xs[pos] : 0.0;
     if (__ballot_sync(0xffffffffu, mine && ((xm > 0.0) != (b > 0.0) || xm == 0.0))) return false;
     double gk = rhs;
@@ -76,9 +90,22 @@ __device__ bool lasso_polish(const double* A, int K, double rhs, double kappa, d
 }
 
 // min 0.5 b'Ab - rhs'b + kappa |b|_1 : cyclic coordinate descent from 0 (glmnet's start) + exact polish.
+__device__ int g_lasso_dbg[4];   // SIMPLES_TRACE diagnostics: [0] solves, [1] total CD sweeps, [2] max sweeps, [3] capped
+
+__device__ __forceinline__ void lasso_note(int sweeps, int lane) {
+    if (lane == 0) {
+        atomicAdd(&g_lasso_dbg[0], 1);
+        atomicAdd(&g_lasso_dbg[1], sweeps);
+        atomicMax(&g_lasso_dbg[2], sweeps);
+        if (sweeps >= 20000) atomicAdd(&g_lasso_dbg[3], 1);
+    }
+}
+
 __device__ double lasso_solve(const double* A, int K, double rhs, double kappa, double* L, double* xs, int* idx, int lane) {
     double b = 0.0, r = rhs;
     const bool kl = lane < K;
+    unsigned pat_p = 0u, pat_n = 0u, fail_p = ~0u, fail_n = ~0u;
+    int stable = 0, last_fail = -1000;
     for (int sweep = 0; sweep < 20000; ++sweep) {
         double maxd = 0.0, maxb = 1.0;
         for (int k = 0; k < K; ++k) {
@@ -96,11 +123,25 @@ __device__ double lasso_solve(const double* A, int K, double rhs, double kappa, 
             maxb = fmax(maxb, fabs(bn));
         }
         const bool done = maxd <= 1e-15 * maxb;
-        if (sweep >= 3 && ((sweep & 3) == 3 || done)) {
-            if (lasso_polish(A, K, rhs, kappa, b, L, xs, idx, lane)) return b;
-            if (done) return b;
+        // The exact polish costs several sweeps and can only succeed once the active set has settled: try it when the
+        // sign pattern has been the same for three sweeps (a pattern that failed is retried 16 sweeps later, when the
+        // inactive coordinates' gradients have moved), and when coordinate descent has converged by itself.
+        const unsigned np = __ballot_sync(0xffffffffu, kl && b > 0.0), nn = __ballot_sync(0xffffffffu, kl && b < 0.0);
+        stable = (np == pat_p && nn == pat_n) ? stable + 1 : 0;
+        pat_p = np;
+        pat_n = nn;
+        const bool fresh = !(np == fail_p && nn == fail_n) || sweep - last_fail >= 16;
+        if (done || (stable >= 2 && fresh)) {
+            if (lasso_polish(A, K, rhs, kappa, b, L, xs, idx, lane) || done) {
+                lasso_note(sweep + 1, lane);
+                return b;
+            }
+            fail_p = np;
+            fail_n = nn;
+            last_fail = sweep;
         }
     }
+    lasso_note(20000, lane);
     return b;
 }
 
@@ -488,6 +529,14 @@ __global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
 }  // namespace
 
 int mstep_gene_ctas(int G) { return (G + GW - 1) / GW; }
+
+void lasso_debug_fetch(int out[4], bool reset) {
+    cudaMemcpyFromSymbol(out, g_lasso_dbg, sizeof(int) * 4);
+    if (reset) {
+        const int z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_lasso_dbg, z, sizeof z);
+    }
+}
 
 void launch_mstep(const MstepArgs& a, cudaStream_t st) {
     const int K0 = a.d.K0, M0 = a.d.M0;

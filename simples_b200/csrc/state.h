@@ -165,6 +165,7 @@ struct MstepArgs {
 };
 void launch_mstep(const MstepArgs& a, cudaStream_t st);
 int mstep_gene_ctas(int G);
+void lasso_debug_fetch(int out[4], bool reset);   // {solves, total CD sweeps, max sweeps, capped} since the last reset
 
 // low-quality-gene fit (R/SIMPLE.R:305-411)
 struct LqSolveArgs {
