@@ -98,3 +98,20 @@ class CellShard:
         parts = [None] * self.world_size
         dist.all_gather_object(parts, np.ascontiguousarray(A_local), group=self.group)
         return np.concatenate(parts, axis=1)
+
+
+class Replicas:
+    """One process per GPU, each holding the WHOLE data set (no cell sharding): independent runs are dealt to the
+    ranks and only small Python objects are exchanged (``selectKM(..., replicas=Replicas())``)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+
+    def allgather(self, obj):
+        parts = [None] * self.world_size
+        self._dist.all_gather_object(parts, obj, group=self.group)
+        return parts

@@ -248,34 +248,60 @@ def SIMPLE_B(dat, K0, bulk, celltype, M0=1, clus=None, K=20, b=1, iter=10, est_z
 def selectKM(dat, bulk=None, celltype=None, b=1, K0=10, M0=1, iter=10, est_lam=1, impt_it=5, penl=1, sigma0=100,
              pi_alpha=1, beta=None, verbose=False, max_lambda=True, lambda_=None, sigma=None, mu=None, est_z=1, clus=None,
              p_min=0.4, cutoff=0.1, K=20, min_gene=300, num_mc=3, fix_num=False, mcmc=50, burnin=2, rel=0.01, *, seed=0,
-             comm=None, consensus=None, resident=False):
+             comm=None, consensus=None, resident=False, replicas=None, _simple=None):
     """``selectKM`` (R/select_KM.R:126-189): BIC grid over the number of clusters and factors with the reference's
     early stopping along K.  ``bulk`` / ``celltype`` / ``b`` are accepted and ignored exactly as in the reference
-    (it always calls ``SIMPLE``, :152-155).  Returns BICs (dict of dicts [M][K]), mK, mM, result."""
-    dat = _as_matrix(dat, resident)                                           # uploaded once for the whole grid
-    n = _n_total(dat.shape[1], comm)
+    (it always calls ``SIMPLE``, :152-155).  Returns BICs (dict of dicts [M][K]), mK, mM, result.
+
+    ``replicas`` (a ``simples_b200.dist.Replicas``): one process per GPU, every process holds the whole ``dat``; the
+    M = 1 pass runs everywhere (it provides ``init_imp`` for the others, :185), the remaining values of M are dealt
+    round-robin to the ranks, each runs its own early-stopped K loop, and the BIC table is gathered.  The selected
+    (mK, mM) is the same as the sequential loop's (first minimum in (M, K) order); ``result`` is the full run on the
+    rank that computed it and ``None`` elsewhere."""
+    run = SIMPLE if _simple is None else _simple
+    dat = _as_matrix(dat, resident) if _simple is None else dat               # uploaded once for the whole grid
+    n = _n_total(np.shape(dat)[1], comm)
     Ms = sorted(set(np.atleast_1d(M0).astype(int).tolist()) | {1})            # :136-137
     Ks = sorted(np.atleast_1d(K0).astype(int).tolist())
-    BICs = {m: {k: math.nan for k in Ks} for m in Ms}
-    best, mBIC, mK, mM, init_imp = {}, math.inf, None, None, None
-    for M1 in Ms:                                                             # :145
-        prev = math.inf
+    state = dict(p_min=p_min)
+
+    def k_loop(M1, init_imp):
+        """The inner loop of :147-183 for one M: BIC row, and the first minimum (crit, K, result) of the row."""
+        row, bestM, prev = {}, (math.inf, None, None), math.inf
         for K1 in Ks:
-            result = SIMPLE(dat, K1, M1, iter=iter, est_lam=est_lam, impt_it=impt_it, penl=penl, init_imp=init_imp,
-                            sigma0=sigma0, pi_alpha=pi_alpha, beta=beta, verbose=verbose, max_lambda=max_lambda,
-                            lambda_=lambda_, sigma=sigma, mu=mu, est_z=est_z, clus=clus, p_min=p_min, cutoff=cutoff, K=K,
-                            min_gene=min_gene, num_mc=num_mc, fix_num=fix_num, mcmc=mcmc, burnin=burnin, seed=seed,
-                            comm=comm, consensus=consensus, resident=resident)
-            if p_min is None:
-                p_min = result["p_min"]                                       # :156
+            result = run(dat, K1, M1, iter=iter, est_lam=est_lam, impt_it=impt_it, penl=penl, init_imp=init_imp,
+                         sigma0=sigma0, pi_alpha=pi_alpha, beta=beta, verbose=verbose, max_lambda=max_lambda,
+                         lambda_=lambda_, sigma=sigma, mu=mu, est_z=est_z, clus=clus, p_min=state["p_min"], cutoff=cutoff,
+                         K=K, min_gene=min_gene, num_mc=num_mc, fix_num=fix_num, mcmc=mcmc, burnin=burnin, seed=seed,
+                         comm=comm, consensus=consensus, resident=resident)
+            if state["p_min"] is None:
+                state["p_min"] = result["p_min"]                              # :156
             crit = result["BIC0"] if n < 1000 else result["BIC"]              # :158-182
-            if mBIC > crit:
-                mBIC, mK, mM = crit, K1, M1
-                best[M1] = result
-            BICs[M1][K1] = crit
+            if bestM[0] > crit:
+                bestM = (crit, K1, result)
+            row[K1] = crit
             if (crit - prev) > -abs(crit) * rel:
                 break
             prev = crit
-        if M1 == 1:
-            init_imp = best[1]["impt"]                                        # :185
-    return dict(BICs=BICs, mK=mK, mM=mM, result=best[mM])
+        return row, bestM
+
+    BICs = {m: {k: math.nan for k in Ks} for m in Ms}
+    rows, bests = {}, {}
+    rows[1], bests[1] = k_loop(1, None)                                       # every replica: init_imp for M > 1 (:185)
+    init_imp = bests[1][2]["impt"]
+    rest = [m for m in Ms if m != 1]
+    mine = rest if replicas is None else rest[replicas.rank::replicas.world_size]
+    for M1 in mine:                                                           # :145
+        rows[M1], bests[M1] = k_loop(M1, init_imp)
+    summary = {m: (rows[m], bests[m][0], bests[m][1]) for m in rows}
+    if replicas is not None:
+        merged = {}
+        for part in replicas.allgather(summary):
+            merged.update(part)
+        summary = merged
+    mBIC, mK, mM = math.inf, None, None
+    for m in Ms:                                                              # first minimum in (M, K) order == :159-176
+        BICs[m].update(summary[m][0])
+        if mBIC > summary[m][1]:
+            mBIC, mK, mM = summary[m][1], summary[m][2], m
+    return dict(BICs=BICs, mK=mK, mM=mM, result=bests[mM][2] if mM in bests else None)

@@ -124,3 +124,52 @@ def test_driver_host_logic_sharded():
     assert np.array_equal(hq_a, _hq_genes(dat, 0.1, 0.5, 12, False, None))
     assert np.array_equal(hq_b, _hq_genes(dat, 0.1, 0.99, 12, False, None)) and len(hq_b) == 12
     assert tot == 31 and mx == 2.0 and nt == 31
+
+
+def _fake_simple(dat, K1, M1, **kw):
+    """Stand-in for SIMPLE(): a deterministic BIC surface with a unique minimum at (M, K) = (3, 6)."""
+    bic = 1000.0 + 40.0 * (M1 - 3) ** 2 + 9.0 * (K1 - 6) ** 2 - (5.0 if kw.get("init_imp") is not None else 0.0)
+    return dict(BIC=bic, BIC0=bic + 1.0, impt=("impt", M1, K1), p_min=0.37, tag=(M1, K1))
+
+
+def _km_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simples_b200 import Replicas
+    from simples_b200.driver import selectKM
+    dat = np.zeros((5, 2000))                                   # n >= 1000 -> BIC (not BIC0) is the criterion
+    out = selectKM(dat, K0=[2, 4, 6, 8, 10], M0=[1, 2, 3, 4, 5], p_min=None, replicas=Replicas(), _simple=_fake_simple)
+    q.put((rank, out["BICs"], out["mK"], out["mM"], None if out["result"] is None else out["result"]["tag"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_select_km_replicas_equal_sequential():
+    """selectKM over replicas (values of M dealt to the ranks) == the sequential loop of R/select_KM.R:145-186."""
+    import torch.multiprocessing as mp
+    from simples_b200.driver import selectKM
+    seq = selectKM(np.zeros((5, 2000)), K0=[2, 4, 6, 8, 10], M0=[1, 2, 3, 4, 5], p_min=None, _simple=_fake_simple)
+    assert (seq["mM"], seq["mK"]) == (3, 6) and seq["result"]["tag"] == (3, 6)
+    assert np.isnan(seq["BICs"][3][10]) and not np.isnan(seq["BICs"][3][8])     # early stop along K (:169,180)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 13
+    ps = [ctx.Process(target=_km_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in ps:
+        p_.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p_ in ps:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    owners = 0
+    for rank, bics, mK, mM, tag in got:
+        assert (mM, mK) == (3, 6)
+        for m in seq["BICs"]:
+            for k in seq["BICs"][m]:
+                a, b_ = bics[m][k], seq["BICs"][m][k]
+                assert (np.isnan(a) and np.isnan(b_)) or a == b_
+        owners += tag == (3, 6)
+    assert owners == 1                                           # M = 3 was dealt to exactly one rank

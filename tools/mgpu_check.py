@@ -52,7 +52,18 @@ for clus in (sim["Z"], None):
             e = rel(pr[k], sl); msgs.append(f"SIMPLE[{tag}].{k}[shard0]={e:.1e}"); ok &= e <= 1e-6
         ok &= bool(np.array_equal(pr["initclus"], fr["initclus"][a:b]))
         e = abs(pr["BIC"] - fr["BIC"]) / abs(fr["BIC"]); msgs.append(f"SIMPLE[{tag}].BIC={e:.1e}"); ok &= e <= 1e-9
+# ---- selectKM with the grid dealt over replicas (every rank holds the whole data) vs the sequential loop ----
+skw = dict(K0=[2, 3, 4], M0=[1, 2, 3], iter=2, min_gene=150, mcmc=0, seed=4, clus=None, K=5, resident=True)
+rep = sb.selectKM(sim["Y2"], replicas=sb.Replicas(), **skw)
 if rank == 0:
-    print(json.dumps({"world": world, "ok": bool(ok), "driver": msgs[-20:]}), flush=True)
+    seq = sb.selectKM(sim["Y2"], **skw)
+    same = (rep["mK"], rep["mM"]) == (seq["mK"], seq["mM"])
+    for m in seq["BICs"]:
+        for k in seq["BICs"][m]:
+            a, b = rep["BICs"][m][k], seq["BICs"][m][k]
+            same &= bool((np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-9 * abs(b))
+    msgs.append(f"selectKM replicas == sequential: {same} (mM={seq['mM']}, mK={seq['mK']})"); ok &= same
+if rank == 0:
+    print(json.dumps({"world": world, "ok": bool(ok), "driver": msgs[-21:]}), flush=True)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
