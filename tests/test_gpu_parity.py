@@ -608,3 +608,27 @@ def test_golden_stages(sb):
     for k in ("loglik_tot", "beta", "sigma", "mu", "pi", "lambda", "z", "impt", "Yimp0", "pg"):
         assert rel(run[k], g["run_" + k]) <= 1e-5, k
     assert abs(run["BIC"] - float(g["run_BIC"])) <= 1e-6 * abs(float(g["run_BIC"]))
+
+
+def test_driver_properties_at_scale(sb):
+    """Size-independent properties of a whole SIMPLE() run at 20k cells x 600 genes (the oracle driver would take
+    minutes here): recovered cell types, observed entries untouched, finite outputs, BIC consistent with the last
+    log-likelihood, and the device-resident run identical to the host-buffer run."""
+    from simples_b200 import synth
+    gp = synth.gene_params(600, 5, 5, seed=2)
+    Y2, Z = synth.simulate_shard(gp, 20000, shard=0, seed=2)
+    kw = dict(K0=5, M0=5, iter=4, clus=None, K=8, p_min=0.4, min_gene=300, mcmc=4, burnin=1, seed=11, consensus=False)
+    res = sb.SIMPLE(Y2, **kw)
+    G, n = Y2.shape
+    assert O.adjusted_rand_index(np.argmax(res["z"], axis=1), Z) >= 0.85
+    obs = Y2 > 0.1
+    # observed entries come back through the centring round trip (y - mean) + mean, as in the reference: 1 ulp
+    assert np.allclose(res["impt"][obs], Y2[obs], rtol=1e-14, atol=1e-14)
+    assert np.isfinite(res["impt"]).all() and np.isfinite(res["Yimp0"]).all()
+    assert (res["impt_var"][obs] == 0).all() and (res["impt_var"] >= 0).all()
+    bic, bic0 = O.bic_ref(res["loglik_tot"][-1], n, G, 5, 5)
+    assert abs(res["BIC"] - bic) <= 1e-9 * abs(bic) and abs(res["BIC0"] - bic0) <= 1e-9 * abs(bic0)
+    assert abs(res["pi"].sum() - 1) <= 1e-12 and np.allclose(res["z"].sum(axis=1), 1.0, atol=1e-10)
+    assert (res["sigma"] >= 1e-4).all() and (res["sigma"] <= 9).all() and res["consensus_cluster"] is None
+    dev = sb.SIMPLE(Y2, resident=True, **kw)
+    assert np.array_equal(res["beta"], dev["beta"]) and np.array_equal(res["impt"], dev["impt"].cpu().numpy())
