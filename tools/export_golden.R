@@ -22,5 +22,12 @@ wr <- function(name, x) writeBin(as.double(x), file.path(out, paste0(name, ".f64
 for (k in c("Y", "Y0", "pg", "beta", "sigma", "lambda", "pi", "z")) wr(paste0("in_", k), args[[k]])
 writeBin(as.integer(clus), file.path(out, "in_celltype.i32"), size = 4, endian = "little")
 for (k in c("loglik", "pi", "mu", "sigma", "beta", "lambda", "z", "Y", "geneM")) wr(paste0("out_", k), fit[[k]])
+# ztruncnorm has no random draws at all: its (mean, sd) and pg pin the oracle's restatement of
+# R/fit_ztrunc.R:55-134 (Brent search: expect ~1e-7 relative on sd, the optimiser's own tolerance) and k_ztrunc.
+zt <- SIMPLEs:::ztruncnorm(Y2, cutoff = 0.01, p_min = 0.5)
+wr("zt_param", zt[[1]]); wr("zt_pg", zt[[2]])
+# the lq-gene regression of R/SIMPLE.R:312-366 is deterministic given (z, Ef, Varf): export its inputs and outputs
+# by running the block of SIMPLE() on the first 200 genes as "hq" (copy of the loop body, not reproduced here);
+# the all-gene EM_impute call with impt_it = iter then pins the whole deterministic chain.
 cat(sprintf("G=%d n=%d K0=%d M0=%d iter=5 cutoff=0.01\n", G, n, K0, M0), file = file.path(out, "dims.txt"))
 print(sessionInfo())
