@@ -632,3 +632,16 @@ def test_driver_properties_at_scale(sb):
     assert (res["sigma"] >= 1e-4).all() and (res["sigma"] <= 9).all() and res["consensus_cluster"] is None
     dev = sb.SIMPLE(Y2, resident=True, **kw)
     assert np.array_equal(res["beta"], dev["beta"]) and np.array_equal(res["impt"], dev["impt"].cpu().numpy())
+
+
+@pytest.mark.parametrize("K0,M0", [(1, 1), (3, 1), (2, 5)])
+def test_do_impute_small_models(sb, K0, M0):
+    """do_impute with M0 = 1 (the reference still calls rmultinom there, Q12) and K0 = 1."""
+    st = make_case(150, 90, 2, max(M0, 1), K0, M0, seed=40 + K0 + M0)
+    em = O.em_impute_fast(*em_args(st, M0, K0, 2), celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=2)
+    args = (st["Y0"], em["Y"], em["beta"], em["lambda"], em["sigma"], em["mu"], em["pi"], em["geneM"], em["geneSd"],
+            st["celltype"])
+    kw = dict(mcmc=3, burnin=1, pg=st["pg"], cutoff=0.1, seed=8)
+    ref, got = O.do_impute_ref(*args, **kw), sb.do_impute(*args, **kw)
+    assert rel(got["impt"], ref["impt"]) <= 1e-6 and abs(got["loglik"] - ref["loglik"]) <= 1e-8 * abs(ref["loglik"])
+    assert rel(got["EF"], ref["EF"]) <= 1e-7 and rel(got["consensus_cluster"], ref["consensus_cluster"]) <= 1e-8
