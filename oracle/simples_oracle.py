@@ -2,7 +2,13 @@
 
 Follows, line by line, ``R/EM_impute.R:75-339`` and ``R/do_impute.R:29-160`` of
 JunLiuLab/SIMPLEs (paths relative to /root/reference), including the quirks
-listed in SURVEY.md section 8(c).  PARITY UNPINNED (see ``oracle/__init__``).
+listed in SURVEY.md section 8(c), and -- for the rows of SURVEY.md 8(f) -- the
+stages around them: ``R/fit_ztrunc.R:2-134`` (ztruncnorm; optim's Brent is
+restated from the published Netlib fmin), ``R/SIMPLE.R:15-73`` /
+``R/SIMPLE_B.R:23-114`` (init_impute / init_impute_bulk), ``R/SIMPLE.R:258-266``
+(clustering start), ``R/SIMPLE.R:305-411`` (lq-gene fit) and the drivers
+``R/SIMPLE.R:200-455``, ``R/SIMPLE_B.R:229-455``, ``R/select_KM.R:126-189``.
+PARITY UNPINNED (see ``oracle/__init__``).
 
 Two M-step formulations are provided and cross-checked by the tests:
 
