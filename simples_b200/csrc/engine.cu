@@ -131,6 +131,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     s.n_alloc = c->n_alloc;
     CKR(c->dalloc(&s.P, size_t(c->NS_max) * na * d.NQP));
     CKR(c->dalloc(&s.S2, size_t(c->NS_max) * na));
+    CKR(c->dalloc(&s.proj_part, size_t(NUM_SMS_B200) * 128 * (d.NQP + 1)));
     CKR(c->dalloc(&s.V, na * d.VS));
     CKR(c->dalloc(&s.zsum, na));
     CKR(c->dalloc(&s.Fh, na * d.FS));
@@ -228,9 +229,9 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
     DevState& s = c->s;
     const Dims& d = s.d;
     for (int sc = 0; sc < d.NS; ++sc) {
-        P p(c, KC_PROJ);
+        P p(c, KC_PROJ, proj_launches(d.n, d.ldG, s.proj_part != nullptr));
         ProjArgs pa{s.Y, s.Q + size_t(sc) * d.ldG * d.QS, s.isg + size_t(sc) * d.ldG, s.P + size_t(sc) * d.n * d.NQP,
-                    s.S2 + size_t(sc) * d.n, d.n, d.ldG, d.NQP, d.QS};
+                    s.S2 + size_t(sc) * d.n, d.n, d.ldG, d.NQP, d.QS, s.proj_part};
         launch_proj(pa, c->tmapY, c->stream);
     }
     if (c->cluster_pending) {

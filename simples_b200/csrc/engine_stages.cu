@@ -301,7 +301,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
     CKR(c->dalloc(&P, size_t(na) * NQP));
     CKR(c->dalloc(&S2, size_t(na)));
     {
-        ProjArgs pa{Y, A, isg, P, S2, n, ldG, NQP, QS};
+        ProjArgs pa{Y, A, isg, P, S2, n, ldG, NQP, QS, nullptr};
         launch_proj(pa, tmapY, st);
     }
     CK(cudaGetLastError());

@@ -25,9 +25,26 @@ __host__ __device__ constexpr size_t stage_bytes(int QS) {
 }
 static_assert((2 * YBOX * 8) % 1024 == 0, "box alignment");
 
+// P / S2 rows of the gene-split tail tiles = fixed-order sum of the S partial rows
+__global__ void k_proj_reduce(ProjArgs a, int cell_begin, int rows, int S) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = a.NQP + 1;
+    if (e >= rows * W) return;
+    const int r = e / W, c = e - r * W;
+    const int cell = cell_begin + r;
+    if (cell >= a.n) return;
+    double s = 0.0;
+    for (int p = 0; p < S; ++p) s += a.part[(size_t(p) * rows + r) * W + c];
+    if (c < a.NQP) a.P[size_t(cell) * a.NQP + c] = s;
+    else a.S2[cell] = s;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(THREADS, 1) k_proj(const __grid_constant__ CUtensorMap tmapY, ProjArgs a, int stages,
-                                                     int ntiles) {
+                                                     int tile_begin, int nitems, int S) {
+    // Work item w = (tile, part): tile = tile_begin + w / S over the gene-chunk range part of S.  S = 1 writes P / S2
+    // directly; S > 1 (the last, partial round of tiles, split along the genes so that every SM has work) writes
+    // partial sums to a.part, summed in a fixed order by k_proj_reduce.
     constexpr int QS = NT * 8 + 4;
     constexpr size_t SB = (stage_bytes(QS) + 1023) / 1024 * 1024;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -54,9 +71,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+                const int tile = tile_begin + w / S, part = w - (w / S) * S;
                 const int cell0 = tile * TC;
-                for (int c = 0; c < nchunks; ++c) {
+                const int cb = nchunks * part / S, ce = nchunks * (part + 1) / S;
+                for (int c = cb; c < ce; ++c) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* sp = stage0 + stage * SB;
                     double* Ys = reinterpret_cast<double*>(sp);
@@ -82,8 +101,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(const __grid_constant__ CUt
         for (int kk = 0; kk < 4; ++kk) off[kk] = swz16(r0, 4 * kk + t);
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+            const int tile = tile_begin + w / S, part = w - (w / S) * S;
             const int cell0 = tile * TC;
+            const int cb = nchunks * part / S, ce = nchunks * (part + 1) / S;
             double acc[2][NT][2];
             double s2[2] = {0.0, 0.0};
 #pragma unroll
@@ -91,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(const __grid_constant__ CUt
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = cb; c < ce; ++c) {
                 mbar_wait(&full[stage], phase);
                 const unsigned char* sp = stage0 + stage * SB;
                 const double* Ys = reinterpret_cast<const double*>(sp);
@@ -123,7 +144,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(const __grid_constant__ CUt
                 double s = s2[mt];
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (cell < a.n) {
+                if (S > 1) {       // partial row: [part][(tile - tile_begin) * TC + row][NQP + 1]
+                    const size_t prows = size_t(nitems / S) * TC;
+                    double* prow = a.part + (size_t(part) * prows + size_t(tile - tile_begin) * TC + (r0 + mt * 8)) * (a.NQP + 1);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        prow[nt * 8 + 2 * t] = acc[mt][nt][0];
+                        prow[nt * 8 + 2 * t + 1] = acc[mt][nt][1];
+                    }
+                    if (t == 0) prow[a.NQP] = s;
+                } else if (cell < a.n) {
                     double* prow = a.P + size_t(cell) * a.NQP;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
@@ -148,10 +178,34 @@ void launch_nt(const ProjArgs& a, const CUtensorMap& tm, cudaStream_t st) {
         attr_set = true;
     }
     const int ntiles = (a.n + TC - 1) / TC;
-    const int grid = ntiles < NUM_SMS_B200 ? ntiles : NUM_SMS_B200;
-    k_proj<NT><<<grid, THREADS, smem, st>>>(tm, a, stages, ntiles);
+    const int nchunks = a.ldG / GC;
+    // Full rounds of NUM_SMS tiles run as they are; a last partial round of `rem` tiles is split along the genes into
+    // S parts per tile (rem * S <= NUM_SMS items) so that it costs 1/S of a round instead of a whole one.
+    const int head = (ntiles / NUM_SMS_B200) * NUM_SMS_B200, rem = ntiles - head;
+    int S = (rem > 0 && a.part) ? NUM_SMS_B200 / rem : 1;
+    if (S > 8) S = 8;
+    while (S > 1 && nchunks / S < 4) --S;
+    if (S <= 1) {
+        const int grid = ntiles < NUM_SMS_B200 ? ntiles : NUM_SMS_B200;
+        k_proj<NT><<<grid, THREADS, smem, st>>>(tm, a, stages, 0, ntiles, 1);
+        return;
+    }
+    if (head > 0) k_proj<NT><<<NUM_SMS_B200, THREADS, smem, st>>>(tm, a, stages, 0, head, 1);
+    k_proj<NT><<<rem * S, THREADS, smem, st>>>(tm, a, stages, head, rem * S, S);
+    const int rows = rem * TC;
+    k_proj_reduce<<<(rows * (a.NQP + 1) + 255) / 256, 256, 0, st>>>(a, head * TC, rows, S);
 }
 }  // namespace
+
+// kernels enqueued by one launch_proj (the tail split adds a second k_proj and the reduction)
+int proj_launches(int n, int ldG, bool have_scratch) {
+    const int ntiles = (n + TC - 1) / TC, nchunks = ldG / GC;
+    const int head = (ntiles / NUM_SMS_B200) * NUM_SMS_B200, rem = ntiles - head;
+    int S = (rem > 0 && have_scratch) ? NUM_SMS_B200 / rem : 1;
+    if (S > 8) S = 8;
+    while (S > 1 && nchunks / S < 4) --S;
+    return S <= 1 ? 1 : (head > 0 ? 3 : 2);
+}
 
 void launch_proj(const ProjArgs& a, const CUtensorMap& tmapY, cudaStream_t st) {
     switch (a.NQP / 8) {

@@ -66,6 +66,7 @@ struct DevState {
     uint32_t* mask;
     int32_t* celltype0;
     double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs, *P, *S2, *V, *zsum, *Fh, *W;
+    double* proj_part;   // k_proj tail-split scratch
     int n_alloc;
     int32_t* im;
     ClusterConsts cc;
@@ -91,8 +92,10 @@ struct DevState {
 struct ProjArgs {
     const double* Y; const double* Q; const double* isg; double* P; double* S2;
     int n, ldG, NQP, QS;
+    double* part;   // scratch [NUM_SMS * 128][NQP + 1] for the gene-split tail tiles (nullptr: no split)
 };
 void launch_proj(const ProjArgs& a, const CUtensorMap& tmapY, cudaStream_t st);   // tmapY: box {16 genes, 128 cells}
+int proj_launches(int n, int ldG, bool have_scratch);
 
 struct CellArgs {
     Dims d;
