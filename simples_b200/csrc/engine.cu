@@ -408,7 +408,7 @@ int em_iteration(simples_ctx* c) {
 
     // ---- M-step ----
     {
-        P p(c, KC_GENE, 3);
+        P p(c, KC_GENE, 4);
         MstepArgs ma{};
         ma.d = d;
         ma.stats = stats;
@@ -423,6 +423,7 @@ int em_iteration(simples_ctx* c) {
         ma.priorB = s.priorB;
         ma.part_gene = s.part_gene;
         ma.ncta_gene = s.ncta_gene;
+        ma.part_mu = s.part_mu;
         ma.penl = c->penl;
         ma.sigma0 = c->sigma0;
         ma.pi_alpha = c->pi_alpha;
@@ -540,6 +541,7 @@ int simples_em_create(const simples_em_args* a, simples_ctx** out) {
     CKR(c->dalloc(&s.part_ss, size_t(s.nsplit_ss) * M0 * (K0 * K0 + K0)));
     s.ncta_gene = mstep_gene_ctas(d.G);
     CKR(c->dalloc(&s.part_gene, size_t(s.ncta_gene)));
+    CKR(c->dalloc(&s.part_mu, size_t(M0) * mu_gene_splits(ldG) * (K0 * K0 + K0)));
     CKR(c->dalloc(&s.priorB, 2));
     c->iter_cap = std::max(a->iter, 1);
     CKR(c->dalloc(&s.loglik, size_t(c->iter_cap)));

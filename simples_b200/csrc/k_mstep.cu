@@ -458,22 +458,22 @@ __global__ void __launch_bounds__(1024) k_lmp(MstepArgs a) {
 
 constexpr int MG = 256;
 
-__global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
+// mu update, phase 1: partial sums of C_m = B' diag(1/s) B and rhs_m = B' (v / s) over the gene tiles gs, gs + GS, ...
+// (s_g = nz_m + sigma_g / sigma0, v = Y z_m).  grid (M0, GS); partials are summed in a fixed order by k_mu_fin.
+__global__ void __launch_bounds__(256) k_mu_acc(MstepArgs a, int GS) {
     extern __shared__ __align__(16) double sm[];
     const Dims& d = a.d;
     const int K0 = d.K0, M0 = d.M0, ldG = d.ldG;
     const StatView sv = stat_view(a.stats, d, a.general);
-    const int m = blockIdx.x;
+    const int m = blockIdx.x, gs = blockIdx.y;
     const int ucol = a.general ? K0 * M0 + m : K0 + m;
     const double nzm = sv.nz[m];
     double* sB = sm;               // [MG][K0]
     double* sw = sB + MG * K0;     // 1/s
     double* sv_ = sw + MG;         // v/s
-    double* sCm = sv_ + MG;        // [K0][K0]
-    double* srhs = sCm + K0 * K0;  // [K0]
     const int NE = K0 * K0 + K0;
     double acc[5] = {0, 0, 0, 0, 0};
-    for (int g0 = 0; g0 < ldG; g0 += MG) {
+    for (int g0 = gs * MG; g0 < ldG; g0 += GS * MG) {
         __syncthreads();
         for (int idx = threadIdx.x; idx < MG * K0; idx += blockDim.x)
             sB[idx] = (g0 + idx / K0 < ldG) ? a.beta[size_t(g0) * K0 + idx] : 0.0;      // rows past ldG contribute 0
@@ -500,16 +500,31 @@ __global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
             acc[q] = s;
         }
     }
-    __syncthreads();
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
         const int e = threadIdx.x + q * 256;
-        if (e >= NE) continue;
+        if (e < NE) a.part_mu[(size_t(m) * GS + gs) * NE + e] = acc[q];
+    }
+}
+
+// phase 2: per cluster the K0 x K0 solve (:311) and mu_gm = (v_g - b_g' x) / s_g for every gene (:313-315)
+__global__ void __launch_bounds__(256) k_mu_fin(MstepArgs a, int GS) {
+    __shared__ double sCm[MAXK * MAXK], srhs[MAXK];
+    const Dims& d = a.d;
+    const int K0 = d.K0, M0 = d.M0;
+    const StatView sv = stat_view(a.stats, d, a.general);
+    const int m = blockIdx.x;
+    const int ucol = a.general ? K0 * M0 + m : K0 + m;
+    const double nzm = sv.nz[m];
+    const int NE = K0 * K0 + K0;
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+        double s = 0.0;
+        for (int gs = 0; gs < GS; ++gs) s += a.part_mu[(size_t(m) * GS + gs) * NE + e];
         if (e < K0 * K0) {
             const int j = e / K0, k = e - j * K0;
-            sCm[e] = acc[q] + ((j == k) ? a.sigma0 / a.lam[m * K0 + k] : 0.0);   // :311
+            sCm[e] = s + ((j == k) ? a.sigma0 / a.lam[m * K0 + k] : 0.0);   // :311
         } else {
-            srhs[e - K0 * K0] = acc[q];
+            srhs[e - K0 * K0] = s;
         }
     }
     __syncthreads();
@@ -518,7 +533,7 @@ __global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
         warp_chol_solve(sCm, srhs, K0, threadIdx.x);
     }
     __syncthreads();
-    for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g < d.G; g += gridDim.y * blockDim.x) {
         const double s = nzm + a.sigma[size_t(g) * M0 + m] / a.sigma0;
         double t = 0.0;
         for (int k = 0; k < K0; ++k) t += a.beta[size_t(g) * K0 + k] * srhs[k];
@@ -529,6 +544,7 @@ __global__ void __launch_bounds__(256) k_mu(MstepArgs a) {
 }  // namespace
 
 int mstep_gene_ctas(int G) { return (G + GW - 1) / GW; }
+int mu_gene_splits(int ldG) { const int t = (ldG + MG - 1) / MG; return t < 8 ? t : 8; }
 
 void lasso_debug_fetch(int out[4], bool reset) {
     cudaMemcpyFromSymbol(out, g_lasso_dbg, sizeof(int) * 4);
@@ -553,13 +569,15 @@ void launch_mstep(const MstepArgs& a, cudaStream_t st) {
     }
     k_lmp<<<1, 1024, 0, st>>>(a);
     {
-        const size_t smem = sizeof(double) * (size_t(MG) * K0 + 2 * MG + K0 * K0 + K0);
+        const int GS = mu_gene_splits(a.d.ldG);
+        const size_t smem = sizeof(double) * (size_t(MG) * K0 + 2 * MG);
         static size_t attr2 = 0;
         if (smem > 48 * 1024 && smem > attr2) {
-            cudaFuncSetAttribute(k_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            cudaFuncSetAttribute(k_mu_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             attr2 = smem;
         }
-        k_mu<<<M0, 256, smem, st>>>(a);
+        k_mu_acc<<<dim3(M0, GS), 256, smem, st>>>(a, GS);
+        k_mu_fin<<<dim3(M0, (a.d.G + 2047) / 2048), 256, 0, st>>>(a, GS);
     }
 }
 

@@ -86,6 +86,7 @@ struct DevState {
     double *priorB;    // [2]: current, previous
     double *part_gene; // per-CTA priorB partials
     int ncta_gene;
+    double *part_mu;   // k_mu_acc partial sums
 };
 
 // ---- launchers (each in its own .cu) ------------------------------------------------------------
@@ -163,11 +164,13 @@ struct MstepArgs {
     double *loglik_slot;      // loglik[it-1]
     double *priorB;           // [0]=current (written), [1]=previous (read, then updated)
     double *part_gene; int ncta_gene;
+    double *part_mu;          // [M0][mu_gene_splits][K0*K0 + K0] partial sums of the mu update
     double penl, sigma0, pi_alpha;
     int do_lambda, compat_priorb_prev;
 };
 void launch_mstep(const MstepArgs& a, cudaStream_t st);
 int mstep_gene_ctas(int G);
+int mu_gene_splits(int ldG);
 void lasso_debug_fetch(int out[4], bool reset);   // {solves, total CD sweeps, max sweeps, capped} since the last reset
 
 // low-quality-gene fit (R/SIMPLE.R:305-411)
