@@ -36,7 +36,7 @@ __all__ = [
     "PI_REF", "COMPAT_STALE_DT", "COMPAT_PI", "COMPAT_MU_DIV_N",
     "COMPAT_PRIORB_PREV", "COMPAT_DEFAULT",
     "philox4x32", "cell_uniforms", "entry_uniforms", "trunc_z", "sym_sqrt",
-    "lasso_solve", "lasso_solve_batch", "lambda_solve_k", "lambda_step",
+    "lasso_solve", "lasso_solve_batch", "lasso_glmnet_compat", "glmnet_band", "lambda_solve_k", "lambda_step",
     "cluster_terms", "epass", "factor_means", "sample_sweep",
     "local_stats", "stats_pack", "stats_unpack", "mstep_from_stats",
     "em_impute_ref", "em_impute_fast", "do_impute_ref",
@@ -236,6 +236,123 @@ def lasso_solve(A, rhs, kappa):
     kap = np.asarray(kappa, dtype=np.float64)
     kap = kap[None] if kap.ndim == 0 else kap[None, :]
     return lasso_solve_batch(np.asarray(A), np.asarray(rhs)[None, :], kap)[0]
+
+
+# ----------------------------------------------------------------------------
+# glmnet-compatible stopping (TEST ONLY): what the reference's own lasso call returns
+# ----------------------------------------------------------------------------
+LASSO_MODE = "exact"            # "exact" | "glmnet": which solver mstep_from_stats / lq_regress_fast use
+GLMNET_THRESH = 1e-7            # glmnet's default `thresh` (R/EM_impute.R:257-259 passes none)
+
+
+def lasso_glmnet_compat(A, rhs, kappa, N, sum_y, sum_y2, thresh=GLMNET_THRESH, maxit=100000, info=None):
+    """The lasso of R/EM_impute.R:257-259 as glmnet itself solves it, from the Gram form.
+
+    glmnet (>= 2.0-16, ``family="gaussian"``, ``standardize=F``, ``intercept=F``, one user
+    ``lambda``, fewer than 500 variables => covariance updating) is not in /root/reference;
+    this restates its published algorithm (Friedman, Hastie, Tibshirani 2010, J. Stat.
+    Softw. 33(1) section 2.2, and the ``elnet1`` loop of the package's Fortran source):
+
+    * observation weights ``1/N``; the response is scaled by its *population* standard
+      deviation ``ys`` (also without an intercept) and the user ``lambda`` divided by it;
+    * cyclic coordinate descent from 0 on the covariance form ``g_k = <x_k, r>``,
+      ``xv_k = <x_k, x_k>``; strong-rule screening ``|g_k| > 2 lambda`` with a KKT pass over
+      the excluded coordinates; after every full pass that changed something, passes over
+      the active set only until converged;
+    * converged when the largest ``xv_k * delta_k^2`` of a pass is below ``thresh``.
+
+    ``A`` = X'X (K x K), ``rhs`` = X'y, ``kappa`` = N * lambda_user (the penalty on the
+    0.5 * RSS scale, as in ``lasso_solve``); ``N, sum_y, sum_y2`` describe the response.
+    Returns the coefficients on the original scale.  ``info`` (dict) receives ``passes``.
+    """
+    A = np.asarray(A, dtype=np.float64)
+    K = A.shape[0]
+    ys = math.sqrt(max(sum_y2 / N - (sum_y / N) ** 2, 0.0))
+    if not ys > 0.0:
+        return np.zeros(K)
+    C = A / N
+    xv = np.diag(C).copy()
+    g = np.asarray(rhs, dtype=np.float64) / N / ys
+    alm = float(kappa) / N / ys
+    a = np.zeros(K)
+    ix = np.abs(g) > 2.0 * alm                       # strong rule with alm0 = 0 (single user lambda)
+    active = np.zeros(K, dtype=bool)
+    nlp = 0
+
+    def update(k, cols):
+        ak = a[k]
+        u = g[k] + ak * xv[k]
+        v = abs(u) - alm
+        nk = math.copysign(v, u) / xv[k] if v > 0.0 else 0.0
+        if nk == ak:
+            return 0.0
+        a[k] = nk
+        d = nk - ak
+        g[cols] -= C[cols, k] * d
+        return xv[k] * d * d
+
+    while True:
+        # full pass over the screened set
+        nlp += 1
+        dlx = 0.0
+        for k in range(K):
+            if not ix[k]:
+                continue
+            before = a[k]
+            dk = update(k, ix)
+            if a[k] != before:
+                active[k] = True
+            dlx = max(dlx, dk)
+        if dlx < thresh:
+            # KKT pass over the excluded coordinates (their gradient was not maintained)
+            excl = ~ix
+            if excl.any():
+                gex = np.asarray(rhs, dtype=np.float64)[excl] / N / ys - C[np.ix_(excl, np.ones(K, bool))] @ a
+                viol = np.abs(gex) > alm
+                if viol.any():
+                    idx = np.flatnonzero(excl)[viol]
+                    ix[idx] = True
+                    g[idx] = gex[viol]
+                    continue
+            break
+        if nlp > maxit:
+            raise RuntimeError("glmnet-compat lasso: maxit reached")
+        # passes over the active set only; gradients of the other screened coordinates are refreshed afterwards
+        da = a.copy()
+        while True:
+            nlp += 1
+            dlx = 0.0
+            for k in np.flatnonzero(active):
+                dlx = max(dlx, update(k, active))
+            if dlx < thresh:
+                break
+            if nlp > maxit:
+                raise RuntimeError("glmnet-compat lasso: maxit reached")
+        da = a - da
+        rest = ix & ~active
+        if rest.any():
+            g[rest] -= C[np.ix_(rest, active)] @ da[active]
+    if info is not None:
+        info["passes"] = nlp
+    return a * ys
+
+
+def glmnet_band(A, kappa, N, sum_y, sum_y2, beta_compat, thresh=GLMNET_THRESH):
+    """Bound on |beta_exact - beta_compat| implied by glmnet's stopping rule (same support).
+
+    At the stop every coordinate changed by less than sqrt(thresh / xv_k) (scaled units) in the last pass, so
+    the stationarity residual on the support S is at most R = max_k sum_j |C_kj| sqrt(thresh / xv_j), and the
+    exact minimiser on S differs by at most ||C_SS^-1||_inf * R (times ys on the original scale).
+    """
+    A = np.asarray(A, dtype=np.float64)
+    ys = math.sqrt(max(sum_y2 / N - (sum_y / N) ** 2, 0.0))
+    S = np.asarray(beta_compat) != 0.0
+    if not S.any() or not ys > 0.0:
+        return 0.0
+    C = A[np.ix_(S, S)] / N
+    step = np.sqrt(thresh / np.diag(C))
+    R = float(np.max(np.abs(C) @ step))
+    return ys * float(np.max(np.sum(np.abs(np.linalg.inv(C)), axis=1))) * R
 
 
 # ----------------------------------------------------------------------------
@@ -489,7 +606,11 @@ def mstep_from_stats(st, n, Ms, beta, sigma, lam, mu, M0, K0, it, penl, max_lamb
         sumY2 = d2 / sg0
         var = (sumY2 - sumY * sumY / N) / (N - 1)                            # var(Y_aug)  (Q7)
         kappa = penl * var                                                   # :258
-        nb = lasso_solve_batch(A, bt, kappa * sg0)
+        if LASSO_MODE == "glmnet":      # what glmnet's own stopping rule returns (test only)
+            nb = np.stack([lasso_glmnet_compat(A / sg0[g], bt[g] / sg0[g], kappa[g], N, sumY[g], sumY2[g])
+                           for g in range(G)])
+        else:
+            nb = lasso_solve_batch(A, bt, kappa * sg0)
         quad = np.einsum("gj,jk,gk->g", nb, A, nb)
         sg = (d2 - 2 * np.sum(nb * bt, axis=1) + quad + 1) / (n + 3)         # :263-267
     else:
@@ -501,7 +622,10 @@ def mstep_from_stats(st, n, Ms, beta, sigma, lam, mu, M0, K0, it, penl, max_lamb
         sumY2 = np.sum(D2 / sigma, axis=1)
         var = (sumY2 - sumY * sumY / N) / (N - 1)
         kappa = penl * var
-        nb = lasso_solve_batch(A, rhs, kappa)
+        if LASSO_MODE == "glmnet":
+            nb = np.stack([lasso_glmnet_compat(A[g], rhs[g], kappa[g], N, sumY[g], sumY2[g]) for g in range(G)])
+        else:
+            nb = lasso_solve_batch(A, rhs, kappa)
         quad = np.einsum("gj,mjk,gk->g", nb, C, nb)
         sg = (D2.sum(axis=1) - 2 * np.einsum("gk,mgk->g", nb, bm) + quad + 1) / (n + 3)
     priorB = float(np.sum(penl * var / sg * np.abs(nb).sum(axis=1)))         # :268,275

@@ -75,7 +75,7 @@ void set_dims(Dims& d, int G, int n, int M0, int K0, int MB, long long n_total, 
     d.MB = MB;
     d.NS = 1;
     d.NQ = K0 + M0;
-    d.NQP = round_up(d.NQ, 8);
+    d.NQP = std::max(16, round_up(d.NQ, 8));
     d.QS = d.NQP + 4;
     d.NF = K0;
     d.NFP = round_up(K0, 4);
@@ -111,6 +111,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.Y, na * ldG));
     CKR(c->dalloc(&s.mask, na * nwords));
     CK(make_tmap_2d(&c->tmapY, s.Y, ldG, c->n_alloc, 16, 128));
+    CK(make_tmap_2d(&c->tmapY8, s.Y, ldG, c->n_alloc, 16, 8));
     CKR(c->dalloc(&s.celltype0, na));
     CKR(c->dalloc(&s.beta, size_t(ldG) * K0));
     CKR(c->dalloc(&s.sigma, size_t(ldG) * M0));
@@ -128,6 +129,14 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.isdA, size_t(ldG) * M0));
     CKR(c->dalloc(&s.musdA, size_t(ldG) * M0));
     CKR(c->dalloc(&s.igs, size_t(ldG)));
+    CKR(c->dalloc(&s.BM, size_t(ldG) * d.QS));
+    CKR(c->dalloc(&s.gv, size_t(ldG) * 4));
+    CKR(c->dalloc(&s.mc_counter, 1));
+    {   // SIMPLES_FUSED_MC=1 selects the fused sweep + projection kernel (k_mcpass.cuh).  It is parity-green but measured
+        // slower than the separate kernels at C3 (2.6 ms vs 1.8 + 0.36 ms per MC pass, profiles/r02_notes.md), so it is opt-in.
+        const char* e = getenv("SIMPLES_FUSED_MC");
+        c->fused_mc = e && atoi(e) != 0;
+    }
     s.n_alloc = c->n_alloc;
     CKR(c->dalloc(&s.P, size_t(c->NS_max) * na * d.NQP));
     CKR(c->dalloc(&s.S2, size_t(c->NS_max) * na));
@@ -225,10 +234,10 @@ int upload_z(simples_ctx* c, const double* z) {
 
 // one E-pass: projections + cell epilogue
 int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_membership, bool write_W, bool write_Vg,
-           double pi_const) {
+           double pi_const, bool have_P) {
     DevState& s = c->s;
     const Dims& d = s.d;
-    for (int sc = 0; sc < d.NS; ++sc) {
+    for (int sc = 0; sc < d.NS && !have_P; ++sc) {
         P p(c, KC_PROJ, proj_launches(d.n, d.ldG, s.proj_part != nullptr));
         ProjArgs pa{s.Y, s.Q + size_t(sc) * d.ldG * d.QS, s.isg + size_t(sc) * d.ldG, s.P + size_t(sc) * d.n * d.NQP,
                     s.S2 + size_t(sc) * d.n, d.n, d.ldG, d.NQP, d.QS, s.proj_part};
@@ -272,7 +281,8 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
 int run_prep(simples_ctx* c) {
     DevState& s = c->s;
     P p(c, KC_PREP, 2);
-    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.igs, s.cc, 0};
+    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.igs, s.cc, 0,
+                s.BM, s.gv};
     if (c->profile) {                      // serial on the main stream so the per-class events mean something
         launch_prep(pa, c->stream, c->stream);
     } else {
@@ -322,6 +332,41 @@ int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2) {
     return SIMPLES_OK;
 }
 
+// fused MC pass: the sweep and the projection of the E-pass that follows it (cluster-shared sigma)
+bool use_fused_mc(const simples_ctx* c) { return c->fused_mc && c->s.d.NS == 1 && mcpass_supported(c->s.d); }
+
+int run_mcpass(simples_ctx* c, bool clip, double* rec1, double* rec2) {
+    DevState& s = c->s;
+    P p(c, KC_SWEEP);
+    McArgs ma{};
+    ma.d = s.d;
+    ma.mask = s.mask;
+    ma.n_alloc = s.n_alloc;
+    ma.Fh = s.Fh;
+    ma.im = s.im;
+    ma.celltype0 = s.celltype0;
+    ma.BM = s.BM;
+    ma.gv = s.gv;
+    ma.gmean = s.gmean;
+    ma.gsd = s.gsd;
+    ma.isg = s.isg;
+    ma.pg = s.pg;
+    ma.cutoff = c->cutoff;
+    ma.lower = c->lower;
+    ma.upper = c->upper;
+    ma.clip = clip;
+    ma.seed = c->seed;
+    ma.sweep = c->sweep;
+    ma.P = s.P;
+    ma.S2 = s.S2;
+    ma.rec1 = rec1;
+    ma.rec2 = rec2;
+    ma.counter = s.mc_counter;
+    launch_mcpass(ma, c->tmapY8, c->stream);
+    CK(cudaGetLastError());
+    return SIMPLES_OK;
+}
+
 int em_iteration(simples_ctx* c) {
     DevState& s = c->s;
     Dims& d = s.d;
@@ -333,18 +378,20 @@ int em_iteration(simples_ctx* c) {
     const bool draw_mem = d.M0 > 1;
 
     CKR(run_prep(c));
-    CKR(e_pass(c, update_z, false, sampling, draw_mem, !sampling, general && !sampling, pi_const));
+    CKR(e_pass(c, update_z, false, sampling, draw_mem, !sampling, general && !sampling, pi_const, false));
     {
         P p(c, KC_REDUCE);
         launch_finalize_cell(s.part_cell, s.ncta_cell, d.M0, c->cellsum_main, c->stream);
     }
     if (sampling) {
+        const bool fused = use_fused_mc(c);
         for (int mc = 0; mc < c->num_mc; ++mc) {
-            CKR(run_sweep(c, true, nullptr, nullptr));
+            if (fused) CKR(run_mcpass(c, true, nullptr, nullptr));
+            else CKR(run_sweep(c, true, nullptr, nullptr));
             c->sweep += 1;
             const bool last = (mc == c->num_mc - 1);
             CKR(e_pass(c, update_z, (c->compat & SIMPLES_COMPAT_STALE_DT) != 0, !last, draw_mem, last, general && last,
-                       pi_const));
+                       pi_const, fused));
         }
     }
     c->z_null = false;
@@ -810,13 +857,15 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     if (trace_mi) cudaStreamSynchronize(c->stream);
     const auto tm0 = clk_mi::now();
     CKR(run_prep(c));   // parameters are fixed: cluster constants computed once, not per sweep
+    const bool fused = use_fused_mc(c);   // each sweep then also projects the updated Y for the next sweep's E-pass
     for (int it = 1; it <= nit; ++it) {                                       // :67
         const bool rec = it > a->burnin;
         c->sweep = unsigned(it - 1);
-        CKR(e_pass(c, true, false, true, true, rec, false, pi_const));        // :69-104, :107, :112
+        CKR(e_pass(c, true, false, true, true, rec, false, pi_const, fused && it > 1));   // :69-104, :107, :112
         launch_finalize_cell(s.part_cell, s.ncta_cell, M0, c->tot_mi + size_t(it - 1) * (2 * M0 + 1), c->stream);   // :89
         if (rec && c->cons) launch_consensus(s.z, c->cons, n, M0, c->stream);   // :96
-        CKR(run_sweep(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));   // :109-136, :140-141
+        if (fused) CKR(run_mcpass(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));
+        else CKR(run_sweep(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));   // :109-136, :140-141
         if (rec) launch_mi_record_factors(d, s.W, s.z, s.cc.Mm, c->rEF, c->rF2, c->rVF, c->stream);   // :143-147
     }
     CK(cudaGetLastError());

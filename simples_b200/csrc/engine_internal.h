@@ -77,6 +77,8 @@ struct simples_ctx {
     int NS_max = 1;
     long long nnz0 = 0;
     CUtensorMap tmapY;                // Y as [n_alloc][ldG], box {16 genes, 128 cells}, SWIZZLE_128B
+    CUtensorMap tmapY8;               // same, box {16 genes, 8 cells}: the per-warp tiles of the fused MC pass
+    bool fused_mc = false;            // SIMPLES_FUSED_MC=1: fused impute_sweep + estep_project kernel for the MC passes (opt-in)
     double* cellsum_main = nullptr;   // [2 M0 + 1] of the main E-pass of the current iteration
     double* cellsum_last = nullptr;   // [2 M0 + 1] of the last E-pass (nz, c feed the M-step)
     double* stage = nullptr;          // staging buffer for chunked H2D / D2H
@@ -196,7 +198,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
 bool sigma_is_shared(const double* sigma, int G, int M0);
 int upload_z(simples_ctx* c, const double* z);
 int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_membership, bool write_W, bool write_Vg,
-           double pi_const);
+           double pi_const, bool have_P = false);
 int run_prep(simples_ctx* c);
 int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2);
 int fetch_genemajor(simples_ctx* c, const double* dev, int cols, double* host);

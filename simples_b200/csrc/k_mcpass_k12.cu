@@ -1,0 +1,17 @@
+// Instantiations of the fused MC pass for sweep-GEMM depth <= 12 (see k_mcpass.cuh).
+#include "k_mcpass.cuh"
+
+namespace sb {
+
+void launch_mcpass_k12(const McArgs& a, const CUtensorMap& tm, cudaStream_t st) {
+    switch (a.d.NQP / 8) {
+        case 2: mcp::launch_mcpass_variant<3, 2>(a, tm, st); break;
+        case 3: mcp::launch_mcpass_variant<3, 3>(a, tm, st); break;
+        case 4: mcp::launch_mcpass_variant<3, 4>(a, tm, st); break;
+        case 5: mcp::launch_mcpass_variant<3, 5>(a, tm, st); break;
+        case 6: mcp::launch_mcpass_variant<3, 6>(a, tm, st); break;
+        default: break;   // excluded by mcpass_supported()
+    }
+}
+
+}  // namespace sb

@@ -30,6 +30,17 @@ __global__ void k_build_ops(PrepArgs a) {
         a.musdA[size_t(g) * M0 + m] = a.mu[size_t(g) * M0 + m] * sd;
     }
     a.igs[g] = 1.0 / sd;
+    if (a.BM) {            // fused MC pass operands (cluster-shared sigma: column 0)
+        double* bmr = a.BM + size_t(g) * d.QS;
+        for (int k = 0; k < K0; ++k) bmr[k] = a.beta[size_t(g) * K0 + k];
+        for (int m = 0; m < M0; ++m) bmr[K0 + m] = a.mu[size_t(g) * M0 + m];
+        for (int c = K0 + M0; c < d.QS; ++c) bmr[c] = 0.0;
+        const double sdv = sqrt(a.sigma[size_t(g) * M0]) * sd;
+        a.gv[size_t(g) * 4 + 0] = 1.0 / sdv;
+        a.gv[size_t(g) * 4 + 1] = sdv;
+        a.gv[size_t(g) * 4 + 2] = mean;
+        a.gv[size_t(g) * 4 + 3] = 1.0 / sd;
+    }
     double* qs = a.Qs + size_t(g) * d.FS;
     for (int k = 0; k < K0; ++k) qs[k] = a.beta[size_t(g) * K0 + k] * sd;
     for (int c = K0; c < d.FS; ++c) qs[c] = 0.0;

@@ -61,7 +61,7 @@ __device__ __forceinline__ void load_chunk_bulk(const SweepArgs& a, const ChunkB
 
 // NKS = number of K-steps of 4 held as register A-fragments (K0 <= 4 NKS); MINB = resident CTAs per SM aimed at
 template <int NKS, int MINB>
-__global__ void __launch_bounds__(SW * 32, MINB) k_sweep(SweepArgs a) {
+__global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__ SweepArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB, ldG = a.d.ldG, n = a.d.n;
     const int KST = a.d.NFP / 4;
@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(SweepArgs a) {
             const int r = code >> 5, gl = code & 31;
             const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
             const double ms = msW[r * MSS + gl];
-            const Philox4 px = entry_philox(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + wc0 + r),
-                                            (uint32_t)(chunk * SG + gl));
+            const unsigned long long gc = (unsigned long long)(a.d.cell_offset + wc0 + r);
+            const Philox4 px = philox4x32_10_keys((uint32_t)(chunk * SG + gl), (uint32_t)gc, a.sweep, (uint32_t)(gc >> 32) << 8, a.rk);
             const double ub = u52(px.x2, px.x3);
             const float rf = (float)((a.cutoff - ms) * b.isd[gl * M0 + im]);
             const float ax = fabsf(rf) * 0.70710678f;
@@ -353,7 +353,8 @@ static void launch_variant(const SweepArgs& a, dim3 grid, size_t smem, cudaStrea
     k_sweep<NKS, MINB><<<grid, SW * 32, smem, st>>>(a);
 }
 
-void launch_sweep(const SweepArgs& a, cudaStream_t st) {
+void launch_sweep(SweepArgs a, cudaStream_t st) {
+    philox_round_keys(a.seed, a.rk);
     const size_t smem = sizeof(double) * (size_t(SW) * 8 * MSS + 2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
                         SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int) + 64;
     const int tiles = (a.d.n + SC - 1) / SC;

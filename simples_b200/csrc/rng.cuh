@@ -33,6 +33,29 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
+// Philox4x32-10 with the round keys k_r = k_0 + r W precomputed (they are the same for every entry of a launch):
+// kernels take them as parameters, so each round is two IMAD.WIDE + two LOP3 with a constant-bank operand.
+// Bit-identical to philox4x32_10.
+__device__ __forceinline__ Philox4 philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ rk[2 * r], n2 = uint32_t(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c0 = n0;
+        c1 = uint32_t(p1);
+        c2 = n2;
+        c3 = uint32_t(p0);
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+inline void philox_round_keys(uint64_t seed, uint32_t (&rk)[20]) {
+    for (int r = 0; r < 10; ++r) {
+        rk[2 * r] = uint32_t(seed) + uint32_t(r) * 0x9E3779B9u;
+        rk[2 * r + 1] = uint32_t(seed >> 32) + uint32_t(r) * 0xBB67AE85u;
+    }
+}
+
 // ((x >> 12) + 0.5) * 2^-52  in (0,1)
 // (== [1 + m 2^-52] - 1 + 2^-53 with m = x >> 12 the top 52 bits; every step is exact)
 __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {

@@ -66,6 +66,8 @@ struct DevState {
     uint32_t* mask;
     int32_t* celltype0;
     double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs, *P, *S2, *V, *zsum, *Fh, *W;
+    double *BM, *gv;     // fused MC pass operands: [ldG][QS] rows [B_g | mu_g | 0], [ldG][4] {isd, sds, mean, 1/sd}
+    unsigned* mc_counter;
     double* proj_part;   // k_proj tail-split scratch
     int n_alloc;
     int32_t* im;
@@ -122,9 +124,29 @@ struct SweepArgs {
     double cutoff, lower, upper;
     int clip;
     unsigned long long seed; unsigned sweep;
+    uint32_t rk[20];       // Philox round keys, filled by launch_sweep
     double *rec1, *rec2;   // optional do_impute accumulators (same layout as Y), nullptr otherwise
 };
-void launch_sweep(const SweepArgs& a, cudaStream_t st);
+void launch_sweep(SweepArgs a, cudaStream_t st);
+
+// fused MC pass (k_mcpass.cuh): impute_sweep + the projection of the following E-pass; cluster-shared sigma only
+struct McArgs {
+    Dims d;
+    const uint32_t* mask; int n_alloc;
+    const double* Fh; const int32_t *im, *celltype0;
+    const double* BM;      // [ldG][QS]  rows [B_g | mu_g | 0]
+    const double* gv;      // [ldG][4]   {1/(sqrt(sigma) sd), sqrt(sigma) sd, gene mean, 1/sd}  (per-entry gathers)
+    const double *gmean, *gsd, *isg;   // [ldG] dense per-gene vectors (isg = 1/sigma)
+    const double* pg;      // [ldG][MB]
+    double cutoff, lower, upper; int clip;
+    unsigned long long seed; unsigned sweep;
+    uint32_t rk[20];       // Philox round keys k_r = (seed_lo + r W0, seed_hi + r W1), filled by launch_mcpass
+    double *P, *S2;        // outputs of the projection: [n][NQP], [n]
+    double *rec1, *rec2;   // optional do_impute accumulators (layout of Y), nullptr otherwise
+    unsigned* counter;     // task counter, zeroed by the launcher
+};
+bool mcpass_supported(const Dims& d);
+void launch_mcpass(McArgs a, const CUtensorMap& tmapY8, cudaStream_t st);   // tmapY8: box {16 genes, 8 cells}
 
 struct MstatsArgs {
     const double *Y, *V, *zsum; double* part;   // part [splitK][ldG][NVP+1]
@@ -152,6 +174,7 @@ void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out
 struct PrepArgs {
     Dims d; const double *beta, *sigma, *mu, *lam, *pi, *gmean, *gsd;
     double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs; ClusterConsts cc; int stale_q;
+    double *BM, *gv;     // may be nullptr
 };
 void launch_prep(const PrepArgs& a, cudaStream_t st, cudaStream_t st_cluster);
 

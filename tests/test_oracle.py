@@ -365,3 +365,79 @@ def test_golden_stages_regression():
     lq = np.arange(40, 90)
     m_, b_, s_ = O.lq_regress_fast(Y2[lq], Y2[lq], g["lq_sigma_in"], g["em_z"], Ef, Varf, 1, 1)
     assert rel(m_, g["lq_mu"]) <= 1e-10 and rel(b_, g["lq_beta"]) <= 1e-10 and rel(s_, g["lq_sigma"]) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# glmnet-compatible stopping (SURVEY A.2, R/EM_impute.R:257-259): the reference's lasso stops at thresh = 1e-7 on
+# xv_k * delta_k^2 in y-standardised units, so real glmnet output is NOT the exact minimiser the oracle / CUDA path
+# compute.  These tests derive the band inside which real glmnet output must fall (instead of guessing it); the
+# R-golden loader (tests/test_r_golden.py) uses the same machinery for its tolerances.
+# ---------------------------------------------------------------------------------------------------------------
+def _aug_problem(rng, n, K0, M0, corr):
+    """One gene's augmented regression in Gram form, shaped like R/EM_impute.R:238-253."""
+    L = np.eye(K0) + corr * rng.standard_normal((K0, K0)) / math.sqrt(K0)
+    X = rng.standard_normal((M0 * n, K0)) @ L
+    bt = np.where(rng.random(K0) < 0.5, rng.standard_normal(K0), 0.0)
+    y = X @ bt + rng.standard_normal(M0 * n)
+    V = np.linalg.cholesky(L.T @ L * 0.3).T
+    Xa = np.concatenate([X, V])
+    ya = np.concatenate([y, np.zeros(K0)])
+    N = Xa.shape[0]
+    return Xa.T @ Xa, Xa.T @ ya, 1.0 * np.var(ya, ddof=1), N, ya.sum(), (ya * ya).sum()
+
+
+@pytest.mark.parametrize("corr", [0.0, 1.0, 3.0])
+def test_glmnet_compat_band_contains_exact_minimiser(corr):
+    from oracle import simples_oracle as SO
+    rng = np.random.default_rng(11 + int(corr))
+    worst = 0.0
+    for _ in range(40):
+        A, rhs, kappa, N, sy, sy2 = _aug_problem(rng, 150, 8, 3, corr)
+        exact = O.lasso_solve(A, rhs, kappa)
+        info = {}
+        compat = SO.lasso_glmnet_compat(A, rhs, kappa, N, sy, sy2, info=info)
+        assert 1 <= info["passes"] < 10000
+        band = SO.glmnet_band(A, kappa, N, sy, sy2, compat)
+        dev = float(np.abs(exact - compat).max())
+        if np.array_equal(exact != 0, compat != 0):
+            assert dev <= band + 1e-14, (dev, band)
+            worst = max(worst, dev / (np.abs(exact).max() + 1e-300))
+        else:   # a coefficient at the edge of the support may differ: it is then tiny
+            flip = (exact != 0) != (compat != 0)
+            assert np.all(np.abs(exact[flip]) + np.abs(compat[flip]) <= 10 * band + 1e-12)
+        # premise of glmnet_band: at glmnet's stop the stationarity residual is at most
+        # R = max_k sum_j |C_kj| sqrt(thresh / xv_j) (scaled units)
+        ys = math.sqrt(sy2 / N - (sy / N) ** 2)
+        a = compat / ys
+        C = A / N
+        g = rhs / N / ys - C @ a
+        alm = kappa / N / ys
+        R = float(np.max(np.abs(C) @ np.sqrt(SO.GLMNET_THRESH / np.diag(C))))
+        on = a != 0
+        assert np.all(np.abs(g[on] - alm * np.sign(a[on])) <= R * (1 + 1e-9))
+        assert np.all(np.abs(g[~on]) <= alm + R * (1 + 1e-9))
+    # relative deviation of real-glmnet-style output from the exact minimiser: small for the nearly orthogonal designs the
+    # EM produces (posterior factor means), up to ~10 % for strongly correlated ones -- always inside the derived band
+    assert worst < (5e-3 if corr == 0.0 else 0.5)
+
+
+def test_glmnet_compat_em_run_band():
+    """Whole deterministic EM run (impt_it = iter never samples, R/EM_impute.R:161) with glmnet's stopping rule vs the
+    exact minimiser: the propagated differences are the tolerances to expect against real R output."""
+    from oracle import simples_oracle as SO
+    sim = O.simulate(n=300, G=400, K=4, MC=3, S0=10, seed=2)
+    K0, M0 = 6, 3
+    st = O.bench_state(sim, K0, M0)
+    args = (st["Y"], st["Y0"], st["pg"], M0, K0, 0.1, 5, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"])
+    kw = dict(celltype=st["celltype"], impt_it=5, est_z=1, est_lam=1, seed=3)
+    exact = O.em_impute_fast(*args, **kw)
+    SO.LASSO_MODE = "glmnet"
+    try:
+        compat = O.em_impute_fast(*args, **kw)
+    finally:
+        SO.LASSO_MODE = "exact"
+    dev = {k: rel(compat[k], exact[k]) for k in ("loglik", "pi", "mu", "sigma", "beta", "lambda", "z")}
+    # observed on this case: beta 1.0e-4, z 5e-4, mu 3e-5, sigma 3e-6, pi 3e-6, lambda 6e-7, loglik 2e-8
+    assert 1e-9 < dev["beta"] < 2e-3, dev          # not identical (the rule really stops early), but close
+    assert dev["loglik"] < 1e-6 and dev["sigma"] < 1e-4 and dev["mu"] < 1e-3 and dev["z"] < 1e-2, dev
+    assert np.array_equal(np.argmax(compat["z"], 1), np.argmax(exact["z"], 1))
