@@ -24,12 +24,21 @@
  *     failure; simples_last_error() gives the message (thread-local).
  *   - There is NO CPU fallback: without a usable sm_100 device every compute
  *     entry point fails with SIMPLES_ENODEV.
- *   - Multi-GPU: one process per GPU.  Each process passes its contiguous
- *     shard of cells (columns of Y/Y0, rows of z, slice of celltype),
- *     `n_total`/`cell_offset`, and an `allreduce` callback that sums a device
- *     buffer of doubles over all ranks in place (the host layer wires it to
- *     NCCL through torch.distributed).  Exactly one all-reduce per EM
- *     iteration plus two at call start (gene means, default mu).
+ *   - Multi-GPU, two ways (cells are sharded, parameters replicated, exactly
+ *     one all-reduce of the M-step statistics per EM iteration plus two at
+ *     call start: gene means, default mu; NCCL is loaded with dlopen):
+ *     (1) ONE process drives several GPUs: simples_init(ndev > 1, devs).
+ *         simples_em_impute / simples_do_impute then take the FULL host
+ *         matrices, shard the cells over the devices with one host thread per
+ *         device, all-reduce through NCCL inside the library and return the
+ *         full results.  This is the route of an R session (.Call).
+ *     (2) one process per GPU (torchrun): each process passes its contiguous
+ *         shard of cells (columns of Y/Y0, rows of z, slice of celltype) with
+ *         `n_total`/`cell_offset`.  The sum over ranks is either the library's
+ *         own rank communicator (simples_comm_init_rank) or an `allreduce`
+ *         callback that sums a device buffer of doubles in place.
+ *   - Limits: K0 <= 32, M0 <= 32 (register-tiled kernels), G, n < 2^31 per
+ *     device shard, n_total < 2^63.
  */
 #ifndef SIMPLES_B200_H
 #define SIMPLES_B200_H
@@ -42,6 +51,7 @@ extern "C" {
 #endif
 
 #define SIMPLES_ABI_VERSION 1
+#define SIMPLES_MAX_DEVICES 16
 
 #if defined(__GNUC__)
 #define SIMPLES_API __attribute__((visibility("default")))
@@ -236,9 +246,23 @@ typedef struct simples_clus_out {
 
 /* ---- lifecycle / errors ------------------------------------------------ */
 SIMPLES_API int simples_abi_version(void);
-/* Select the device this process drives (ndev must be 1: one process per GPU). */
+/* Select the device(s) this process drives.  ndev = 1: one process per GPU.
+ * ndev in 2..SIMPLES_MAX_DEVICES: this process drives all of them (NCCL
+ * communicators created here); the one-shot EM / MI entry points shard the
+ * cells over them, the other entry points run on devs[0]. */
 SIMPLES_API int simples_init(int ndev, const int *devs);
 SIMPLES_API void simples_shutdown(void);
+SIMPLES_API int simples_device_count(void);
+/* One process per GPU: build this process's rank communicator inside the
+ * library.  Rank 0 calls simples_comm_unique_id (128 bytes), the host layer
+ * broadcasts the bytes, every rank calls simples_comm_init_rank after
+ * simples_init.  Entry points called with n_total > n and allreduce = NULL
+ * then reduce over it. */
+SIMPLES_API int simples_comm_unique_id(void *id128, size_t cap);
+SIMPLES_API int simples_comm_init_rank(int nranks, int rank, const void *id128);
+SIMPLES_API void simples_comm_destroy(void);
+SIMPLES_API int simples_comm_nranks(void);
+SIMPLES_API int simples_nccl_version(void);          /* e.g. 22809, or -1 when libnccl cannot be loaded */
 SIMPLES_API const char *simples_last_error(void);
 
 /* ---- one-shot calls with HOST buffers (what the .Call shim binds) ------- */

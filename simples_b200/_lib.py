@@ -123,9 +123,27 @@ EXPORTS = [
     "simples_kernel_name", "simples_kernel_count", "simples_em_nnz0", "simples_em_kernel_launches",
     "simples_em_yimp0", "simples_bic",
     "simples_ctx_destroy",
+    "simples_device_count", "simples_comm_unique_id", "simples_comm_init_rank", "simples_comm_destroy", "simples_comm_nranks",
+    "simples_nccl_version",
 ]
 
 _lib = None
+
+
+def _point_at_nccl():
+    """The library dlopens libnccl on demand (multi-GPU only).  Prefer the copy bundled with PyTorch (the one torch itself
+    loads, so both share it) over a system libnccl; SIMPLES_NCCL_LIB set by the user wins."""
+    if os.environ.get("SIMPLES_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["SIMPLES_NCCL_LIB"] = cand
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def load():
@@ -137,8 +155,12 @@ def load():
         raise ImportError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(simples_b200 has no CPU fallback)")
+    _point_at_nccl()
     lib = C.CDLL(LIB_PATH)
     lib.simples_abi_version.restype = C.c_int
+    lib.simples_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    lib.simples_comm_init_rank.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    lib.simples_comm_destroy.restype = None
     lib.simples_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
     lib.simples_last_error.restype = C.c_char_p
     lib.simples_em_impute.argtypes = [C.POINTER(EmArgs), C.POINTER(EmOut)]
@@ -174,7 +196,25 @@ def check(rc):
     return rc
 
 
-def init(device: int = 0):
-    """Bind this process to one GPU (one process per GPU)."""
-    devs = (C.c_int * 1)(int(device))
-    check(load().simples_init(1, devs))
+def init(device=0):
+    """``init(i)``: bind this process to GPU i (one process per GPU).  ``init([i, j, ...])``: this process drives all
+    listed GPUs -- EM_impute / do_impute then shard the cells over them inside the library (host threads + NCCL)."""
+    ids = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+    devs = (C.c_int * len(ids))(*ids)
+    check(load().simples_init(len(ids), devs))
+
+
+def comm_init_from_torch(group=None):
+    """One process per GPU (torchrun): build the library's own NCCL rank communicator, the unique id travelling over
+    torch.distributed.  Afterwards sharded calls need no Python all-reduce callback."""
+    import torch.distributed as dist
+    lib = load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        check(lib.simples_comm_unique_id(buf, 128))
+    obj = [bytes(buf.raw)]
+    dist.broadcast_object_list(obj, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    idb = C.create_string_buffer(obj[0], 128)
+    check(lib.simples_comm_init_rank(world, rank, idb))
+    return world

@@ -90,7 +90,8 @@ class _Comm:
                 self.error = e
                 return 1
 
-        self.cb = _lib.ALLREDUCE_FN(_cb)
+        # native communicator (CellShard(native=True)): NULL callback => the library all-reduces over its own NCCL comm
+        self.cb = _lib.ALLREDUCE_FN() if getattr(comm, "native", False) else _lib.ALLREDUCE_FN(_cb)
 
 
 def _em_args(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu, celltype, penl, est_z,
@@ -304,7 +305,7 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
         setattr(a, k, _ptr(keep[k]))
     a.mcmc, a.burnin, a.cutoff = int(mcmc), int(burnin), float(cutoff)
     a.seed, a.ref_compat_flags = int(seed) & 0xFFFFFFFFFFFFFFFF, int(ref_compat)
-    want_cons = bool(consensus) and comm is None
+    want_cons = bool(consensus) and comm is None and _lib.load().simples_device_count() <= 1
     a.want_consensus = int(want_cons)
     cw = None
     if comm is not None:

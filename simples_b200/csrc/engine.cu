@@ -3,12 +3,16 @@
 // this process's shard of cells.  The EM loop is enqueued on one CUDA stream without any
 // host <-> device synchronisation: all data-dependent decisions (lambda eligibility, lasso active
 // sets, priorB bookkeeping) happen on the device.
+#include <mutex>
+#include <thread>
+
 #include "engine_internal.h"
 
 namespace sbe {
 
 thread_local std::string g_err;
 int g_device = -1;
+thread_local int t_device = -1;
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -28,24 +32,47 @@ int ensure_device() {
         int dev = 0;
         cudaGetDevice(&dev);
         g_device = dev;
+        if (g_ndev == 0) {
+            g_ndev = 1;
+            g_devs[0] = dev;
+        }
     }
+    const int dev = t_device >= 0 ? t_device : g_device;
+    static std::mutex mu;
+    static int checked[64] = {0};          // 1 = sm_100 verified and pool configured
+    CK(cudaSetDevice(dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && checked[dev]) return SIMPLES_OK;
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, g_device));
+    CK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) {
         char buf[256];
-        snprintf(buf, sizeof buf, "device %d (%s) is sm_%d%d; this library is built for sm_100a (B200) only", g_device,
-                 prop.name, prop.major, prop.minor);
+        snprintf(buf, sizeof buf, "device %d (%s) is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.name,
+                 prop.major, prop.minor);
         return fail(SIMPLES_ENODEV, buf);
     }
-    CK(cudaSetDevice(g_device));
-    static int pool_dev = -1;
-    if (pool_dev != g_device) {            // keep freed blocks cached in the default pool between calls
+    {   // keep freed blocks cached in the default pool between calls
         cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, g_device));
+        CK(cudaDeviceGetDefaultMemPool(&pool, dev));
         unsigned long long thr = ~0ull;
         CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        pool_dev = g_device;
     }
+    if (dev < 64) checked[dev] = 1;
+    return SIMPLES_OK;
+}
+
+// A per-rank condition (e.g. non-finite input in one shard) must fail on EVERY rank, or the others would wait in the
+// next collective forever: sum the count over the ranks first.
+int agree_all_ranks(simples_ctx* c, long long* count) {
+    if (!c->allreduce) return SIMPLES_OK;
+    double* d = nullptr;
+    CKR(c->dalloc(&d, 1));
+    launch_fill(d, 1, double(*count), c->stream);
+    CKR(allreduce(c, d, 1));
+    double h = 0;
+    CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *count = (long long)h;
     return SIMPLES_OK;
 }
 
@@ -207,7 +234,9 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
         unsigned long long h_bad = 0;
         CK(cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDefault, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (h_bad) return fail(SIMPLES_EINVAL, "Y contains " + std::to_string(h_bad) + " non-finite value(s)");
+        long long bad_all = (long long)h_bad;
+        CKR(agree_all_ranks(c, &bad_all));
+        if (bad_all) return fail(SIMPLES_EINVAL, "Y contains " + std::to_string(bad_all) + " non-finite value(s)");
     }
     return SIMPLES_OK;
 }
@@ -225,7 +254,8 @@ int upload_z(simples_ctx* c, const double* z) {
     const int n = s.d.n, M0 = s.d.M0;
     double* tmp = nullptr;
     CK(cudaMallocAsync(&tmp, size_t(n) * M0 * 8, c->stream));
-    CK(cudaMemcpyAsync(tmp, z, size_t(n) * M0 * 8, cudaMemcpyDefault, c->stream));
+    const size_t ldh = c->io_ld ? size_t(c->io_ld) : size_t(n);      // column stride of the host matrix
+    CK(cudaMemcpy2DAsync(tmp, size_t(n) * 8, z, ldh * 8, size_t(n) * 8, M0, cudaMemcpyDefault, c->stream));
     launch_transpose(tmp, s.z, M0, n, n, M0, c->stream);
     CK(cudaFreeAsync(tmp, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -496,11 +526,12 @@ int fetch_genemajor(simples_ctx* c, const double* dev, int cols, double* host) {
 }
 
 // device [rows][cols] -> host col-major rows x cols via device transpose
-int fetch_transposed(simples_ctx* c, const double* dev, int rows, int cols, int ld, double* host) {
+int fetch_transposed(simples_ctx* c, const double* dev, int rows, int cols, int ld, double* host, long long ld_host) {
     double* tmp = nullptr;
     CK(cudaMallocAsync(&tmp, size_t(rows) * cols * 8, c->stream));
     launch_transpose(dev, tmp, rows, cols, ld, rows, c->stream);
-    CK(cudaMemcpyAsync(host, tmp, size_t(rows) * cols * 8, cudaMemcpyDefault, c->stream));
+    const size_t ldh = ld_host ? size_t(ld_host) : size_t(rows);
+    CK(cudaMemcpy2DAsync(host, ldh * 8, tmp, size_t(rows) * 8, size_t(rows) * 8, cols, cudaMemcpyDefault, c->stream));
     CK(cudaFreeAsync(tmp, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SIMPLES_OK;
@@ -516,16 +547,44 @@ int simples_abi_version(void) { return SIMPLES_ABI_VERSION; }
 const char* simples_last_error(void) { return g_err.c_str(); }
 
 int simples_init(int ndev, const int* devs) {
-    if (ndev != 1 || !devs) return fail(SIMPLES_EINVAL, "simples_init: exactly one device per process (one process per GPU)");
+    if (ndev < 1 || ndev > SIMPLES_MAX_DEVICES || !devs)
+        return fail(SIMPLES_EINVAL, "simples_init: ndev must be in 1..SIMPLES_MAX_DEVICES");
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
     if (e != cudaSuccess || cnt == 0) return fail(SIMPLES_ENODEV, "simples_init: no CUDA device available (no CPU fallback)");
-    if (devs[0] < 0 || devs[0] >= cnt) return fail(SIMPLES_EINVAL, "simples_init: device index out of range");
+    for (int i = 0; i < ndev; ++i) {
+        if (devs[i] < 0 || devs[i] >= cnt) return fail(SIMPLES_EINVAL, "simples_init: device index out of range");
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(SIMPLES_EINVAL, "simples_init: duplicate device");
+    }
+    comm_destroy_all();
     g_device = devs[0];
+    g_ndev = ndev;
+    for (int i = 0; i < ndev; ++i) g_devs[i] = devs[i];
+    for (int i = 0; i < ndev; ++i) {       // every device must be an sm_100 part
+        t_device = devs[i];
+        const int r = ensure_device();
+        t_device = -1;
+        if (r != SIMPLES_OK) {
+            g_ndev = 1;
+            return r;
+        }
+    }
+    if (ndev > 1) {
+        const int r = comm_init_all(ndev, devs);
+        if (r != SIMPLES_OK) {
+            g_ndev = 1;
+            return r;
+        }
+    }
     return ensure_device();
 }
 
-void simples_shutdown(void) { g_device = -1; }
+void simples_shutdown(void) {
+    comm_destroy_all();
+    g_device = -1;
+    g_ndev = 0;
+}
 
 int simples_kernel_count(void) { return KC_COUNT; }
 const char* simples_kernel_name(int k) { return (k >= 0 && k < KC_COUNT) ? kKernelNames[k] : ""; }
@@ -536,7 +595,20 @@ void simples_ctx_destroy(simples_ctx* ctx) {
     delete ctx;
 }
 
-int simples_em_create(const simples_em_args* a, simples_ctx** out) {
+}   // extern "C"
+
+namespace sbe {
+// allreduce of a context: the caller's callback, else the library's rank communicator when the cells are sharded
+void pick_allreduce(simples_ctx* c, simples_allreduce_fn fn, void* user, long long n, long long n_total) {
+    c->allreduce = fn;
+    c->allreduce_user = user;
+    if (!fn && n_total > n && g_rank_comm) {
+        c->allreduce = nccl_allreduce_cb;
+        c->allreduce_user = g_rank_comm;
+    }
+}
+
+int em_create_impl(const simples_em_args* a, simples_ctx** out, long long io_ld) {
     if (!a || !out) return fail(SIMPLES_EINVAL, "null argument");
     *out = nullptr;
     CKR(check_common(a->G, a->n, a->M0, a->K0, a->MB));
@@ -568,8 +640,8 @@ int simples_em_create(const simples_em_args* a, simples_ctx** out) {
     c->num_mc = a->num_mc;
     c->seed = a->seed;
     c->compat = a->ref_compat_flags;
-    c->allreduce = a->allreduce;
-    c->allreduce_user = a->allreduce_user;
+    pick_allreduce(c, a->allreduce, a->allreduce_user, a->n, a->n_total);
+    c->io_ld = io_ld;
     c->z_null = (a->z == nullptr);
 
     const bool shared = sigma_is_shared(a->sigma, a->G, a->M0);
@@ -638,6 +710,11 @@ int simples_em_create(const simples_em_args* a, simples_ctx** out) {
     *out = guard.release();
     return SIMPLES_OK;
 }
+}   // namespace sbe
+
+extern "C" {
+
+int simples_em_create(const simples_em_args* a, simples_ctx** out) { return em_create_impl(a, out, 0); }
 
 int simples_em_set_profile(simples_ctx* c, int enable) {
     if (!c) return fail(SIMPLES_EINVAL, "null ctx");
@@ -728,29 +805,32 @@ int simples_em_fetch(simples_ctx* c, simples_em_out* o) {
     DevState& s = c->s;
     const Dims& d = s.d;
     const int M0 = d.M0, K0 = d.K0;
-    if (o->loglik && c->it > 0) CK(cudaMemcpy(o->loglik, s.loglik, size_t(c->it) * 8, cudaMemcpyDefault));
-    if (o->pi) CK(cudaMemcpy(o->pi, s.pi, size_t(M0) * 8, cudaMemcpyDefault));
-    if (o->mu) CKR(fetch_genemajor(c, s.mu, M0, o->mu));
-    if (o->sigma) CKR(fetch_genemajor(c, s.sigma, M0, o->sigma));
-    if (o->beta) CKR(fetch_genemajor(c, s.beta, K0, o->beta));
-    if (o->lambda) {
-        std::vector<double> t(size_t(M0) * K0);
-        CK(cudaMemcpy(t.data(), s.lam, t.size() * 8, cudaMemcpyDefault));
-        for (int k = 0; k < K0; ++k)
-            for (int m = 0; m < M0; ++m) o->lambda[size_t(k) * M0 + m] = t[size_t(m) * K0 + k];
+    const long long ldh = c->io_ld ? c->io_ld : d.n;       // rows of the full n x . host matrices
+    if (c->write_shared) {                                 // replicated results: identical on every shard
+        if (o->loglik && c->it > 0) CK(cudaMemcpy(o->loglik, s.loglik, size_t(c->it) * 8, cudaMemcpyDefault));
+        if (o->pi) CK(cudaMemcpy(o->pi, s.pi, size_t(M0) * 8, cudaMemcpyDefault));
+        if (o->mu) CKR(fetch_genemajor(c, s.mu, M0, o->mu));
+        if (o->sigma) CKR(fetch_genemajor(c, s.sigma, M0, o->sigma));
+        if (o->beta) CKR(fetch_genemajor(c, s.beta, K0, o->beta));
+        if (o->lambda) {
+            std::vector<double> t(size_t(M0) * K0);
+            CK(cudaMemcpy(t.data(), s.lam, t.size() * 8, cudaMemcpyDefault));
+            for (int k = 0; k < K0; ++k)
+                for (int m = 0; m < M0; ++m) o->lambda[size_t(k) * M0 + m] = t[size_t(m) * K0 + k];
+        }
+        if (o->Varf) CK(cudaMemcpy(o->Varf, s.cc.Mm, size_t(M0) * K0 * K0 * 8, cudaMemcpyDefault));   // symmetric
+        if (o->geneM) CK(cudaMemcpy(o->geneM, s.gmean, size_t(d.G) * 8, cudaMemcpyDefault));
+        if (o->geneSd) CK(cudaMemcpy(o->geneSd, s.gsd, size_t(d.G) * 8, cudaMemcpyDefault));
+        if (o->priorB) CK(cudaMemcpy(o->priorB, s.priorB, 8, cudaMemcpyDefault));
     }
-    if (o->z) CKR(fetch_transposed(c, s.z, d.n, M0, M0, o->z));
+    if (o->z) CKR(fetch_transposed(c, s.z, d.n, M0, M0, o->z, ldh));
     if (o->Ef)
         for (int m = 0; m < M0; ++m)
-            CKR(fetch_transposed(c, s.W + size_t(m) * d.n * K0, d.n, K0, K0, o->Ef + size_t(m) * d.n * K0));
-    if (o->Varf) CK(cudaMemcpy(o->Varf, s.cc.Mm, size_t(M0) * K0 * K0 * 8, cudaMemcpyDefault));   // symmetric
+            CKR(fetch_transposed(c, s.W + size_t(m) * d.n * K0, d.n, K0, K0, o->Ef + size_t(m) * ldh * K0, ldh));
     if (o->Y)
         CKR(fetch_big(c, o->Y, [&](double* dst, size_t c0, size_t nc) {
             launch_uncenter(s.Y + c0 * d.ldG, dst, s.gmean, s.gsd, int(nc), d.G, d.ldG, c->stream);   // :335
         }));
-    if (o->geneM) CK(cudaMemcpy(o->geneM, s.gmean, size_t(d.G) * 8, cudaMemcpyDefault));
-    if (o->geneSd) CK(cudaMemcpy(o->geneSd, s.gsd, size_t(d.G) * 8, cudaMemcpyDefault));
-    if (o->priorB) CK(cudaMemcpy(o->priorB, s.priorB, 8, cudaMemcpyDefault));
     return SIMPLES_OK;
 }
 
@@ -775,12 +855,17 @@ int simples_bic(double loglik_last, int64_t n, int32_t G, int32_t K0, int32_t M0
     return SIMPLES_OK;
 }
 
-int simples_em_impute(const simples_em_args* a, simples_em_out* o) {
+}   // extern "C"
+
+namespace sbe {
+
+int em_impute_one(const simples_em_args* a, simples_em_out* o, long long io_ld, bool write_shared) {
     using clk = std::chrono::steady_clock;
     const bool trace = getenv("SIMPLES_TRACE") != nullptr;
     const auto t0 = clk::now();
     simples_ctx* c = nullptr;
-    CKR(simples_em_create(a, &c));
+    CKR(em_create_impl(a, &c, io_ld));
+    c->write_shared = write_shared;
     const auto t1 = clk::now();
     int r = simples_em_run(c, a->iter);
     if (r == SIMPLES_OK) r = simples_em_sync(c);
@@ -792,20 +877,97 @@ int simples_em_impute(const simples_em_args* a, simples_em_out* o) {
     const auto t4 = clk::now();
     if (trace) {
         auto ms = [](clk::time_point x, clk::time_point y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
-        fprintf(stderr, "[simples_b200] em_impute: create(H2D+prologue) %.1f ms, run(%d it) %.1f ms, fetch(D2H) %.1f ms, destroy %.1f ms\n",
-                ms(t0, t1), a->iter, ms(t1, t2), ms(t2, t3), ms(t3, t4));
+        fprintf(stderr, "[simples_b200] em_impute(dev %d): create(H2D+prologue) %.1f ms, run(%d it) %.1f ms, fetch(D2H) %.1f ms, destroy %.1f ms\n",
+                t_device >= 0 ? t_device : g_device, ms(t0, t1), a->iter, ms(t1, t2), ms(t2, t3), ms(t3, t4));
     }
     return r;
 }
 
+// contiguous, balanced cell ranges (the same rule as simples_b200.dist.partition)
+std::vector<long long> shard_bounds(long long n, int parts) {
+    std::vector<long long> b(parts + 1, 0);
+    const long long base = n / parts, rem = n % parts;
+    for (int r = 0; r < parts; ++r) b[r + 1] = b[r] + base + (r < rem ? 1 : 0);
+    return b;
+}
+
+// run body(rank) on one host thread per device; the first failure (lowest rank) is reported
+template <typename F>
+int run_on_devices(int ndev, F body) {
+    std::vector<int> rc(ndev, SIMPLES_OK);
+    std::vector<std::string> errs(ndev);
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r)
+        th.emplace_back([&, r] {
+            t_device = g_devs[r];
+            rc[r] = body(r);
+            errs[r] = g_err;
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < ndev; ++r)
+        if (rc[r] != SIMPLES_OK) return fail(rc[r], "device " + std::to_string(g_devs[r]) + ": " + errs[r]);
+    return SIMPLES_OK;
+}
+
+bool multi_device_call(const void* cb, long long n, long long n_total, const void* stream) {
+    return g_ndev > 1 && !cb && !stream && (n_total == 0 || n_total == n) && n >= g_ndev;
+}
+
+// One process, several GPUs: the cells (columns of Y / Y0, rows of z, Ef) are sharded over the devices, every shard
+// runs the ordinary single-shard code on its own host thread, and the all-reduce is NCCL inside the library.
+int em_impute_sharded(const simples_em_args* a, simples_em_out* o) {
+    if (!a) return fail(SIMPLES_EINVAL, "null argument");
+    CKR(check_common(a->G, a->n, a->M0, a->K0, a->MB));
+    if (a->celltype)
+        for (int i = 0; i < a->n; ++i)      // validated up front: a failure inside one shard would stall the others
+            if (a->celltype[i] < 1 || a->celltype[i] > a->MB) return fail(SIMPLES_EINVAL, "celltype must be in 1..ncol(pg)");
+    const int nd = g_ndev;
+    const std::vector<long long> b = shard_bounds(a->n, nd);
+    const size_t G = size_t(a->G);
+    return run_on_devices(nd, [&](int r) -> int {
+        simples_em_args la = *a;
+        const long long c0 = b[r], nl = b[r + 1] - b[r];
+        la.n = int(nl);
+        la.Y = a->Y + size_t(c0) * G;
+        la.Y0 = a->Y0 + size_t(c0) * G;
+        la.z = a->z ? a->z + c0 : nullptr;
+        la.celltype = a->celltype ? a->celltype + c0 : nullptr;
+        la.n_total = a->n;
+        la.cell_offset = c0;
+        la.allreduce = nccl_allreduce_cb;
+        la.allreduce_user = g_comms[r];
+        simples_em_out lo{};
+        if (o) {
+            lo = *o;
+            lo.z = o->z ? o->z + c0 : nullptr;
+            lo.Ef = o->Ef ? o->Ef + c0 : nullptr;
+            lo.Y = o->Y ? o->Y + size_t(c0) * G : nullptr;
+        }
+        return em_impute_one(&la, o ? &lo : nullptr, a->n, r == 0);
+    });
+}
+
+}   // namespace sbe
+
+extern "C" {
+
+int simples_em_impute(const simples_em_args* a, simples_em_out* o) {
+    if (a && multi_device_call((const void*)a->allreduce, a->n, a->n_total, a->stream)) return em_impute_sharded(a, o);
+    return em_impute_one(a, o, 0, true);
+}
+
+}   // extern "C"
+
+namespace sbe {
 // ---------------------------------------------------------------------------------------------
-int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
+int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, bool write_shared) {
     if (!a || !o) return fail(SIMPLES_EINVAL, "null argument");
     CKR(check_common(a->G, a->n, a->M0, a->K0, a->MB));
     if (!a->dat || !a->Y || !a->beta || !a->lambda || !a->sigma || !a->mu || !a->pi || !a->pg)
         return fail(SIMPLES_EINVAL, "dat, Y, beta, lambda, sigma, mu, pi and pg are required");
     if (a->mcmc < 1 || a->burnin < 0) return fail(SIMPLES_EINVAL, "mcmc must be >= 1 and burnin >= 0");
-    if (a->want_consensus && a->allreduce) return fail(SIMPLES_EINVAL, "consensus_cluster is single-rank only");
+    if (a->want_consensus && (a->allreduce || a->n_total > a->n))
+        return fail(SIMPLES_EINVAL, "consensus_cluster is single-rank only");
     CKR(ensure_device());
 
     std::unique_ptr<simples_ctx> guard(new simples_ctx());
@@ -820,8 +982,9 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     c->cutoff = a->cutoff;
     c->seed = a->seed;
     c->compat = a->ref_compat_flags;
-    c->allreduce = a->allreduce;
-    c->allreduce_user = a->allreduce_user;
+    pick_allreduce(c, a->allreduce, a->allreduce_user, a->n, a->n_total);
+    c->io_ld = io_ld;
+    c->write_shared = write_shared;
     c->mcmc = a->mcmc;
     c->burnin = a->burnin;
     const bool shared = sigma_is_shared(a->sigma, a->G, a->M0);
@@ -877,7 +1040,7 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
                 std::chrono::duration<double, std::milli>(clk_mi::now() - tm0).count() / nit, c->nnz0);
 
     // ---- outputs (R/do_impute.R:156-159) ----
-    if (o->loglik) {
+    if (o->loglik && c->write_shared) {
         std::vector<double> t(size_t(nit) * (2 * M0 + 1));
         CK(cudaMemcpy(t.data(), c->tot_mi, t.size() * 8, cudaMemcpyDefault));
         double sacc = 0.0;
@@ -900,9 +1063,10 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
         CK(cudaMemcpy(f2.data(), c->rF2, f2.size() * 8, cudaMemcpyDefault));
         CK(cudaMemcpy(vf.data(), c->rVF, vf.size() * 8, cudaMemcpyDefault));
         const double mc = a->mcmc;
+        const size_t ldh = c->io_ld ? size_t(c->io_ld) : size_t(n);
         for (int i = 0; i < n; ++i)
             for (int k = 0; k < K0; ++k) {
-                const size_t e = size_t(i) * K0 + k, h = size_t(k) * n + i;
+                const size_t e = size_t(i) * K0 + k, h = size_t(k) * ldh + i;
                 const double m1 = ef[e] / mc;
                 if (o->EF) o->EF[h] = m1;
                 if (o->varF) o->varF[h] = f2[e] / mc - m1 * m1 + vf[e] / mc;
@@ -916,6 +1080,48 @@ int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return SIMPLES_OK;
+}
+
+int do_impute_sharded(const simples_mi_args* a, simples_mi_out* o) {
+    if (!a || !o) return fail(SIMPLES_EINVAL, "null argument");
+    CKR(check_common(a->G, a->n, a->M0, a->K0, a->MB));
+    if (a->want_consensus && o->consensus_cluster)
+        return fail(SIMPLES_EINVAL, "consensus_cluster (n x n) is not materialised when the cells are sharded over devices");
+    if (a->celltype)
+        for (int i = 0; i < a->n; ++i)
+            if (a->celltype[i] < 1 || a->celltype[i] > a->MB) return fail(SIMPLES_EINVAL, "celltype must be in 1..ncol(pg)");
+    const int nd = g_ndev;
+    const std::vector<long long> b = shard_bounds(a->n, nd);
+    const size_t G = size_t(a->G);
+    return run_on_devices(nd, [&](int r) -> int {
+        simples_mi_args la = *a;
+        const long long c0 = b[r], nl = b[r + 1] - b[r];
+        la.n = int(nl);
+        la.dat = a->dat + size_t(c0) * G;
+        la.Y = a->Y + size_t(c0) * G;
+        la.celltype = a->celltype ? a->celltype + c0 : nullptr;
+        la.want_consensus = 0;
+        la.n_total = a->n;
+        la.cell_offset = c0;
+        la.allreduce = nccl_allreduce_cb;
+        la.allreduce_user = g_comms[r];
+        simples_mi_out lo = *o;
+        lo.impt = o->impt ? o->impt + size_t(c0) * G : nullptr;
+        lo.impt_var = o->impt_var ? o->impt_var + size_t(c0) * G : nullptr;
+        lo.EF = o->EF ? o->EF + c0 : nullptr;
+        lo.varF = o->varF ? o->varF + c0 : nullptr;
+        lo.consensus_cluster = nullptr;
+        return do_impute_one(&la, &lo, a->n, r == 0);
+    });
+}
+
+}   // namespace sbe
+
+extern "C" {
+
+int simples_do_impute(const simples_mi_args* a, simples_mi_out* o) {
+    if (a && multi_device_call((const void*)a->allreduce, a->n, a->n_total, a->stream)) return do_impute_sharded(a, o);
+    return do_impute_one(a, o, 0, true);
 }
 
 }  // extern "C"

@@ -19,8 +19,17 @@ namespace sbe {
 using namespace sb;
 
 extern thread_local std::string g_err;
-extern int g_device;
+extern int g_device;                    // device of a one-device process (simples_init(1, ...))
+extern thread_local int t_device;       // device of the calling host thread in a multi-device run (-1: g_device)
+extern int g_ndev;                      // devices this process drives (0 before simples_init)
+extern int g_devs[SIMPLES_MAX_DEVICES];
+extern void* g_comms[SIMPLES_MAX_DEVICES];   // ncclComm_t per device (single-process multi-GPU)
+extern void* g_rank_comm;               // ncclComm_t of this process in a one-process-per-GPU job, or nullptr
 int fail(int code, const std::string& msg);
+int nccl_load();
+int nccl_allreduce_cb(void* comm, double* dev_buf, size_t count, void* stream);
+int comm_init_all(int ndev, const int* devs);
+void comm_destroy_all();
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
@@ -70,6 +79,11 @@ struct simples_ctx {
     simples_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
     bool z_null = false;
+    // single-process multi-GPU run: this context holds one shard; row-sharded host matrices (z, Ef, EF, varF) are
+    // addressed with the leading dimension of the FULL matrix (io_ld, 0 = the local n) through pointers that already
+    // point at the shard's first row; only the first shard writes the replicated outputs (parameters, loglik)
+    long long io_ld = 0;
+    bool write_shared = true;
     int it = 0;             // EM iterations done
     unsigned sweep = 0;     // MC sweeps done (tape position)
     int iter_cap = 0;
@@ -189,6 +203,7 @@ struct Tracer {
 
 int ensure_device();
 int allreduce(simples_ctx* c, double* buf, size_t count);
+void pick_allreduce(simples_ctx* c, simples_allreduce_fn fn, void* user, long long n, long long n_total);
 std::vector<double> to_rowmajor(const double* src, int rows, int cols, int ldrows, double padval);
 void set_dims(sb::Dims& d, int G, int n, int M0, int K0, int MB, long long n_total, long long cell_offset);
 int check_common(int G, int n, int M0, int K0, int MB);
@@ -197,12 +212,13 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
                  const double* lambda, const double* pi, const int32_t* celltype, double cutoff, bool sigma_shared);
 bool sigma_is_shared(const double* sigma, int G, int M0);
 int upload_z(simples_ctx* c, const double* z);
+int agree_all_ranks(simples_ctx* c, long long* count);
 int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_membership, bool write_W, bool write_Vg,
            double pi_const, bool have_P = false);
 int run_prep(simples_ctx* c);
 int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2);
 int fetch_genemajor(simples_ctx* c, const double* dev, int cols, double* host);
-int fetch_transposed(simples_ctx* c, const double* dev, int rows, int cols, int ld, double* host);
+int fetch_transposed(simples_ctx* c, const double* dev, int rows, int cols, int ld, double* host, long long ld_host = 0);
 
 // chunked D2H of a per-entry G x n result produced by `fill(chunk_dev_out, cell0, ncells)`.
 // The staging buffer is split in two halves: the fill kernel of chunk k+1 (compute stream) overlaps the

@@ -28,8 +28,7 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     c->cutoff = a->cutoff;
     c->seed = a->seed;
     c->sweep = a->sweep;
-    c->allreduce = a->allreduce;
-    c->allreduce_user = a->allreduce_user;
+    pick_allreduce(c, a->allreduce, a->allreduce_user, a->n, a->n_total);
     const int Gq = a->Gq, n = a->n, M0 = a->M0, K0 = a->K0;
     {
         std::vector<double> b0(size_t(Gq) * K0, 0.0), l1(size_t(M0) * K0, 1.0), p1(M0, 1.0 / M0);
@@ -171,8 +170,7 @@ int simples_init_impute(const simples_init_args* a, simples_init_out* o) {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    c->allreduce = a->allreduce;
-    c->allreduce_user = a->allreduce_user;
+    pick_allreduce(c, a->allreduce, a->allreduce_user, a->n, a->n_total);
     const size_t GM = size_t(G) * M0, nst = 5 * GM;
     double *Y2 = nullptr, *part = nullptr, *stats = nullptr, *pg1 = nullptr, *fit = nullptr;
     int32_t* clus0 = nullptr;
@@ -232,8 +230,7 @@ int simples_init_cluster(const simples_clus_args* a, simples_clus_out* o) {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    c->allreduce = a->allreduce;
-    c->allreduce_user = a->allreduce_user;
+    pick_allreduce(c, a->allreduce, a->allreduce_user, a->n, a->n_total);
     cudaStream_t st = c->stream;
     const int G = a->G, n = a->n, K = a->K, M0 = a->M0, R = a->nstart;
     const int ldG = round_up(G, GPAD), na = round_up(n, 128);

@@ -336,18 +336,10 @@ void launch_cell(const CellArgs& a, cudaStream_t st) {
     const int mm_in_smem = 0;
     const size_t smem = fixed;
     if (K0 <= 16) {
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
-            cudaFuncSetAttribute(k_cell<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr = smem;
-        }
+        ensure_dyn_smem_k(k_cell<4, 2>, smem);
         k_cell<4, 2><<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem, pw_doubles);
     } else {
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
-            cudaFuncSetAttribute(k_cell<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr = smem;
-        }
+        ensure_dyn_smem_k(k_cell<8, 4>, smem);
         k_cell<8, 4><<<a.ncta, CW * 32, smem, st>>>(a, mm_in_smem, pw_doubles);
     }
 }

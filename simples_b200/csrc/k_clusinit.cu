@@ -373,11 +373,7 @@ void launch_km_pass(const KmArgs& a, int mode, int rsel, int32_t* labels, cudaSt
     const int RG = km_restart_group(a.M0, a.K);
     const size_t smem = sizeof(double) * (size_t(RG) * a.M0 * a.K + size_t(KMW) * 32 * (a.K + 1) +
                                           size_t(KMW) * RG * a.M0 * (a.K + 1));
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_km_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
-    }
+    ensure_dyn_smem_k(k_km_pass, smem);
     const int nwarps = a.nsplit * KMW;
     const int cpw = ((a.n + nwarps - 1) / nwarps + 31) / 32 * 32;
     dim3 grid(a.nsplit, mode == 2 ? 1 : (a.R + RG - 1) / RG);

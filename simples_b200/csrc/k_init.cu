@@ -219,11 +219,7 @@ int init_stats_splits(int n) { return n >= 4096 ? 32 : (n >= 256 ? 4 : 1); }
 void launch_init_stats(const double* Y2, const int32_t* clus0, int n, int G, int M0, double cutoff, double* part, int nsplit,
                        cudaStream_t st) {
     const size_t smem = sizeof(double) * size_t(M0) * NST * GB;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_init_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
-    }
+    ensure_dyn_smem_k(k_init_stats, smem);
     dim3 grid((G + GB - 1) / GB, nsplit);
     k_init_stats<<<grid, GB, smem, st>>>(Y2, clus0, n, G, M0, cutoff, part);
 }

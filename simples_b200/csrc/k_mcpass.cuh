@@ -389,7 +389,7 @@ k_mcpass(const __grid_constant__ CUtensorMap tm, const __grid_constant__ McArgs 
 template <int NKS, int NT, int MW, int MINB, int CU>
 void launch_mcpass_cfg(const McArgs& a, const CUtensorMap& tm, cudaStream_t st) {
     constexpr size_t smem = smem_bytes(MW);
-    cudaFuncSetAttribute(k_mcpass<NKS, NT, MW, MINB, CU>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    ensure_dyn_smem_k(k_mcpass<NKS, NT, MW, MINB, CU>, smem);
     const int ntasks = (a.d.n + 7) / 8;
     int grid = NUM_SMS_B200 * MINB;
     if (grid * MW > ntasks) grid = (ntasks + MW - 1) / MW;

@@ -119,11 +119,7 @@ template <int NT>
 void launch_nt(const MstatsArgs& a, cudaStream_t st) {
     constexpr int VS = NT * 8 + 4;
     const size_t smem = 128 + STAGES * stage_bytes(VS);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_mstats<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr_set = true;
-    }
+    ensure_dyn_smem_k(k_mstats<NT>, size_t(int(smem)));
     const int cps = (((a.n + a.splitK - 1) / a.splitK) + KC - 1) / KC * KC;
     dim3 grid(a.ldG / MT, a.splitK);
     k_mstats<NT><<<grid, THREADS, smem, st>>>(a, cps);

@@ -560,22 +560,14 @@ void launch_mstep(const MstepArgs& a, cudaStream_t st) {
         const size_t KK = size_t(K0) * K0;
         const size_t smem = sizeof(double) * (KK + size_t(M0) * K0 + GW + GW * KK * (a.general ? 2 : 1) + GW * K0) +
                             sizeof(int) * GW * K0;
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
-            cudaFuncSetAttribute(k_gene_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr = smem;
-        }
+        ensure_dyn_smem_k(k_gene_solve, smem);
         k_gene_solve<<<a.ncta_gene, GW * 32, smem, st>>>(a);
     }
     k_lmp<<<1, 1024, 0, st>>>(a);
     {
         const int GS = mu_gene_splits(a.d.ldG);
         const size_t smem = sizeof(double) * (size_t(MG) * K0 + 2 * MG);
-        static size_t attr2 = 0;
-        if (smem > 48 * 1024 && smem > attr2) {
-            cudaFuncSetAttribute(k_mu_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr2 = smem;
-        }
+        ensure_dyn_smem_k(k_mu_acc, smem);
         k_mu_acc<<<dim3(M0, GS), 256, smem, st>>>(a, GS);
         k_mu_fin<<<dim3(M0, (a.d.G + 2047) / 2048), 256, 0, st>>>(a, GS);
     }
@@ -585,11 +577,7 @@ void launch_lq_solve(const LqSolveArgs& a, cudaStream_t st) {
     const int K0 = a.d.K0, M0 = a.d.M0;
     const size_t KK = size_t(K0) * K0;
     const size_t smem = sizeof(double) * (KK + size_t(M0) * K0 + 2 * GW * KK + GW * K0) + sizeof(int) * GW * K0;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_lq_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
-    }
+    ensure_dyn_smem_k(k_lq_solve, smem);
     k_lq_solve<<<(a.d.G + GW - 1) / GW, GW * 32, smem, st>>>(a);
 }
 

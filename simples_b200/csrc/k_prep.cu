@@ -166,11 +166,7 @@ void launch_prep(const PrepArgs& a, cudaStream_t st, cudaStream_t st_cluster) {
     k_build_ops<<<(a.d.ldG + 127) / 128, 128, 0, st>>>(a);
     const int K0 = a.d.K0;
     const size_t smem = sizeof(double) * (size_t(GT) * K0 + 5 * GT + 4 * K0 * K0 + 2);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
-    }
+    ensure_dyn_smem_k(k_cluster, smem);
     k_cluster<<<a.d.M0, 256, smem, st_cluster>>>(a);
 }
 

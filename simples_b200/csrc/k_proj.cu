@@ -172,11 +172,7 @@ void launch_nt(const ProjArgs& a, const CUtensorMap& tm, cudaStream_t st) {
     int stages = int((227 * 1024 - 256 - 1024) / SB);
     if (stages > 5) stages = 5;
     const size_t smem = stages * SB + 256 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_proj<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-    }
+    ensure_dyn_smem_k(k_proj<NT>, size_t(227 * 1024));
     const int ntiles = (a.n + TC - 1) / TC;
     const int nchunks = a.ldG / GC;
     // Full rounds of NUM_SMS tiles run as they are; a last partial round of `rem` tiles is split along the genes into

@@ -345,11 +345,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
 
 template <int NKS, int MINB>
 static void launch_variant(const SweepArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_sweep<NKS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr = smem;
-    }
+    ensure_dyn_smem_k(k_sweep<NKS, MINB>, smem);
     k_sweep<NKS, MINB><<<grid, SW * 32, smem, st>>>(a);
 }
 

@@ -91,6 +91,12 @@ struct DevState {
     double *part_mu;   // k_mu_acc partial sums
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute: remembered per (kernel, current device),
+// thread-safe, so that one process can drive several GPUs (one host thread each) and re-initialise on another device.
+void ensure_dyn_smem(const void* kernel, size_t bytes);
+template <typename K>
+inline void ensure_dyn_smem_k(K kernel, size_t bytes) { ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes); }
+
 // ---- launchers (each in its own .cu) ------------------------------------------------------------
 struct ProjArgs {
     const double* Y; const double* Q; const double* isg; double* P; double* S2;

@@ -1,5 +1,10 @@
 #include <cudaTypedefs.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "state.h"
 #include "tmap.h"
 
 namespace sb {
@@ -23,6 +28,20 @@ cudaError_t make_tmap_2d(CUtensorMap* out, const double* base, int ldG, int n_al
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+void ensure_dyn_smem(const void* kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = done[std::make_pair(kernel, dev)];
+    if (bytes > cur) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+        cur = bytes;
+    }
 }
 
 }  // namespace sb

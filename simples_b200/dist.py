@@ -39,10 +39,17 @@ class _DevPtr:
 class CellShard:
     """This rank's shard of the cells + the all-reduce used by the library."""
 
-    def __init__(self, n_total, rank=None, world_size=None, group=None):
+    def __init__(self, n_total, rank=None, world_size=None, group=None, native=False):
+        """``native=True``: the library reduces over its own NCCL rank communicator (built here from a unique id
+        broadcast over torch.distributed); no Python callback runs inside the EM loop."""
         import torch.distributed as dist
         self._dist = dist
         self.group = group
+        self.native = bool(native)
+        if self.native:
+            from ._lib import comm_init_from_torch, load
+            if load().simples_comm_nranks() != dist.get_world_size(group):
+                comm_init_from_torch(group)
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.bounds = partition(n_total, self.world_size)

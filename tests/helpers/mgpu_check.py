@@ -2,8 +2,9 @@
 reproduce the single-GPU result (parameters to reduction-order rounding, Y / z shards equal to the
 corresponding slices), because the Philox tape is keyed by the GLOBAL cell index."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+_TESTS = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(_TESTS))
+sys.path.insert(0, _TESTS)
 import numpy as np
 import torch, torch.distributed as dist
 import simples_b200 as sb
@@ -23,6 +24,14 @@ mi = sb.do_impute(sh.cols(st["Y0"]), part["Y"], part["beta"], part["lambda"], pa
                   part["geneM"], part["geneSd"], sh.rows(st["celltype"]), mcmc=3, burnin=1, pg=st["pg"], seed=5, comm=sh)
 ok = True
 msgs = []
+# the same sharded call with the all-reduce inside the library (its own NCCL rank communicator, no Python callback)
+shn = sb.CellShard(n, native=True)
+partn = sb.EM_impute(shn.cols(st["Y"]), shn.cols(st["Y0"]), st["pg"], M0, K0, 0.1, 4, st["beta"], st["sigma"], st["lam"],
+                     st["pi"], shn.rows(st["z"]), celltype=shn.rows(st["celltype"]), comm=shn, **kw)
+for k in ("loglik", "pi", "mu", "sigma", "beta", "lambda", "Y", "z"):
+    e = rel(partn[k], part[k]); ok &= e <= 1e-12
+    if rank == 0: msgs.append(f"native.{k}={e:.1e}")
+assert shn.n_allreduce == 0 and sb.load().simples_comm_nranks() == world
 if rank == 0:
     full = sb.EM_impute(*em_args(st, M0, K0, 4), celltype=st["celltype"], **kw)
     fmi = sb.do_impute(st["Y0"], full["Y"], full["beta"], full["lambda"], full["sigma"], full["mu"], full["pi"],
