@@ -6,8 +6,10 @@ for N > 1) prints ONE JSON line on rank 0.
 
 * step      = one steady-state EM iteration of the all-genes EM_impute call (impt_it = 1, num_mc = 3:
               1 + 3 E-passes, 3 imputation sweeps, statistics, all-reduce, M-step; R/EM_impute.R:120-333)
-* workload  = BASELINE.json configs[2] ("C3"): synthetic 100k cells x 2k genes, K0 = M0 = 10, PER GPU
-              (weak scaling: N GPUs hold N x 100k cells, cells sharded, one NCCL all-reduce / iteration)
+* workload  = BASELINE.json configs[2] ("C3"): synthetic 100k cells x 2k genes, K0 = M0 = 10 -- the configuration the metric is
+              quoted on.  With N GPUs the SAME 100k cells are sharded over the ranks (strong scaling, the default: the
+              metric fixes the problem); `--mode weak` keeps 100k cells PER GPU.  One NCCL all-reduce per iteration,
+              issued by the library itself (rank communicator inside libsimples_b200, no Python in the EM loop)
 * value     = imputed entries / s over the whole job, inputs resident in HBM, device time (CUDA events
               on the library's stream, max over ranks);  em_iters_per_sec is reported beside it
 * e2e       = same metric through the C-ABI call simples_em_impute with HOST (pinned) buffers:
@@ -31,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(n=100_000, G=2000, K=10, MC=10, K0=10, M0=10, cutoff=0.1, num_mc=3, seed=1)
-METRIC = "imputed entries/sec (EM_impute, 100k cells x 2k genes per GPU, K0=M0=10)"
+METRIC = "imputed entries/sec (EM_impute, 100k cells x 2k genes, K0=M0=10)"
 UNIT = "entries/s"
 
 
@@ -45,10 +47,11 @@ def measured_peaks():
 
 
 def fp64_peak():
-    p = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return float(json.load(f)["fp64_dgemm_tflops"]), "measured cuBLAS DGEMM 8192^3 (profiles/r01_fp64_peak.json)"
+    for name in ("r02_fp64_peak.json", "r01_fp64_peak.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                return float(json.load(f)["fp64_dgemm_tflops"]), f"measured cuBLAS DGEMM 8192^3 (profiles/{name})"
     return 40.0, "nominal B200 FP64"
 
 
@@ -108,9 +111,9 @@ def em_kwargs(st, comm=None):
 
 def algorithmic(n, G, K0, M0, num_mc, rho):
     """Per-launch algorithmic bytes / flops of each hot kernel."""
-    NQP = (K0 + M0 + 7) // 8 * 8
+    NQP = max(16, (K0 + M0 + 7) // 8 * 8)
     NVP = (K0 + M0 + 1 + 7) // 8 * 8
-    NFP = (K0 + M0 + 1 + 7) // 8 * 8
+    NFP = (K0 + 3) // 4 * 4            # depth of the sweep's conditional-mean GEMM (engine.cu set_dims: roundup(K0, 4))
     return {
         "estep_project": dict(bytes=8.0 * G * n, flops=2.0 * n * G * NQP + 3.0 * n * G),
         "impute_sweep": dict(bytes=rho * 8.0 * G * n + G * n / 8.0, flops=2.0 * n * G * NFP),
@@ -119,33 +122,45 @@ def algorithmic(n, G, K0, M0, num_mc, rho):
 
 
 def run_reference(args):
-    """CPU arm: the oracle port of the reference algorithm on a bounded sample of the workload."""
+    """CPU arm: the oracle port of the reference algorithm (R is not installed here or on the GPU box) on a bounded sample
+    of the workload, honouring --steps / --warmup: 1 deterministic + W warm-up + K timed steady-state EM iterations in one
+    call, per-iteration times taken at the M-step boundaries."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle as O
-    ncell = 3000
+    from oracle import simples_oracle as SO
+    ncell = 1500
+    W, K = max(args.warmup, 1), max(args.steps, 1)
     st = make_workload(ncell, 0, pinned=False)
     a = (st["Y"], st["Y0"], st["pg"], CFG["M0"], CFG["K0"], CFG["cutoff"])
     kw = dict(celltype=st["celltype"], penl=1, est_z=1, max_lambda=True, est_lam=1, impt_it=1, sigma0=100, pi_alpha=1,
               num_mc=CFG["num_mc"], seed=1234)
     nnz0 = int((st["Y0"] <= CFG["cutoff"]).sum())
-    # it = 1 never samples (impt_it = 1 => sampling from it = 2): time (1 + steps) iterations minus 1 iteration
-    t0 = time.perf_counter()
-    O.em_impute_fast(*a, 1, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"], **kw)
-    t1 = time.perf_counter()
-    steps = max(1, min(args.steps, 3))
-    O.em_impute_fast(*a, 1 + steps, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"], **kw)
-    t2 = time.perf_counter()
-    t_iter = max(((t2 - t1) - (t1 - t0)) / steps, 1e-9)
+    stamps = []
+    orig = SO.mstep_from_stats
+
+    def stamped(*aa, **kk):          # the M-step closes an iteration (R/EM_impute.R:234-318)
+        r = orig(*aa, **kk)
+        stamps.append(time.perf_counter())
+        return r
+
+    SO.mstep_from_stats = stamped
+    try:
+        O.em_impute_fast(*a, 1 + W + K, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"], **kw)
+    finally:
+        SO.mstep_from_stats = orig
+    t_iter = max((stamps[-1] - stamps[W]) / K, 1e-9)       # stamps[0] = end of the deterministic first iteration
     val = nnz0 * CFG["num_mc"] / t_iter
     cores = os.cpu_count() or 1
-    sample = f"{ncell} cells x {CFG['G']} genes of the same synthetic workload, {steps} steady-state EM iterations (NumPy/OpenBLAS port)"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": 1, "ms_per_step": t_iter * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    sample = (f"{ncell} cells x {CFG['G']} genes of the same synthetic workload, {K} timed steady-state EM iterations after "
+              f"{W} warm-up (NumPy/OpenBLAS port of the reference algorithm)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": t_iter * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3 sample: synthetic zero-inflated log-counts, K0=M0=10, num_mc=3", "cells": ncell,
-                       "genes": CFG["G"]},
+            "config": {"workload": "C3 sample: synthetic zero-inflated log-counts, K0=M0=10, impt_it=1, num_mc=3 (steady-state EM "
+                                   f"iteration) on a bounded sample of {ncell} of the 100k cells (throughput in entries/s is size-independent "
+                                   "for this O(n) algorithm)", "cells": ncell, "genes": CFG["G"], "K0": CFG["K0"], "M0": CFG["M0"]},
             "em_iters_per_sec": 1.0 / t_iter,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,7 +212,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--cells", type=int, default=CFG["n"], help="cells per GPU (default: the C3 workload)")
+    ap.add_argument("--cells", type=int, default=None, help="cells per GPU (overrides --mode; non-headline)")
+    ap.add_argument("--mode", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the metric's 100k cells sharded over the ranks (default), weak = 100k cells per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-iter", type=int, default=10)
@@ -229,11 +246,17 @@ def main():
     torch.cuda.set_device(local)
     sb.init(local)
     comm = None
-    n = args.cells
+    if args.cells is not None:
+        n_total, mode = args.cells * world, "weak"
+    elif args.mode == "weak":
+        n_total, mode = CFG["n"] * world, "weak"
+    else:
+        n_total, mode = CFG["n"], "strong"
+    n = n_total // world
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        comm = sb.CellShard(n * world)
-        assert comm.n_local == n
+        comm = sb.CellShard(n_total, native=True)     # all-reduce inside the library (its own NCCL rank communicator)
+        n = comm.n_local
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
 
@@ -244,7 +267,7 @@ def main():
     kw_ctx = {k: v for k, v in kw.items()}
 
     # ---------------- device-resident timing ----------------
-    ctx = sb.EMContext(*pos, iter=W + K, **kw_ctx)
+    ctx = sb.EMContext(*pos, iter=W + 2 * K + 2, **kw_ctx)
     nnz0 = ctx.nnz0
     rho = nnz0 / float(G * n)
     ctx.run(W)
@@ -270,7 +293,22 @@ def main():
         total_ms = float(t.item())
         dist.barrier()
     ms_per_step = total_ms / K
-    value = world * nnz0 * CFG["num_mc"] / (ms_per_step * 1e-3)
+    nnz_all = nnz0
+    if world > 1:
+        t = torch.tensor([float(nnz0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        nnz_all = int(t.item())
+    value = nnz_all * CFG["num_mc"] / (ms_per_step * 1e-3)
+    # the same K iterations again WITHOUT the nvidia-smi sampler thread: its driver queries stall the launching thread
+    # (that is the gap between wall_ms_per_step and the device time above; the device-timed value is unaffected)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.run(K)
+    ctx.sync()
+    torch.cuda.synchronize()
+    wall_quiet = time.perf_counter() - t0
 
     # ---------------- per-kernel profile (separate, untimed pass) ----------------
     ctx.set_profile(True)
@@ -295,10 +333,12 @@ def main():
         kern[k]["fp64_tflops"] = alg[k]["flops"] / d / 1e12
         kern[k]["fp64_frac"] = kern[k]["fp64_tflops"] / f64_peak
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tp) and n == CFG["n"]:
-        with open(tp) as f:
-            traffic = json.load(f).get(dom)
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp) and n == CFG["n"]:
+            with open(tp) as f:
+                traffic = json.load(f).get(dom)
+            break
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kern[dom]["hbm_frac"], "traffic": traffic, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": alg[dom]["bytes"], "ms_per_launch": kern[dom]["ms_per_launch"],
@@ -335,7 +375,7 @@ def main():
             t_e = float(t.item())
         h2d = 8.0 * (2 * G * n + G * (K0 + 2 * M0) + M0 * K0 + M0 + n * M0) + 4.0 * n
         d2h = 8.0 * (G * n + n * M0 + n * K0 * M0 + M0 * K0 * K0 + 2 * G * M0 + G * K0 + M0 * K0 + M0 + 2 * G + it_e + 1)
-        e2e = {"value": world * nnz0 * CFG["num_mc"] * (it_e - 1) / t_e, "unit": UNIT,
+        e2e = {"value": nnz_all * CFG["num_mc"] * (it_e - 1) / t_e, "unit": UNIT,
                "h2d_bytes_per_step": h2d / it_e, "d2h_bytes_per_step": d2h / it_e,
                "em_iters_per_sec": it_e / t_e, "iters_per_call": it_e, "call_seconds": t_e,
                "note": "one simples_em_impute call: H2D(Y, Y0, params) + iter EM iterations (it=1 does not sample) + D2H(return list)"}
@@ -347,15 +387,18 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": ("NON-HEADLINE override (--K0/--M0/--cells): " if CFG.get("override") or n != CFG["n"] else "")
-                                       + f"C3: synthetic zero-inflated log-counts {n // 1000}k cells x {G / 1000:g}k genes per GPU, K0={K0}, M0={M0}, "
-                                       "impt_it=1, num_mc=3 (steady-state EM iteration)",
-                           "cells_per_gpu": n, "genes": G, "K0": K0, "M0": M0, "zero_fraction": rho,
-                           "l2": "inputs (1.6 GB Y per GPU) exceed L2; no flush needed",
-                           "parallelism": f"cells sharded over {world} GPU(s), one NCCL all-reduce per iteration"},
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": mode if world > 1 else "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": ("NON-HEADLINE override (--K0/--M0/--genes/--cells): " if CFG.get("override") or args.cells is not None else "")
+                                       + f"C3: synthetic zero-inflated log-counts, {n_total // 1000}k cells x {G / 1000:g}k genes in total, K0={K0}, M0={M0}, "
+                                       f"impt_it=1, num_mc=3 (steady-state EM iteration); {mode} scaling: {n} cells on each of {world} GPU(s)",
+                           "cells_total": n_total, "cells_per_gpu": n, "genes": G, "K0": K0, "M0": M0, "zero_fraction": rho,
+                           "l2": (f"Y is {8e-9 * G * n:.2f} GB per GPU; the L2 (126 MB) is flushed between kernels by the kernels' own "
+                                  "streaming of Y" if 8.0 * G * n > 4 * 126e6 else
+                                  f"Y is only {8e-9 * G * n:.2f} GB per GPU: partly L2-resident between passes (stated, not flushed)"),
+                           "parallelism": f"cells sharded over {world} GPU(s), one NCCL all-reduce per iteration issued inside the library"},
                 "em_iters_per_sec": 1e3 / ms_per_step, "wall_ms_per_step": wall * 1e3 / K,
+                "wall_ms_per_step_without_clock_sampler": wall_quiet * 1e3 / K,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern,
                 "cpu_baseline": cpu, "e2e": e2e, "loglik_last": float(ll[-1]) if len(ll) else None}
         _emit(line)

@@ -159,6 +159,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.BM, size_t(ldG) * d.QS));
     CKR(c->dalloc(&s.gv, size_t(ldG) * 4));
     CKR(c->dalloc(&s.mc_counter, 1));
+    CKR(c->dalloc(&s.part_prep, prep_scratch_doubles(d, c->NS_max)));
     {   // SIMPLES_FUSED_MC=1 selects the fused sweep + projection kernel (k_mcpass.cuh).  It is parity-green but measured
         // slower than the separate kernels at C3 (2.6 ms vs 1.8 + 0.36 ms per MC pass, profiles/r02_notes.md), so it is opt-in.
         const char* e = getenv("SIMPLES_FUSED_MC");
@@ -312,7 +313,7 @@ int run_prep(simples_ctx* c) {
     DevState& s = c->s;
     P p(c, KC_PREP, 2);
     PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.igs, s.cc, 0,
-                s.BM, s.gv};
+                s.BM, s.gv, s.part_prep};
     if (c->profile) {                      // serial on the main stream so the per-class events mean something
         launch_prep(pa, c->stream, c->stream);
     } else {
@@ -506,6 +507,7 @@ int em_iteration(simples_ctx* c) {
         ma.pi_alpha = c->pi_alpha;
         ma.do_lambda = c->max_lambda && it >= c->est_lam;
         ma.compat_priorb_prev = (c->compat & SIMPLES_COMPAT_PRIORB_PREV) != 0;
+        ma.debug = getenv("SIMPLES_TRACE") != nullptr;
         launch_mstep(ma, c->stream);
     }
     CK(cudaGetLastError());

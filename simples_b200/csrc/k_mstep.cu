@@ -92,8 +92,8 @@ __device__ bool lasso_polish(const double* A, int K, double rhs, double kappa, d
 // min 0.5 b'Ab - rhs'b + kappa |b|_1 : cyclic coordinate descent from 0 (glmnet's start) + exact polish.
 __device__ int g_lasso_dbg[4];   // SIMPLES_TRACE diagnostics: [0] solves, [1] total CD sweeps, [2] max sweeps, [3] capped
 
-__device__ __forceinline__ void lasso_note(int sweeps, int lane) {
-    if (lane == 0) {
+__device__ __forceinline__ void lasso_note(int sweeps, int lane, int debug) {
+    if (debug && lane == 0) {     // 4 same-address atomics per gene serialise in L2: diagnostics only (SIMPLES_TRACE)
         atomicAdd(&g_lasso_dbg[0], 1);
         atomicAdd(&g_lasso_dbg[1], sweeps);
         atomicMax(&g_lasso_dbg[2], sweeps);
@@ -101,7 +101,8 @@ __device__ __forceinline__ void lasso_note(int sweeps, int lane) {
     }
 }
 
-__device__ double lasso_solve(const double* A, int K, double rhs, double kappa, double* L, double* xs, int* idx, int lane) {
+__device__ double lasso_solve(const double* A, int K, double rhs, double kappa, double* L, double* xs, int* idx, int lane,
+                              int debug) {
     double b = 0.0, r = rhs;
     const bool kl = lane < K;
     unsigned pat_p = 0u, pat_n = 0u, fail_p = ~0u, fail_n = ~0u;
@@ -133,7 +134,7 @@ __device__ double lasso_solve(const double* A, int K, double rhs, double kappa, 
         const bool fresh = !(np == fail_p && nn == fail_n) || sweep - last_fail >= 16;
         if (done || (stable >= 2 && fresh)) {
             if (lasso_polish(A, K, rhs, kappa, b, L, xs, idx, lane) || done) {
-                lasso_note(sweep + 1, lane);
+                lasso_note(sweep + 1, lane, debug);
                 return b;
             }
             fail_p = np;
@@ -141,7 +142,7 @@ __device__ double lasso_solve(const double* A, int K, double rhs, double kappa, 
             last_fail = sweep;
         }
     }
-    lasso_note(20000, lane);
+    lasso_note(20000, lane, debug);
     return b;
 }
 
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(GW * 32) k_gene_solve(MstepArgs a) {
             kappa = a.penl * var;
             A = Al;
         }
-        const double b = lasso_solve(A, K0, rhs, kappa, L, sxs + warp * K0, sidx + warp * K0, lane);
+        const double b = lasso_solve(A, K0, rhs, kappa, L, sxs + warp * K0, sidx + warp * K0, lane, a.debug);
         // sg = (sum_m D2 - 2 nb.(sum_m bm) + nb' (sum_m C_m) nb + 1) / (n + 3)
         double ab = 0.0;
         for (int k = 0; k < K0; ++k) {
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(GW * 32) k_lq_solve(LqSolveArgs a) {
     const double sumY2 = warp_sum(ml ? U2 / sgm : 0.0);
     const double var = (sumY2 - sumY * sumY / N) / (N - 1.0);
     const double kappa = a.penl / var;
-    const double b = lasso_solve(Al, K0, rhs, kappa, sL + warp * KK, sxs + warp * K0, sidx + warp * K0, lane);
+    const double b = lasso_solve(Al, K0, rhs, kappa, sL + warp * KK, sxs + warp * K0, sidx + warp * K0, lane, 0);
     double ab_m = 0.0;                                 // lane m: a_m'b
     for (int k = 0; k < K0; ++k) {
         const double bk = __shfl_sync(0xffffffffu, b, k);

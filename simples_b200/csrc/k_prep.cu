@@ -46,83 +46,96 @@ __global__ void k_build_ops(PrepArgs a) {
     for (int c = K0; c < d.FS; ++c) qs[c] = 0.0;
 }
 
-constexpr int GT = 256;  // genes per smem tile
+constexpr int GT = 64;   // genes per CTA of k_gram
 
-__global__ void __launch_bounds__(256) k_cluster(PrepArgs a) {
+// Layout of one partial (and of the reduced vector): [G2 (NS K0 K0) | off (M0 K0) | offq (M0 K0) | cmu (M0) | lsig (NS)]
+__host__ __device__ inline int prep_ne(int K0, int M0, int NS) { return NS * K0 * K0 + 2 * M0 * K0 + M0 + NS; }
+
+// Gene-parallel part of cluster_prep: every CTA sums its GT genes' contributions to
+//   G2_s = B' diag(1/sigma_s) B,  off_m = mu_m'(B/sigma_cs(m)),  offq_m = mu_m'(B/sigma_q),  cmu_m = sum mu^2/sigma,
+//   lsig_s = sum log sigma_s.
+// With cluster-shared sigma (NS = 1) the Gram matrix is the SAME for every cluster and is formed once -- round 1 had each
+// of the M0 cluster CTAs walk all genes in eight barrier-separated tiles (0.28 ms, exposed in strongly scaled runs).
+__global__ void __launch_bounds__(128) k_gram(PrepArgs a, double* part) {
     extern __shared__ __align__(16) double sm[];
     const Dims& d = a.d;
-    const int K0 = d.K0, M0 = d.M0, ldG = d.ldG;
+    const int K0 = d.K0, M0 = d.M0, NS = d.NS, ldG = d.ldG;
+    const int qcol = (NS == 1) ? 0 : M0 - 1;        // sigma column of the stale beta2 (Q1)
+    double* sB = sm;                  // [GT][K0]
+    double* sI = sB + GT * K0;        // [GT][NS]  1/sigma_s
+    double* sMu = sI + GT * NS;       // [GT][M0]
+    double* sL = sMu + GT * M0;       // [GT][NS]  log sigma_s
+    const int g0 = blockIdx.x * GT;
+    for (int idx = threadIdx.x; idx < GT * K0; idx += blockDim.x) {
+        const int r = idx / K0;
+        sB[idx] = (g0 + r < ldG) ? a.beta[size_t(g0) * K0 + idx] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < GT * M0; idx += blockDim.x) {
+        const int r = idx / M0;
+        sMu[idx] = (g0 + r < ldG) ? a.mu[size_t(g0) * M0 + idx] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < GT * NS; idx += blockDim.x) {
+        const int r = idx / NS, sc = idx - r * NS;
+        const double sg = (g0 + r < ldG) ? a.sigma[size_t(g0 + r) * M0 + sc] : 1.0;
+        sI[idx] = 1.0 / sg;
+        sL[idx] = log(sg);
+    }
+    __syncthreads();
+    const int nG2 = NS * K0 * K0, nOff = M0 * K0, NE = prep_ne(K0, M0, NS);
+    double* out = part + size_t(blockIdx.x) * NE;
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+        double s = 0.0;
+        if (e < nG2) {
+            const int sc = e / (K0 * K0), jk = e - sc * K0 * K0, j = jk / K0, k = jk - j * K0;
+            for (int r = 0; r < GT; ++r) s = fma(sB[r * K0 + j] * sI[r * NS + sc], sB[r * K0 + k], s);
+        } else if (e < nG2 + 2 * nOff) {
+            const int f = e - nG2, which = f / nOff, mk = f - which * nOff, m = mk / K0, k = mk - m * K0;
+            const int sc = which ? qcol : ((NS == 1) ? 0 : m);
+            for (int r = 0; r < GT; ++r) s = fma(sMu[r * M0 + m] * sI[r * NS + sc], sB[r * K0 + k], s);
+        } else if (e < nG2 + 2 * nOff + M0) {
+            const int m = e - nG2 - 2 * nOff, sc = (NS == 1) ? 0 : m;
+            for (int r = 0; r < GT; ++r) s = fma(sMu[r * M0 + m] * sMu[r * M0 + m], sI[r * NS + sc], s);
+        } else {
+            const int sc = e - nG2 - 2 * nOff - M0;
+            for (int r = 0; r < GT; ++r) s += sL[r * NS + sc];
+        }
+        out[e] = s;
+    }
+}
+
+// Per-cluster part: fixed-order sum of the k_gram partials, then the K0 x K0 linear algebra by one warp.
+__global__ void __launch_bounds__(128) k_cluster(PrepArgs a, const double* part, int nparts) {
+    extern __shared__ __align__(16) double sm[];
+    const Dims& d = a.d;
+    const int K0 = d.K0, M0 = d.M0, NS = d.NS;
     const int m = blockIdx.x;
-    const int cs = (d.NS == 1) ? 0 : m;
-    const int qcol = (d.NS == 1) ? 0 : M0 - 1;    // sigma column of the stale beta2 (Q1)
-    double* sB = sm;                 // [GT][K0]
-    double* sw = sB + GT * K0;       // [GT] 1/sigma_m
-    double* smw = sw + GT;           // mu/sigma_m
-    double* smq = smw + GT;          // mu/sigma_q
-    double* sm2 = smq + GT;          // mu^2/sigma_m
-    double* sls = sm2 + GT;          // log sigma_m
-    double* sA = sls + GT;           // [K0][K0]
+    const int cs = (NS == 1) ? 0 : m;
+    double* sA = sm;                 // [K0][K0]
     double* sLi = sA + K0 * K0;      // [K0][K0]
     double* sV = sLi + K0 * K0;      // [K0][K0]
     double* sM = sV + K0 * K0;       // [K0][K0]
     double* sRed = sM + K0 * K0;     // [2]
-
-    const int NE = K0 * K0 + 2 * K0 + 2;
-    double acc[5] = {0, 0, 0, 0, 0};   // NE <= 1090 <= 5 * 256
-    for (int g0 = 0; g0 < ldG; g0 += GT) {
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < GT * K0; idx += blockDim.x)
-            sB[idx] = (g0 + idx / K0 < ldG) ? a.beta[size_t(g0) * K0 + idx] : 0.0;      // rows past ldG contribute 0
-        if (threadIdx.x < GT) {
-            const int g = g0 + threadIdx.x;
-            const bool v = g < ldG;
-            const double sg = v ? a.sigma[size_t(g) * M0 + cs] : 1.0, sq = v ? a.sigma[size_t(g) * M0 + qcol] : 1.0;
-            const double mu = v ? a.mu[size_t(g) * M0 + m] : 0.0;
-            sw[threadIdx.x] = 1.0 / sg;
-            smw[threadIdx.x] = mu / sg;
-            smq[threadIdx.x] = mu / sq;
-            sm2[threadIdx.x] = mu * mu / sg;
-            sls[threadIdx.x] = log(sg);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const int e = threadIdx.x + q * 256;
-            if (e >= NE) continue;
-            double s = acc[q];
-            if (e < K0 * K0) {
-                const int j = e / K0, k = e - j * K0;
-                for (int r = 0; r < GT; ++r) s = fma(sB[r * K0 + j] * sw[r], sB[r * K0 + k], s);
-            } else if (e < K0 * K0 + K0) {
-                const int k = e - K0 * K0;
-                for (int r = 0; r < GT; ++r) s = fma(smw[r], sB[r * K0 + k], s);
-            } else if (e < K0 * K0 + 2 * K0) {
-                const int k = e - K0 * K0 - K0;
-                for (int r = 0; r < GT; ++r) s = fma(smq[r], sB[r * K0 + k], s);
-            } else if (e == K0 * K0 + 2 * K0) {
-                for (int r = 0; r < GT; ++r) s += sm2[r];
-            } else {
-                for (int r = 0; r < GT; ++r) s += sls[r];
-            }
-            acc[q] = s;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int e = threadIdx.x + q * 256;
-        if (e >= NE) continue;
+    double* sW = sRed + 2;           // [32] rotation parameters of one Jacobi round
+    const int nG2 = NS * K0 * K0, nOff = M0 * K0, NE = prep_ne(K0, M0, NS);
+    auto total = [&](int e) {
+        double s = 0.0;
+        for (int p = 0; p < nparts; ++p) s += part[size_t(p) * NE + e];
+        return s;
+    };
+    for (int e = threadIdx.x; e < K0 * K0 + 2 * K0 + 2; e += blockDim.x) {
         if (e < K0 * K0) {
             const int j = e / K0, k = e - j * K0;
-            sA[e] = acc[q] + ((j == k) ? 1.0 / a.lam[m * K0 + k] : 0.0);
+            sA[e] = total(cs * K0 * K0 + e) + ((j == k) ? 1.0 / a.lam[m * K0 + k] : 0.0);
         } else if (e < K0 * K0 + K0) {
-            a.cc.off[m * K0 + (e - K0 * K0)] = acc[q];
+            const int k = e - K0 * K0;
+            a.cc.off[m * K0 + k] = total(nG2 + m * K0 + k);
         } else if (e < K0 * K0 + 2 * K0) {
-            a.cc.offq[m * K0 + (e - K0 * K0 - K0)] = acc[q];
+            const int k = e - K0 * K0 - K0;
+            a.cc.offq[m * K0 + k] = total(nG2 + nOff + m * K0 + k);
         } else if (e == K0 * K0 + 2 * K0) {
-            a.cc.cmu[m] = acc[q];
+            a.cc.cmu[m] = total(nG2 + 2 * nOff + m);
         } else {
-            sRed[0] = acc[q];
+            sRed[0] = total(nG2 + 2 * nOff + M0 + cs);
         }
     }
     __syncthreads();
@@ -153,21 +166,29 @@ __global__ void __launch_bounds__(256) k_cluster(PrepArgs a) {
             }
         }
         __syncwarp();
-        warp_sym_sqrt(sA, sV, sLi, K0, lane);
+        warp_sym_sqrt(sA, sV, sLi, sW, K0, lane);
         for (int e = lane; e < K0 * K0; e += 32) a.cc.Mh[size_t(m) * K0 * K0 + e] = sLi[e];
     }
 }
 
 }  // namespace
 
+int prep_parts(int ldG) { return (ldG + GT - 1) / GT; }
+size_t prep_scratch_doubles(const Dims& d, int NS_max) { return size_t(prep_parts(d.ldG)) * prep_ne(d.K0, d.M0, NS_max); }
+
 void launch_prep(const PrepArgs& a, cudaStream_t st, cudaStream_t st_cluster) {
     // the GEMM operands (needed by estep_project / impute_sweep) and the per-cluster constants (needed only by
     // cell_post) are independent: the latter may run on a side stream and overlap the first projection.
     k_build_ops<<<(a.d.ldG + 127) / 128, 128, 0, st>>>(a);
-    const int K0 = a.d.K0;
-    const size_t smem = sizeof(double) * (size_t(GT) * K0 + 5 * GT + 4 * K0 * K0 + 2);
-    ensure_dyn_smem_k(k_cluster, smem);
-    k_cluster<<<a.d.M0, 256, smem, st_cluster>>>(a);
+    const int K0 = a.d.K0, M0 = a.d.M0, NS = a.d.NS;
+    const int nparts = prep_parts(a.d.ldG);
+    {
+        const size_t smem = sizeof(double) * size_t(GT) * (K0 + 2 * NS + M0);
+        ensure_dyn_smem_k(k_gram, smem);
+        k_gram<<<nparts, 128, smem, st_cluster>>>(a, a.part_prep);
+    }
+    const size_t smem = sizeof(double) * (4 * size_t(K0) * K0 + 2 + 32);
+    k_cluster<<<M0, 128, smem, st_cluster>>>(a, a.part_prep, nparts);
 }
 
 }  // namespace sb

@@ -69,43 +69,91 @@ __device__ inline void warp_chol_solve(const double* L, double* b, int K, int la
     __syncwarp();
 }
 
-// Symmetric square root of SPD matrix A (K x K, smem) -> R.  A is destroyed, V is K x K scratch.
-__device__ inline void warp_sym_sqrt(double* A, double* V, double* R, int K, int lane) {
+// Symmetric square root of SPD matrix A (K x K, smem) -> R.  A is destroyed, V is K x K scratch, W is scratch for
+// 2 * 16 doubles (rotation cosines / sines of one round).
+// Jacobi eigen-decomposition with the round-robin ("chess tournament") PARALLEL ordering: a sweep is K'-1 rounds
+// (K' = K rounded up to even) of K'/2 disjoint pivot pairs; the rotations of a round commute in exact arithmetic up to
+// the usual Jacobi coupling, so their parameters are computed together by K'/2 lanes and the column / row updates of
+// all pairs are spread over the warp.  A round costs three warp barriers instead of three per rotation (the cyclic
+// ordering made cluster_prep the longest replicated kernel of a strongly scaled run: profiles/r02_notes.md).
+__device__ inline void warp_sym_sqrt(double* A, double* V, double* R, double* W, int K, int lane) {
     for (int e = lane; e < K * K; e += 32) V[e] = ((e / K) == (e % K)) ? 1.0 : 0.0;
     __syncwarp();
+    const int Ke = (K + 1) & ~1, H = Ke >> 1;          // H <= 16 pairs per round
+    double* Wc = W;
+    double* Ws = W + 16;
     for (int sweep = 0; sweep < 30; ++sweep) {
-        int nrot = 0;
-        for (int p = 0; p < K - 1; ++p) {
-            for (int q = p + 1; q < K; ++q) {
-                const double apq = A[p * K + q];
-                const double app = A[p * K + p], aqq = A[q * K + q];
-                __syncwarp();
-                // converged pair: the rotation would not change the diagonal in double precision
-                if (fabs(apq) <= 4e-16 * sqrt(fabs(app * aqq)) || fabs(apq) <= 1e-300) continue;
-                ++nrot;
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-                if (lane < K) {   // columns p, q
-                    const int i = lane;
-                    const double aip = A[i * K + p], aiq = A[i * K + q];
-                    A[i * K + p] = c * aip - s * aiq;
-                    A[i * K + q] = s * aip + c * aiq;
-                    const double vip = V[i * K + p], viq = V[i * K + q];
-                    V[i * K + p] = c * vip - s * viq;
-                    V[i * K + q] = s * vip + c * viq;
+        unsigned any = 0u;
+        for (int r = 0; r < Ke - 1; ++r) {
+            // pair of slot i in round r
+            auto pair_of = [&](int i, int& p, int& q) {
+                int a, b;
+                if (i == 0) {
+                    a = Ke - 1;
+                    b = r;
+                } else {                       // (r + i) mod (Ke - 1), (r - i) mod (Ke - 1) without divisions
+                    a = r + i;
+                    if (a >= Ke - 1) a -= Ke - 1;
+                    b = r - i;
+                    if (b < 0) b += Ke - 1;
                 }
-                __syncwarp();
-                if (lane < K) {   // rows p, q
-                    const int j = lane;
-                    const double apj = A[p * K + j], aqj = A[q * K + j];
-                    A[p * K + j] = c * apj - s * aqj;
-                    A[q * K + j] = s * apj + c * aqj;
+                p = a < b ? a : b;
+                q = a < b ? b : a;
+            };
+            bool rot = false;
+            if (lane < H) {
+                int p, q;
+                pair_of(lane, p, q);
+                double c = 1.0, sn = 0.0;
+                if (q < K) {
+                    const double apq = A[p * K + q], app = A[p * K + p], aqq = A[q * K + q];
+                    // converged pair: the rotation would not change the diagonal in double precision
+                    if (!(fabs(apq) <= 4e-16 * sqrt(fabs(app * aqq)) || fabs(apq) <= 1e-300)) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(tt * tt + 1.0);
+                        sn = tt * c;
+                        rot = true;
+                    }
                 }
-                __syncwarp();
+                Wc[lane] = c;
+                Ws[lane] = sn;
             }
+            const unsigned rb = __ballot_sync(0xffffffffu, rot);
+            any |= rb;
+            if (rb == 0u) continue;            // warp-uniform
+            __syncwarp();
+            for (int e = lane; e < 32 * H; e += 32) {     // columns: A <- A J, V <- V J  (lane = row i, one pair per step)
+                const int i = lane, sl = e >> 5;
+                if (i >= K) continue;
+                int p, q;
+                pair_of(sl, p, q);
+                const double c = Wc[sl], sn = Ws[sl];
+                if (q < K && sn != 0.0) {
+                    const double aip = A[i * K + p], aiq = A[i * K + q];
+                    A[i * K + p] = c * aip - sn * aiq;
+                    A[i * K + q] = sn * aip + c * aiq;
+                    const double vip = V[i * K + p], viq = V[i * K + q];
+                    V[i * K + p] = c * vip - sn * viq;
+                    V[i * K + q] = sn * vip + c * viq;
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < 32 * H; e += 32) {     // rows: A <- J' A  (lane = column j)
+                const int j = lane, sl = e >> 5;
+                if (j >= K) continue;
+                int p, q;
+                pair_of(sl, p, q);
+                const double c = Wc[sl], sn = Ws[sl];
+                if (q < K && sn != 0.0) {
+                    const double apj = A[p * K + j], aqj = A[q * K + j];
+                    A[p * K + j] = c * apj - sn * aqj;
+                    A[q * K + j] = sn * apj + c * aqj;
+                }
+            }
+            __syncwarp();
         }
-        if (nrot == 0) break;
+        if (any == 0u) break;
     }
     __syncwarp();
     for (int e = lane; e < K * K; e += 32) {

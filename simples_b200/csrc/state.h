@@ -89,6 +89,7 @@ struct DevState {
     double *part_gene; // per-CTA priorB partials
     int ncta_gene;
     double *part_mu;   // k_mu_acc partial sums
+    double *part_prep; // k_gram partial sums
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute: remembered per (kernel, current device),
@@ -181,8 +182,10 @@ struct PrepArgs {
     Dims d; const double *beta, *sigma, *mu, *lam, *pi, *gmean, *gsd;
     double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs; ClusterConsts cc; int stale_q;
     double *BM, *gv;     // may be nullptr
+    double* part_prep;   // k_gram partials: prep_scratch_doubles()
 };
 void launch_prep(const PrepArgs& a, cudaStream_t st, cudaStream_t st_cluster);
+size_t prep_scratch_doubles(const Dims& d, int NS_max);
 
 struct MstepArgs {
     Dims d;
@@ -196,6 +199,7 @@ struct MstepArgs {
     double *part_mu;          // [M0][mu_gene_splits][K0*K0 + K0] partial sums of the mu update
     double penl, sigma0, pi_alpha;
     int do_lambda, compat_priorb_prev;
+    int debug;                // count coordinate-descent sweeps (SIMPLES_TRACE)
 };
 void launch_mstep(const MstepArgs& a, cudaStream_t st);
 int mstep_gene_ctas(int G);

@@ -262,7 +262,7 @@ def test_global_cell_index_64bit_and_seed_hi(sb):
     got = sb.EM_impute(*em_args(st, M0, K0, 3), comm=sh, **kw)
     ref = O.em_impute_fast(*em_args(st, M0, K0, 3), cell0=off, **kw)
     assert_em_close(got, ref, M0)
-    assert sh.calls == 2 + 3        # gene means, default mu, one per EM iteration
+    assert sh.calls == 1 + 2 + 3    # input-validation agreement, gene means, default mu, one per EM iteration
     other = O.em_impute_fast(*em_args(st, M0, K0, 3), cell0=7, **kw)
     assert rel(other["Y"], ref["Y"]) > 1e-3       # the high word really changes the stream
 
