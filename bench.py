@@ -218,10 +218,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-iter", type=int, default=10)
+    ap.add_argument("--config", default="C3", choices=["C3", "C4"],
+                    help="C3 = the metric's configuration (default); C4 = BASELINE configs[3]: 1M cells x 5k genes, K0 = M0 = 20, "
+                         "cells sharded over the ranks (meant for --gpus 8: 125k cells = 5 GB of Y per rank)")
     ap.add_argument("--K0", type=int, default=None, help="override the number of factors (non-headline runs, e.g. C5)")
     ap.add_argument("--M0", type=int, default=None, help="override the number of clusters (non-headline runs)")
     ap.add_argument("--genes", type=int, default=None, help="override the number of genes (non-headline runs, e.g. a C4 shard)")
     args = ap.parse_args()
+    if args.config == "C4":
+        CFG.update(n=1_000_000, G=5000, K=20, MC=20, K0=20, M0=20)
+        CFG["name"] = "C4"
     if args.genes is not None:
         CFG["G"] = args.genes
         CFG["override"] = True
@@ -386,11 +392,11 @@ def main():
         cpu = cpu_baseline_sample()
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        line = {"metric": METRIC if CFG.get("name", "C3") == "C3" else METRIC.replace("100k cells x 2k genes, K0=M0=10", "1M cells x 5k genes, K0=M0=20"), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": mode if world > 1 else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": ("NON-HEADLINE override (--K0/--M0/--genes/--cells): " if CFG.get("override") or args.cells is not None else "")
-                                       + f"C3: synthetic zero-inflated log-counts, {n_total // 1000}k cells x {G / 1000:g}k genes in total, K0={K0}, M0={M0}, "
+                                       + f"{CFG.get('name', 'C3')}: synthetic zero-inflated log-counts, {n_total // 1000}k cells x {G / 1000:g}k genes in total, K0={K0}, M0={M0}, "
                                        f"impt_it=1, num_mc=3 (steady-state EM iteration); {mode} scaling: {n} cells on each of {world} GPU(s)",
                            "cells_total": n_total, "cells_per_gpu": n, "genes": G, "K0": K0, "M0": M0, "zero_fraction": rho,
                            "l2": (f"Y is {8e-9 * G * n:.2f} GB per GPU; the L2 (126 MB) is flushed between kernels by the kernels' own "

@@ -10,6 +10,7 @@
 // Gene-chunk parameters (Qs, sds, 1/sds, pg, mean, 1/sd) are double-buffered in shared memory with
 // cp.async.
 #include <cmath>
+#include <cstdlib>
 
 #include "ptx.cuh"
 #include "rng.cuh"
@@ -355,16 +356,15 @@ void launch_sweep(SweepArgs a, cudaStream_t st) {
                         SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int) + 64;
     const int tiles = (a.d.n + SC - 1) / SC;
     const int resident = smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1);
-    // pick the gene split (1..4) that minimises wave quantisation for the resident CTAs per SM
-    int gsplit = 1;
+    // gridDim.y splits the gene range: more, smaller CTAs even out the tail of the last wave.  Measured on B200 at
+    // 12.5k-100k cells x 2000 genes (profiles/r02_notes.md): 5-8 parts are within 1 % of each other and up to 15 % faster
+    // than the wave-count model of round 1 at the small shards of a strongly scaled run; keep >= 8 chunks per CTA.
+    int gsplit = std::min(6, std::max(1, (a.d.ldG / SG) / 8));
     {
-        const double slots = double(resident) * NUM_SMS_B200;
-        double best = 1e30;
-        for (int gsp = 1; gsp <= 4; ++gsp) {
-            if ((a.d.ldG / SG) / gsp < 8) break;
-            const double w = tiles * double(gsp) / slots;
-            const double loss = std::ceil(w) / w + 0.01 * gsp;      // small penalty for per-CTA start-up
-            if (loss < best) { best = loss; gsplit = gsp; }
+        (void)resident;
+        if (const char* e = getenv("SIMPLES_SWEEP_GSPLIT")) {       // tuning override
+            const int v = atoi(e);
+            if (v >= 1 && (a.d.ldG / SG) / v >= 1) gsplit = v;
         }
     }
     const dim3 grid(tiles, gsplit);
