@@ -73,6 +73,10 @@ extern "C" {
 #define SIMPLES_COMPAT_MU_DIV_N     4u  /* Q3  default mu = Y z / n, :95      */
 #define SIMPLES_COMPAT_PRIORB_PREV  8u  /* Q5  tot[it] -= previous priorB     */
 #define SIMPLES_COMPAT_DEFAULT     15u
+/* Not a quirk but a mode, carried in the same word: the Monte-Carlo sweeps become deterministic -- most probable
+ * cluster, factor at its posterior mean, every zero entry set to its conditional expectation
+ * ms - sds p phi(r) / (p Phi(r) + 1 - p) (R/SIMPLE.R:59 hints at it; the reference itself samples).  EM_impute only. */
+#define SIMPLES_MODE_EXPECT        16u
 
 /* Sum `count` doubles at device pointer `dev_buf` over all ranks, in place,
  * ordered after prior work on `stream` (a cudaStream_t) and before later

@@ -492,7 +492,7 @@ def factor_means(Yc, beta, sigma, mu, Ms):
 
 def sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, gene_mean, gene_sd,
                  cutoff, seed, sweep, cell0=0, draw_membership=True, lower=-np.inf,
-                 upper=np.inf, clip=True):
+                 upper=np.inf, clip=True, expect=False):
     """One MC imputation sweep, R/EM_impute.R:163-199 / R/do_impute.R:107-136,
     with every random variate taken from the Philox tape.  Modifies Yc in
     place; returns the sampled membership (0-based) and factors."""
@@ -501,6 +501,20 @@ def sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, gene_mean,
     K0 = beta.shape[1]
     cells = np.arange(n, dtype=np.uint64) + np.uint64(cell0)
     U = cell_uniforms(seed, sweep, cells, 1 + K0)
+    if expect:
+        # deterministic companion (north_star "conditional-expectation imputation"): most probable cluster,
+        # factor at its posterior mean, every zero entry at its conditional expectation -- no variate is consumed
+        im = np.argmax(z, axis=1)
+        f = np.stack([Wm[m][i] for i, m in enumerate(im)]) if n else np.empty((0, K0))
+        gi, ci = np.nonzero(mask)
+        mm = im[ci]
+        ms = (mu[gi, mm] + np.einsum("ek,ek->e", beta[gi], f[ci])) * gene_sd[gi] + gene_mean[gi]
+        sds = np.sqrt(sigma[gi, mm]) * gene_sd[gi]
+        x = expected_impute(ms, sds, pg[gi, celltype0[ci]], cutoff)
+        if clip:
+            x = np.maximum(np.minimum(x, upper), lower)
+        Yc[gi, ci] = (x - gene_mean[gi]) / gene_sd[gi]
+        return im, f
     if draw_membership:
         cum = np.cumsum(z, axis=1)
         im = np.minimum((U[:, :1] >= cum).sum(axis=1), M0 - 1)               # :164
@@ -533,13 +547,12 @@ def sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, gene_mean,
 
 
 def expected_impute(ms, sds, p, cutoff):
-    """Closed-form E[x] of one zero entry (north_star's 'conditional
-    expectation'; hinted at in R/SIMPLE.R:59) -- used by distributional tests."""
+    """Closed-form E[x] of one zero entry (north_star's 'conditional expectation'; hinted at in R/SIMPLE.R:59):
+    E[x] = pd ms + (1 - pd) (ms - sds phi(r)/Phi(r)) with pd = (1-p)/(Phi(r) p + 1-p), r = (cutoff - ms)/sds.
+    Written as ms - sds p phi(r) / (p Phi(r) + 1 - p): the same number without the 0/0 of the Mills ratio in the tail."""
     r = (cutoff - ms) / sds
     prob = special.ndtr(r)
-    pd = (1 - p) / (prob * p + (1 - p))
-    mills = np.exp(-0.5 * r * r) / _SQRT2PI / np.maximum(prob, 1e-300)
-    return pd * ms + (1 - pd) * (ms - sds * mills)
+    return ms - sds * p * (np.exp(-0.5 * r * r) / _SQRT2PI) / (p * prob + (1 - p))
 
 
 # ----------------------------------------------------------------------------
@@ -710,7 +723,7 @@ def _mstep_literal(Yc, z, Wm, Ms, nz, beta, sigma, lam, mu, M0, K0, it, penl, ma
 
 def _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
                est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
-               seed, compat, literal, shards=None, trace=None, cell0=0):
+               seed, compat, literal, shards=None, trace=None, cell0=0, expect=False):
     pi_const = PI_REF if compat & COMPAT_PI else math.pi
     z = None if z is None else np.array(z, dtype=np.float64)
     Yc, gene_mean, gene_sd, mu = _prologue(Y, z, mu, M0, lower, upper, compat)
@@ -740,7 +753,7 @@ def _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, cel
             for _ in range(num_mc):                                          # :162
                 sample_sweep(Yc, mask, z, Wm, Ms, mu, beta, sigma, pg, celltype0, gene_mean,
                              gene_sd, cutoff, seed, sweep, cell0, draw_membership=(M0 > 1),
-                             lower=lower, upper=upper, clip=True)
+                             lower=lower, upper=upper, clip=True, expect=expect)
                 sweep += 1
                 if compat & COMPAT_STALE_DT:                                 # :202-213  (Q1)
                     ll, lik, sconst, _, _, _ = epass(Yc, beta, sigma, lam, mu, pi, pi_const,
@@ -786,12 +799,12 @@ def em_impute_ref(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=N
 def em_impute_fast(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=None, celltype=None,
                    penl=1, est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1,
                    num_mc=3, lower=-np.inf, upper=np.inf, seed=0, compat=COMPAT_DEFAULT,
-                   shards=None, trace=None, cell0=0):
+                   shards=None, trace=None, cell0=0, mode="sample"):
     """Same algorithm with the sufficient-statistic M-step; ``shards`` = list of
     cell boundaries emulating the multi-GPU partition + all-reduce."""
     return _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
                       est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
-                      seed, compat, literal=False, shards=shards, trace=trace, cell0=cell0)
+                      seed, compat, literal=False, shards=shards, trace=trace, cell0=cell0, expect=(mode == "expect"))
 
 
 # ----------------------------------------------------------------------------

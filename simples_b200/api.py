@@ -74,6 +74,9 @@ def _check_out(b, shape, order, name):
     return b
 
 
+MODE_EXPECT = 16     # SIMPLES_MODE_EXPECT (include/simples_b200.h)
+
+
 class _Comm:
     """Adapter: any object with ``allreduce_sum_(dev_ptr, count, stream)`` plus
     ``n_total`` / ``cell_offset`` (see simples_b200.dist.CellShard)."""
@@ -170,7 +173,8 @@ def _em_result(bufs, M0, iter):
 
 def EM_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu=None, celltype=None, penl=1,
               est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1, verbose=False, num_mc=3,
-              lower=-math.inf, upper=math.inf, *, seed=0, ref_compat=COMPAT_DEFAULT, comm=None, stream=None, out=None):
+              lower=-math.inf, upper=math.inf, *, seed=0, ref_compat=COMPAT_DEFAULT, comm=None, stream=None, out=None,
+              mode="sample"):
     """Monte-Carlo EM imputation on B200 -- drop-in for ``EM_impute`` (R/EM_impute.R:75-339).
 
     Returns a dict with the reference's list names in the reference's order:
@@ -179,9 +183,15 @@ def EM_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu=N
     undefined globals, R/EM_impute.R:327-329).  Keyword-only extras: ``seed``
     (Philox key replacing R's global RNG), ``ref_compat`` (quirk bits),
     ``comm`` (a simples_b200.dist.CellShard when cells are sharded over GPUs), ``out`` (optional dict of
-    pre-allocated output arrays, see ``em_out_shapes`` -- lets a caller keep results in pinned memory).
+    pre-allocated output arrays, see ``em_out_shapes`` -- lets a caller keep results in pinned memory),
+    ``mode``: ``"sample"`` (the reference's behaviour) or ``"expect"`` (deterministic companion: most probable cluster,
+    factor at its posterior mean, zero entries at their conditional expectation, cf. R/SIMPLE.R:59).
     """
     lib = _lib.load()
+    if mode not in ("sample", "expect"):
+        raise ValueError("mode must be 'sample' or 'expect'")
+    if mode == "expect":
+        ref_compat = int(ref_compat) | MODE_EXPECT
     a, keep, (G, n, _) = _em_args(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda_, pi, z, mu, celltype, penl,
                                   est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper, seed,
                                   ref_compat, comm, stream)

@@ -303,6 +303,7 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
         ca.ll_const = double(d.G) * std::log(2.0 * pi_const);
         ca.seed = c->seed;
         ca.sweep = c->sweep;
+        ca.expect = c->kind == 0 && (c->compat & SIMPLES_MODE_EXPECT) != 0;
         launch_cell(ca, c->stream);
     }
     CK(cudaGetLastError());
@@ -358,13 +359,16 @@ int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2) {
     sa.sweep = c->sweep;
     sa.rec1 = rec1;
     sa.rec2 = rec2;
+    sa.expect = c->kind == 0 && (c->compat & SIMPLES_MODE_EXPECT) != 0;
     launch_sweep(sa, c->stream);
     CK(cudaGetLastError());
     return SIMPLES_OK;
 }
 
 // fused MC pass: the sweep and the projection of the E-pass that follows it (cluster-shared sigma)
-bool use_fused_mc(const simples_ctx* c) { return c->fused_mc && c->s.d.NS == 1 && mcpass_supported(c->s.d); }
+bool use_fused_mc(const simples_ctx* c) {
+    return c->fused_mc && c->s.d.NS == 1 && mcpass_supported(c->s.d) && !(c->compat & SIMPLES_MODE_EXPECT);
+}
 
 int run_mcpass(simples_ctx* c, bool clip, double* rec1, double* rec2) {
     DevState& s = c->s;

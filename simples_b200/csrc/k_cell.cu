@@ -175,7 +175,14 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
         if (a.sample) {
             if (lane < 8) {
                 int im = 0;
-                if (a.draw_membership) {
+                if (a.expect) {                 // most probable cluster (first maximum)
+                    double best = zw[lane * M0];
+                    for (int m = 1; m < M0; ++m)
+                        if (zw[lane * M0 + m] > best) {
+                            best = zw[lane * M0 + m];
+                            im = m;
+                        }
+                } else if (a.draw_membership) {
                     double u0, u1;
                     cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + cell0 + lane), 0u, u0, u1);
                     double cum = 0.0;
@@ -281,6 +288,10 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
             for (int id = lane; id < 8 * K0; id += 32) {
                 const int r = id / K0, k = id - r * K0;
                 double ua, ub;
+                if (a.expect) {
+                    epw[r * KR + k] = 0.0;      // factor at its posterior mean
+                    continue;
+                }
                 cell_uniform_pair(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + cell0 + r), unsigned(1 + k) >> 1, ua, ub);
                 epw[r * KR + k] = qnorm(((1 + k) & 1) ? ub : ua);
             }

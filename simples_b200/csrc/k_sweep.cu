@@ -175,6 +175,24 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
         //   U : inside the band (~1e-5 of the entries) -> exact FP64 decision
         int nDc = 0, nS = 0, nU = 0;
         const int rounds = (total + 31) >> 5;
+        if (a.expect) {      // SIMPLES_MODE_EXPECT (warp-uniform): every entry gets its conditional expectation, no variates
+#pragma unroll 1
+            for (int e = lane; e < total; e += 32) {
+                const int code = list[e];
+                const int r = code >> 5, gl = code & 31;
+                const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
+                const double x = expect_entry(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct], a.cutoff);
+                double xx = x;
+                if (a.clip) {
+                    xx = fmin(xx, a.upper);
+                    xx = fmax(xx, a.lower);
+                }
+                a.Y[size_t(wc0 + r) * ldG + chunk * SG + gl] = (xx - b.gm[gl]) * b.igs[gl];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[2 + sb_]);
+            continue;
+        }
 #pragma unroll 2
         for (int it = 0; it < rounds; ++it) {
             const int e = it * 32 + lane;

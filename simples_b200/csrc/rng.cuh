@@ -127,6 +127,14 @@ static __device__ __noinline__ double sample_entry(double ms, double sds, double
 }
 
 
+// SIMPLES_MODE_EXPECT: E[x] = ms - sds p phi(r) / (p Phi(r) + 1 - p), r = (cutoff - ms) / sds (the Mills ratio of the
+// textbook form cancels against 1 - prob_drop, so the tail needs no special case).
+static __device__ __noinline__ double expect_entry(double ms, double sds, double isd, double p, double cutoff) {
+    const double r = (cutoff - ms) * isd;
+    const double phi = exp_mhalfsq(fabs(r)) * 0.398942280401432677939946059934;
+    return ms - sds * p * phi / fma(p, pnorm(r), 1.0 - p);
+}
+
 // x = ms + sds Phi^-1(|v|) for an entry whose quantile argument is already known (k_sweep, dense blocks);
 // v < 0 marks a truncated draw, clamped to the cutoff (R/EM_impute.R:191-192).
 static __device__ __noinline__ double quantile_draw(double ms, double sds, double cutoff, double v) {

@@ -117,6 +117,7 @@ struct CellArgs {
     double* part;         // [ncta][2*M0+1]: nz, c, tot
     int ncta;
     int update_z, stale_q, write_W, write_Vg, sample, draw_membership;
+    int expect;           // SIMPLES_MODE_EXPECT: membership = argmax z, factor = posterior mean (no draws)
     double ll_const;      // G * log(2 PI)
     unsigned long long seed;
     unsigned sweep;
@@ -133,6 +134,7 @@ struct SweepArgs {
     unsigned long long seed; unsigned sweep;
     uint32_t rk[20];       // Philox round keys, filled by launch_sweep
     double *rec1, *rec2;   // optional do_impute accumulators (same layout as Y), nullptr otherwise
+    int expect;            // SIMPLES_MODE_EXPECT: conditional expectation instead of a draw
 };
 void launch_sweep(SweepArgs a, cudaStream_t st);
 

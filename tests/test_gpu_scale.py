@@ -122,3 +122,20 @@ def test_single_process_multi_gpu_c_abi(sb):
         assert rel(two["Ef"][m], one["Ef"][m]) <= 1e-8
     assert abs(mi_two["loglik"] - mi_one["loglik"]) <= 1e-9 * abs(mi_one["loglik"])
     assert rel(mi_two["impt"], mi_one["impt"]) <= 1e-8 and rel(mi_two["EF"], mi_one["EF"]) <= 1e-8
+
+
+def test_expect_mode_matches_oracle_20k_cells(sb):
+    """mode = "expect" (SIMPLES_MODE_EXPECT): the deterministic companion of the Monte-Carlo sweep -- most probable
+    cluster, factor at its posterior mean, every zero entry at its conditional expectation.  No variate is consumed, so
+    this checks the whole sweep data path (mask, compaction, DMMA conditional means, stores, the E-passes on the updated
+    matrix, the M-step on it) at size independently of the Philox tape."""
+    K0 = M0 = 10
+    st = make_case(20000, 2000, 10, 10, K0, M0, seed=6)
+    kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=7, num_mc=2)
+    ref = O.em_impute_fast(*em_args(st, M0, K0, 3), mode="expect", **kw)
+    got = sb.EM_impute(*em_args(st, M0, K0, 3), mode="expect", **kw)
+    assert_em_close(got, ref, M0)
+    other = sb.EM_impute(*em_args(st, M0, K0, 3), mode="expect", **dict(kw, seed=99))
+    assert np.array_equal(other["Y"], got["Y"]) and np.array_equal(other["beta"], got["beta"])     # tape-independent
+    samp = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
+    assert not np.array_equal(samp["Y"], got["Y"])

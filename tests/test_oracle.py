@@ -441,3 +441,26 @@ def test_glmnet_compat_em_run_band():
     assert 1e-9 < dev["beta"] < 2e-3, dev          # not identical (the rule really stops early), but close
     assert dev["loglik"] < 1e-6 and dev["sigma"] < 1e-4 and dev["mu"] < 1e-3 and dev["z"] < 1e-2, dev
     assert np.array_equal(np.argmax(compat["z"], 1), np.argmax(exact["z"], 1))
+
+
+def test_expected_impute_is_the_sampler_mean_and_tail_safe():
+    """oracle.expected_impute (mode = "expect") in its cancellation-free form equals the textbook form where that is
+    computable, stays finite in the far tail, and is the mean of the sampler."""
+    ms = np.array([-3.0, -0.5, 0.05, 0.4, 2.0, 9.0, 40.0])
+    sds = np.array([0.3, 1.0, 0.7, 0.2, 1.5, 0.8, 0.5])
+    p, cutoff = 0.6, 0.1
+    got = O.expected_impute(ms, sds, p, cutoff)
+    r = (cutoff - ms) / sds
+    prob = special.ndtr(r)
+    pd = (1 - p) / (prob * p + 1 - p)
+    with np.errstate(all="ignore"):
+        text = pd * ms + (1 - pd) * (ms - sds * np.exp(-0.5 * r * r) / math.sqrt(2 * math.pi) / prob)
+    ok = prob > 1e-200
+    assert np.allclose(got[ok], text[ok], rtol=1e-12, atol=0)
+    assert np.all(np.isfinite(got)) and abs(got[-1] - ms[-1]) < 1e-12        # far tail: certain dropout, E[x] = ms
+    rng = np.random.default_rng(3)
+    ua, ub = rng.random(400000), rng.random(400000)
+    for i in (1, 2, 3):
+        drop = ua < pd[i]
+        x = np.where(drop, ms[i] + sds[i] * special.ndtri(ub), ms[i] + sds[i] * O.trunc_z(ub, r[i]))
+        assert abs(x.mean() - got[i]) < 5 * x.std() / math.sqrt(x.size)
