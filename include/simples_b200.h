@@ -304,6 +304,11 @@ SIMPLES_API int64_t simples_em_nnz0(simples_ctx *ctx);
 /* CUDA kernels enqueued by the last simples_em_run on this context. */
 SIMPLES_API int64_t simples_em_kernel_launches(simples_ctx *ctx);
 SIMPLES_API void simples_ctx_destroy(simples_ctx *ctx);
+/* Host-side helper, no GPU involved: bit j of mask[w * n + i] <=> Y0[32 w + j, i] <= cutoff for a column-major G x n
+ * HOST matrix (ceil(G/32) x n words).  This is the only thing the library needs from the observed matrix
+ * (R/EM_impute.R:173): when Y0 / dat live in host memory the entry points pack it with host threads while Y is uploading
+ * and only the mask crosses PCIe.  Returns the number of set bits, or a negative error code. */
+SIMPLES_API int64_t simples_pack_mask(const double *Y0, int32_t G, int32_t n, double cutoff, uint32_t *mask);
 
 #ifdef __cplusplus
 }

@@ -124,7 +124,7 @@ EXPORTS = [
     "simples_em_yimp0", "simples_bic",
     "simples_ctx_destroy",
     "simples_device_count", "simples_comm_unique_id", "simples_comm_init_rank", "simples_comm_destroy", "simples_comm_nranks",
-    "simples_nccl_version",
+    "simples_nccl_version", "simples_pack_mask",
 ]
 
 _lib = None
@@ -161,6 +161,8 @@ def load():
     lib.simples_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
     lib.simples_comm_init_rank.argtypes = [C.c_int, C.c_int, C.c_void_p]
     lib.simples_comm_destroy.restype = None
+    lib.simples_pack_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]
+    lib.simples_pack_mask.restype = C.c_int64
     lib.simples_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
     lib.simples_last_error.restype = C.c_char_p
     lib.simples_em_impute.argtypes = [C.POINTER(EmArgs), C.POINTER(EmOut)]

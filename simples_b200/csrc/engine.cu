@@ -3,6 +3,8 @@
 // this process's shard of cells.  The EM loop is enqueued on one CUDA stream without any
 // host <-> device synchronisation: all data-dependent decisions (lambda eligibility, lasso active
 // sets, priorB bookkeeping) happen on the device.
+#include <immintrin.h>
+
 #include <mutex>
 #include <thread>
 
@@ -122,6 +124,89 @@ int check_common(int G, int n, int M0, int K0, int MB) {
     return SIMPLES_OK;
 }
 
+// 0: device / managed memory, 1: pinned host memory, 2: pageable host memory
+int host_pointer_kind(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 2;
+    }
+    return at.type == cudaMemoryTypeUnregistered ? 2 : (at.type == cudaMemoryTypeHost ? 1 : 0);
+}
+
+int host_pack_threads() {
+    const int hw = int(std::max(1u, std::thread::hardware_concurrency()));
+    int T = std::min(16, std::max(1, hw / std::max(1, std::max(g_ndev, g_rank_nranks))));
+    if (const char* e = getenv("SIMPLES_HOST_THREADS")) T = std::max(1, atoi(e));
+    return T;
+}
+
+// Packing on the host pays when it beats sending the doubles: measured ~3 GB/s per thread against ~50 GB/s of PCIe from
+// pinned memory (and the packing overlaps the upload of Y), ~12 GB/s from pageable memory (R's own matrices).
+bool pack_mask_on_host(const void* Y0) {
+    if (getenv("SIMPLES_DEVICE_MASK")) return false;
+    const int kind = host_pointer_kind(Y0), T = host_pack_threads();
+    return kind == 2 ? T >= 2 : (kind == 1 ? T >= 8 : false);
+}
+
+// mask[w][i] bit j <=> Y0[32 w + j, i] <= cutoff, for the n cells of a column-major G x n host matrix (the device layout:
+// chunk-major words, row stride na).  Cell ranges are packed by host threads (SIMPLES_HOST_THREADS, default: the cores
+// divided by the ranks of the job, at most 16) with SSE2 / AVX2 compares; returns the number of set bits.  Pure
+// marshalling: the imputation itself has no CPU path.
+static inline uint32_t pack32_sse2(const double* y, double cutoff) {
+    const __m128d c = _mm_set1_pd(cutoff);
+    uint32_t m = 0;
+    for (int j = 0; j < 32; j += 2) m |= uint32_t(_mm_movemask_pd(_mm_cmple_pd(_mm_loadu_pd(y + j), c))) << j;
+    return m;
+}
+__attribute__((target("avx2"))) static uint32_t pack32_avx2(const double* y, double cutoff) {
+    const __m256d c = _mm256_set1_pd(cutoff);
+    uint32_t m = 0;
+    for (int j = 0; j < 32; j += 4) m |= uint32_t(_mm256_movemask_pd(_mm256_cmp_pd(_mm256_loadu_pd(y + j), c, _CMP_LE_OQ))) << j;
+    return m;
+}
+
+unsigned long long host_pack_mask(const double* Y0, int G, int n, int nwords, size_t na, double cutoff, uint32_t* mask) {
+    int T = host_pack_threads();
+    T = std::min(T, std::max(1, n / 256));
+    const bool avx2 = __builtin_cpu_supports("avx2");
+    std::vector<unsigned long long> cnt(T, 0);
+    auto work = [&](int t) {
+        // whole blocks of 16 cells per thread: the 16 words of one mask row are written as one 64-byte line (a word-by-
+        // word walk down a cell scatters 63 stores over rows that are 4 na bytes apart)
+        const size_t nb = (size_t(n) + 15) / 16;
+        const size_t i0 = std::min(size_t(n), (nb * t / T) * 16), i1 = std::min(size_t(n), (nb * (t + 1) / T) * 16);
+        unsigned long long c = 0;
+        for (size_t ib = i0; ib < i1; ib += 16) {
+            const int bc = int(std::min<size_t>(16, i1 - ib));
+            for (int w = 0; w < nwords; ++w) {
+                const int g0 = w * 32, len = std::min(32, G - g0);
+                uint32_t buf[16];
+                for (int ii = 0; ii < bc; ++ii) {
+                    const double* y = Y0 + (ib + ii) * size_t(G) + g0;
+                    uint32_t m = 0;
+                    if (len == 32) {
+                        m = avx2 ? pack32_avx2(y, cutoff) : pack32_sse2(y, cutoff);
+                    } else {
+                        for (int j = 0; j < len; ++j) m |= uint32_t(y[j] <= cutoff) << j;
+                    }
+                    buf[ii] = m;
+                    c += __builtin_popcount(m);
+                }
+                memcpy(mask + size_t(w) * na + ib, buf, size_t(bc) * 4);
+            }
+        }
+        cnt[t] = c;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    unsigned long long tot = 0;
+    for (auto v : cnt) tot += v;
+    return tot;
+}
+
 // Allocate and upload everything EM and MI share.
 int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long n_total, long long cell_offset,
                  const double* Y, const double* Y0, const double* pg, const double* beta, const double* sigma,
@@ -200,10 +285,37 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     } else {
         CK(cudaMemcpy2DAsync(s.Y, size_t(ldG) * 8, Y, size_t(G) * 8, size_t(G) * 8, n, cudaMemcpyDefault, c->stream));
     }
-    for (size_t c0 = 0; c0 < size_t(n); c0 += cells_per_chunk) {
-        const size_t nc = std::min(cells_per_chunk, size_t(n) - c0);
-        CK(cudaMemcpyAsync(c->stage, Y0 + c0 * G, nc * G * 8, cudaMemcpyDefault, c->stream));
-        launch_build_mask(c->stage, s.mask, int(nc), int(c0), c->n_alloc, G, ldG, cutoff, c->d_nnz, c->stream);
+    // The observed matrix is needed only as the bit mask Y0 <= cutoff (26 MB at C3 against 1.6 GB of doubles):
+    //   * Y0 aliases Y            -> mask from the copy of Y that is already on the device;
+    //   * Y0 in HOST memory       -> packed by host threads while the DMA engine uploads Y, only the mask crosses PCIe
+    //                                (halves the H2D volume of a call; with pageable R matrices it also avoids a staged copy);
+    //   * Y0 in device memory     -> built chunk-wise by a kernel.
+    c->host_mask_ms = 0.0;
+    if (Y0 == Y) {
+        for (size_t c0 = 0; c0 < size_t(n); c0 += cells_per_chunk) {
+            const size_t nc = std::min(cells_per_chunk, size_t(n) - c0);
+            if (ldG == G) {
+                launch_build_mask(s.Y + c0 * ldG, s.mask, int(nc), int(c0), c->n_alloc, G, ldG, cutoff, c->d_nnz, c->stream);
+            } else {      // the kernel reads an unpadded [cells][G] chunk
+                CK(cudaMemcpy2DAsync(c->stage, size_t(G) * 8, s.Y + c0 * ldG, size_t(ldG) * 8, size_t(G) * 8, nc,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+                launch_build_mask(c->stage, s.mask, int(nc), int(c0), c->n_alloc, G, ldG, cutoff, c->d_nnz, c->stream);
+            }
+        }
+    } else if (pack_mask_on_host(Y0)) {
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<uint32_t> hm(size_t(nwords) * na, 0u);
+        const unsigned long long cnt = host_pack_mask(Y0, G, n, nwords, na, cutoff, hm.data());
+        c->host_mask_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        CK(cudaMemcpyAsync(s.mask, hm.data(), hm.size() * 4, cudaMemcpyDefault, c->stream));
+        CK(cudaMemcpyAsync(c->d_nnz, &cnt, 8, cudaMemcpyDefault, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   // hm goes out of scope
+    } else {
+        for (size_t c0 = 0; c0 < size_t(n); c0 += cells_per_chunk) {
+            const size_t nc = std::min(cells_per_chunk, size_t(n) - c0);
+            CK(cudaMemcpyAsync(c->stage, Y0 + c0 * G, nc * G * 8, cudaMemcpyDefault, c->stream));
+            launch_build_mask(c->stage, s.mask, int(nc), int(c0), c->n_alloc, G, ldG, cutoff, c->d_nnz, c->stream);
+        }
     }
     {
         std::vector<double> hb = to_rowmajor(beta, G, K0, ldG, 0.0);
@@ -592,6 +704,12 @@ void simples_shutdown(void) {
     g_ndev = 0;
 }
 
+// Host-side marshalling helper (no GPU involved): the bit mask the library derives from a HOST matrix of observed values.
+int64_t simples_pack_mask(const double* Y0, int32_t G, int32_t n, double cutoff, uint32_t* mask) {
+    if (!Y0 || !mask || G < 1 || n < 1) return fail(SIMPLES_EINVAL, "simples_pack_mask: bad arguments");
+    return (int64_t)host_pack_mask(Y0, G, n, (G + 31) / 32, size_t(n), cutoff, mask);
+}
+
 int simples_kernel_count(void) { return KC_COUNT; }
 const char* simples_kernel_name(int k) { return (k >= 0 && k < KC_COUNT) ? kKernelNames[k] : ""; }
 
@@ -872,6 +990,7 @@ int em_impute_one(const simples_em_args* a, simples_em_out* o, long long io_ld, 
     simples_ctx* c = nullptr;
     CKR(em_create_impl(a, &c, io_ld));
     c->write_shared = write_shared;
+    const double mask_ms = c->host_mask_ms;
     const auto t1 = clk::now();
     int r = simples_em_run(c, a->iter);
     if (r == SIMPLES_OK) r = simples_em_sync(c);
@@ -883,8 +1002,9 @@ int em_impute_one(const simples_em_args* a, simples_em_out* o, long long io_ld, 
     const auto t4 = clk::now();
     if (trace) {
         auto ms = [](clk::time_point x, clk::time_point y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
-        fprintf(stderr, "[simples_b200] em_impute(dev %d): create(H2D+prologue) %.1f ms, run(%d it) %.1f ms, fetch(D2H) %.1f ms, destroy %.1f ms\n",
-                t_device >= 0 ? t_device : g_device, ms(t0, t1), a->iter, ms(t1, t2), ms(t2, t3), ms(t3, t4));
+        fprintf(stderr, "[simples_b200] em_impute(dev %d): create(H2D+prologue) %.1f ms (host mask packing %.1f ms), run(%d it) %.1f ms, "
+                "fetch(D2H) %.1f ms, destroy %.1f ms\n",
+                t_device >= 0 ? t_device : g_device, ms(t0, t1), mask_ms, a->iter, ms(t1, t2), ms(t2, t3), ms(t3, t4));
     }
     return r;
 }

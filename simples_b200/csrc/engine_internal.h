@@ -25,6 +25,7 @@ extern int g_ndev;                      // devices this process drives (0 before
 extern int g_devs[SIMPLES_MAX_DEVICES];
 extern void* g_comms[SIMPLES_MAX_DEVICES];   // ncclComm_t per device (single-process multi-GPU)
 extern void* g_rank_comm;               // ncclComm_t of this process in a one-process-per-GPU job, or nullptr
+extern int g_rank_nranks;               // ranks of that job (0: none)
 int fail(int code, const std::string& msg);
 int nccl_load();
 int nccl_allreduce_cb(void* comm, double* dev_buf, size_t count, void* stream);
@@ -90,6 +91,7 @@ struct simples_ctx {
     int n_alloc = 0;
     int NS_max = 1;
     long long nnz0 = 0;
+    double host_mask_ms = 0.0;        // host time spent packing the Y0 <= cutoff mask (0: built on the device)
     CUtensorMap tmapY;                // Y as [n_alloc][ldG], box {16 genes, 128 cells}, SWIZZLE_128B
     CUtensorMap tmapY8;               // same, box {16 genes, 8 cells}: the per-warp tiles of the fused MC pass
     bool fused_mc = false;            // SIMPLES_FUSED_MC=1: fused impute_sweep + estep_project kernel for the MC passes (opt-in)
@@ -213,6 +215,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
 bool sigma_is_shared(const double* sigma, int G, int M0);
 int upload_z(simples_ctx* c, const double* z);
 int agree_all_ranks(simples_ctx* c, long long* count);
+unsigned long long host_pack_mask(const double* Y0, int G, int n, int nwords, size_t na, double cutoff, uint32_t* mask);
 int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_membership, bool write_W, bool write_Vg,
            double pi_const, bool have_P = false);
 int run_prep(simples_ctx* c);

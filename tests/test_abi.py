@@ -106,3 +106,29 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dp, f)) as fh:
                     src = fh.read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+
+
+def test_host_mask_packing_matches_numpy(built_lib):
+    """simples_pack_mask (host threads + SSE2/AVX2 compares, no GPU): bit j of word [w][i] <=> Y0[32 w + j, i] <= cutoff,
+    including NaN (never masked), +-0, values exactly at the cutoff, and a ragged last word."""
+    import ctypes as C
+    import time
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for G, n in ((2000, 3000), (77, 513), (32, 1), (1, 300)):
+        Y0 = np.asfortranarray(np.where(rng.random((G, n)) < 0.45, 0.0, rng.gamma(2.0, 1.0, (G, n))))
+        Y0[rng.integers(0, G, 20), rng.integers(0, n, 20)] = 0.1            # exactly at the cutoff: masked (<=)
+        Y0[rng.integers(0, G, 5), rng.integers(0, n, 5)] = np.nan           # NaN: not masked
+        Y0[rng.integers(0, G, 5), rng.integers(0, n, 5)] = -0.0
+        nw = (G + 31) // 32
+        out = np.zeros((nw, n), dtype=np.uint32)
+        t0 = time.perf_counter()
+        cnt = built_lib.simples_pack_mask(Y0.ctypes.data_as(C.c_void_p), G, n, 0.1, out.ctypes.data_as(C.c_void_p))
+        dt = time.perf_counter() - t0
+        with np.errstate(invalid="ignore"):
+            bits = (Y0 <= 0.1)
+        want = np.zeros((nw * 32, n), dtype=bool)
+        want[:G] = bits
+        w = (want.reshape(nw, 32, n).astype(np.uint64) << np.arange(32, dtype=np.uint64)[None, :, None]).sum(axis=1).astype(np.uint32)
+        assert cnt == int(bits.sum()) and np.array_equal(out, w), (G, n)
+    assert dt < 5.0
