@@ -345,13 +345,33 @@ def main():
             with open(tp) as f:
                 traffic = json.load(f).get(dom)
             break
+    # impute_sweep is NOT memory-bound: its binding resource is instruction issue (FP64 inverse-CDF sampler).  The contract's
+    # roofline object is reported against HBM as asked; the issue-slot roofline of the same kernel is given beside it:
+    # warp instructions per launch (ncu smsp__inst_executed.sum of this build at C3) / (148 SMs x 4 schedulers x SM clock).
+    issue = None
+    sp = os.path.join(ROOT, "profiles", "r02_ncu_final_summary.json")
+    if os.path.exists(sp) and dom == "impute_sweep" and n == CFG["n"] and not CFG.get("override") and CFG.get("name", "C3") == "C3":
+        with open(sp) as f:
+            for e in json.load(f):
+                if "k_sweep" in e.get("kernel", ""):
+                    winst = float(e["smsp__inst_executed.sum"])
+                    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                    peak = 148 * 4 * mhz * 1e6
+                    t_bound = winst / peak * 1e3
+                    issue = {"warp_instructions_per_launch": winst, "peak_warp_instructions_per_s": peak,
+                             "issue_bound_ms": t_bound, "frac": t_bound / kern[dom]["ms_per_launch"],
+                             "warp_instructions_per_entry": winst / max(nnz0, 1),
+                             "source": "ncu smsp__inst_executed.sum, profiles/r02_ncu_final_summary.json"}
+                    break
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kern[dom]["hbm_frac"], "traffic": traffic, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": alg[dom]["bytes"], "ms_per_launch": kern[dom]["ms_per_launch"],
                 "fp64_tflops": kern[dom]["fp64_tflops"], "fp64_peak_tflops": f64_peak, "fp64_peak_source": f64_src,
-                "note": "impute_sweep is bound by instruction issue of the per-entry sampler (Philox + FP64 pnorm/qnorm), "
-                        "not by HBM: see DESIGN.md section 4 and profiles/r01_notes.md; the GEMM kernels estep_project / "
-                        "mstep_stats run at 63-64 % of measured HBM and 75 % of measured FP64 DGEMM (kernels[...])"}
+                "issue_roofline": issue,
+                "note": "impute_sweep is bound by instruction issue of the per-entry sampler (Philox + FP64 pnorm/qnorm: 17 warp "
+                        "instructions per zero entry, issue slots 73 % busy), not by HBM: see issue_roofline, DESIGN.md section 4 "
+                        "and profiles/r02_notes.md; the GEMM kernels estep_project / mstep_stats run at 66-68 % of measured HBM "
+                        "and 76-80 % of measured FP64 DGEMM (kernels[...])"}
 
     # ---------------- end-to-end through the C ABI with host buffers ----------------
     e2e = None

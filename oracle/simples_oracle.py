@@ -673,7 +673,8 @@ def _prologue(Y, z, mu, M0, lower, upper, compat):
         if M0 > 1 and z is not None:
             mu = Yc @ z / (n if compat & COMPAT_MU_DIV_N else 1.0)           # :95  (Q3)
             if not compat & COMPAT_MU_DIV_N:
-                mu = mu / np.maximum(z.sum(axis=0), 1e-300)[None, :]
+                nzc = z.sum(axis=0)
+                mu = mu / np.where(nzc != 0.0, nzc, 1.0)[None, :]               # empty cluster: column stays 0
         else:
             mu = np.zeros((G, M0))                                           # :97
     return Yc, gene_mean, gene_sd, np.array(mu, dtype=np.float64)

@@ -5,6 +5,9 @@
 # R/select_KM.R:152-155) call them unchanged.
 # NAMESPACE gains:  useDynLib(SIMPLEs, .registration = TRUE)
 #
+# Multi-GPU: call simples_init_b200(devices = 0:7) once per R session (r/SIMPLE_b200.R); the library then shards the
+# cells over the GPUs inside these two calls (host thread per GPU, NCCL all-reduce) -- the R code does not change.
+#
 # Differences a caller can observe (DESIGN.md section 8):
 #  * random draws come from a Philox4x32-10 tape keyed by `seed` (default: one draw from R's RNG, so
 #    set.seed() still makes runs reproducible) instead of R's Mersenne-Twister stream;
@@ -16,6 +19,7 @@ EM_impute <- function(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lambda, pi, 
                       impt_it = 5, sigma0 = 100, pi_alpha = 1, verbose = F, num_mc = 3, lower = -Inf,
                       upper = Inf, seed = NULL) {
   if (is.null(seed)) seed <- floor(runif(1) * 2^52)
+  Y <- as.matrix(Y); Y0 <- as.matrix(Y0)
   storage.mode(Y) <- "double"; storage.mode(Y0) <- "double"
   pg <- as.matrix(pg); storage.mode(pg) <- "double"
   beta <- as.matrix(beta); sigma <- as.matrix(sigma); lambda <- as.matrix(lambda)
@@ -37,9 +41,14 @@ do_impute <- function(dat, Y, beta, lambda, sigma, mu, pi, pos_mean = NULL, pos_
   G <- nrow(Y)
   MB <- if (is.null(celltype)) 1L else max(celltype)                 # R/do_impute.R:43-45
   if (length(pg) == 1) pg <- matrix(pg, G, MB)                        # R/do_impute.R:47-48
+  dat <- as.matrix(dat); Y <- as.matrix(Y); pg <- as.matrix(pg)
   storage.mode(dat) <- "double"; storage.mode(Y) <- "double"; storage.mode(pg) <- "double"
+  dbl <- function(x) { x <- as.matrix(x); storage.mode(x) <- "double"; x }     # .Call takes REAL() of every matrix
+  beta <- dbl(beta); lambda <- dbl(lambda); sigma <- dbl(sigma); mu <- dbl(mu)
+  if (!is.null(pos_mean)) pos_mean <- as.double(pos_mean)
+  if (!is.null(pos_sd)) pos_sd <- as.double(pos_sd)
   if (!is.null(celltype)) celltype <- as.integer(celltype)
-  .Call("C_simples_do_impute", dat, Y, as.matrix(beta), as.matrix(lambda), as.matrix(sigma), as.matrix(mu),
+  .Call("C_simples_do_impute", dat, Y, beta, lambda, sigma, mu,
         as.double(pi), pos_mean, pos_sd, celltype, as.integer(mcmc), as.integer(burnin), pg,
         as.double(cutoff), as.double(seed), as.logical(consensus), PACKAGE = "SIMPLEs")
 }

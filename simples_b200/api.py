@@ -218,11 +218,20 @@ class EMContext:
         self.G, self.n, self.M0, self.K0 = G, n, int(M0), int(K0)
         self.iters_done = 0
         h = C.c_void_p()
-        check(self._lib.simples_em_create(C.byref(a), C.byref(h)))
+        self._keep = keep
+        self._check(self._lib.simples_em_create(C.byref(a), C.byref(h)))
         self._h = h
 
+    def _check(self, rc):
+        """Raise the Python exception an all-reduce callback stored (instead of the generic ECOMM), else the library's."""
+        cw = getattr(self, "_keep", {}).get("_comm")
+        if rc < 0 and cw is not None and cw.error is not None:
+            err, cw.error = cw.error, None
+            raise err
+        return check(rc)
+
     def run(self, iters):
-        check(self._lib.simples_em_run(self._h, int(iters)))
+        self._check(self._lib.simples_em_run(self._h, int(iters)))
         self.iters_done += int(iters)
 
     def sync(self):

@@ -824,9 +824,13 @@ int em_create_impl(const simples_em_args* a, simples_ctx** out, long long io_ld)
         launch_reduce_parts(part, s.mu, size_t(ldG) * M0, nsplit, c->stream);
         CKR(allreduce(c, s.mu, size_t(ldG) * M0));
         if (c->compat & SIMPLES_COMPAT_MU_DIV_N) {
-            launch_scale(s.mu, size_t(ldG) * M0, 1.0 / double(d.n_total), c->stream);
-        } else {
-            return fail(SIMPLES_EINVAL, "ref_compat_flags without SIMPLES_COMPAT_MU_DIV_N requires an explicit mu");
+            launch_scale(s.mu, size_t(ldG) * M0, 1.0 / double(d.n_total), c->stream);      // Q3: / n
+        } else {                                                                           // the intended cluster means: / nz_m
+            double* nz = nullptr;
+            CKR(c->dalloc(&nz, size_t(2 * M0 + 1)));
+            launch_colsum(s.z, nz, d.n, M0, c->stream);
+            CKR(allreduce(c, nz, size_t(M0)));
+            launch_div_cols(s.mu, nz, size_t(ldG), M0, c->stream);
         }
     }   // else mu = 0 (already zeroed)
     CK(cudaStreamSynchronize(c->stream));

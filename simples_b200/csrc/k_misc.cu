@@ -79,6 +79,15 @@ __global__ void k_scale(double* p, size_t count, double s) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) p[i] *= s;
 }
 
+// A[r][c] /= d[c]   (row-major [rows][cols]); columns with d = 0 are left untouched
+__global__ void k_div_cols(double* A, const double* d, size_t rows, int cols) {
+    const size_t total = rows * cols;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const double dv = d[i % cols];
+        if (dv != 0.0) A[i] /= dv;
+    }
+}
+
 __global__ void k_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG) {
     const size_t total = size_t(n) * G;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -264,6 +273,9 @@ void launch_transpose(const double* in, double* out, int rows, int cols, int ld_
     k_transpose<<<grid, block, 0, st>>>(in, out, rows, cols, ld_in, ld_out);
 }
 void launch_fill(double* p, size_t count, double v, cudaStream_t st) { k_fill<<<gs_grid(count), 256, 0, st>>>(p, count, v); }
+void launch_div_cols(double* A, const double* d, size_t rows, int cols, cudaStream_t st) {
+    k_div_cols<<<gs_grid(rows * cols), 256, 0, st>>>(A, d, rows, cols);
+}
 void launch_scale(double* p, size_t count, double s, cudaStream_t st) { k_scale<<<gs_grid(count), 256, 0, st>>>(p, count, s); }
 void launch_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG,
                      cudaStream_t st) {

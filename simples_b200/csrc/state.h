@@ -268,6 +268,7 @@ void launch_center(double* Y, const double* gmean, const double* gsd, int n, int
 void launch_transpose(const double* in, double* out, int rows, int cols, int ld_in, int ld_out, cudaStream_t st);
 void launch_fill(double* p, size_t count, double v, cudaStream_t st);
 void launch_scale(double* p, size_t count, double s, cudaStream_t st);
+void launch_div_cols(double* A, const double* d, size_t rows, int cols, cudaStream_t st);
 void launch_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG, cudaStream_t st);
 void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2, const double* gmean,
                         const double* gsd, double* impt, double* impt_var, int n, int cell0, int n_alloc, int G, int ldG, int mcmc,

@@ -28,6 +28,19 @@ def partition(n_total: int, world_size: int):
     return b
 
 
+def _is_device_pointer(ptr):
+    """True when `ptr` is CUDA device memory (cudaPointerGetAttributes through cuda-python / torch); host otherwise."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return False
+        from cuda import cudart            # cuda-python
+        err, at = cudart.cudaPointerGetAttributes(int(ptr))
+        return int(err) == 0 and int(at.type) in (2, 3)     # cudaMemoryTypeDevice / Managed
+    except Exception:  # noqa: BLE001
+        return False
+
+
 class _DevPtr:
     """Expose a raw CUDA pointer through __cuda_array_interface__."""
 
@@ -77,6 +90,16 @@ class CellShard:
             ext = torch.cuda.ExternalStream(int(stream)) if stream else torch.cuda.current_stream()
             with torch.cuda.stream(ext):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        elif _is_device_pointer(ptr):
+            # gloo group but the CUDA library is calling (it always passes DEVICE pointers): stage through the host,
+            # ordered on the library's stream
+            t = torch.as_tensor(_DevPtr(ptr, count), device="cuda")
+            ext = torch.cuda.ExternalStream(int(stream)) if stream else torch.cuda.current_stream()
+            with torch.cuda.stream(ext):
+                h = t.cpu()
+                dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
+                t.copy_(h)
+                ext.synchronize()
         else:  # gloo: host pointer (CPU tests of the sharding logic)
             buf = (C.c_double * int(count)).from_address(int(ptr))
             t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))

@@ -88,7 +88,7 @@ def test_compat_flags(sb):
     K0, M0 = 3, 3
     st = make_case(150, 100, 3, 3, K0, M0, seed=6)
     for flags in (O.COMPAT_DEFAULT & ~O.COMPAT_STALE_DT, O.COMPAT_DEFAULT & ~O.COMPAT_PI,
-                  O.COMPAT_DEFAULT & ~O.COMPAT_PRIORB_PREV):
+                  O.COMPAT_DEFAULT & ~O.COMPAT_PRIORB_PREV, O.COMPAT_DEFAULT & ~O.COMPAT_MU_DIV_N, 0):
         kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=1)
         ref = O.em_impute_fast(*em_args(st, M0, K0, 4), compat=flags, **kw)
         got = sb.EM_impute(*em_args(st, M0, K0, 4), ref_compat=flags, **kw)
