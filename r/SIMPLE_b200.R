@@ -1,6 +1,13 @@
 # Replacement bodies / call sites for the stages of SIMPLE() and SIMPLE_B() around EM_impute / do_impute.
 # SHIPPED AS SOURCE (R is not available in the build image).  Each block cites the reference lines it replaces.
 
+# ---- device selection (no counterpart in the reference) ---------------------------------------------------------------
+# simples_init_b200(0)      one GPU (default when never called: the current device)
+# simples_init_b200(0:7)    this R session drives 8 GPUs: EM_impute() / do_impute() shard the cells over them inside
+#                           the library (one host thread per GPU, one NCCL all-reduce per EM iteration); SIMPLE(),
+#                           SIMPLE_B() and selectKM() need no change.
+simples_init_b200 <- function(devices = 0L) .Call(C_simples_init, as.integer(devices))
+
 # ---- R/SIMPLE.R:15-73 ---------------------------------------------------------------------------------------------
 init_impute <- function(Y2, M0, clus, p_min = 0.6, cutoff = 0.1, verbose = F) {
   storage.mode(Y2) <- "double"

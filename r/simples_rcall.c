@@ -226,7 +226,18 @@ SEXP C_simples_lq_fit(SEXP dat, SEXP resp, SEXP sigma, SEXP pg, SEXP z, SEXP Ef,
     return res;
 }
 
-static const R_CallMethodDef call_methods[] = {{"C_simples_em_impute", (DL_FUNC)&C_simples_em_impute, 25},
+/* simples_init(ndev, devs): devices this R session drives.  With more than one device the library shards the cells of
+ * EM_impute / do_impute over them (host thread per GPU + NCCL inside the library); the R code above it is unchanged. */
+SEXP C_simples_init(SEXP devices) {
+    SEXP d = PROTECT(Rf_coerceVector(devices, INTSXP));
+    const int rc = simples_init(Rf_length(d), INTEGER(d));
+    UNPROTECT(1);
+    if (rc != SIMPLES_OK) Rf_error("simples_b200: %s (status %d)", simples_last_error(), rc);
+    return Rf_ScalarInteger(simples_device_count());
+}
+
+static const R_CallMethodDef call_methods[] = {{"C_simples_init", (DL_FUNC)&C_simples_init, 1},
+                                               {"C_simples_em_impute", (DL_FUNC)&C_simples_em_impute, 25},
                                                {"C_simples_do_impute", (DL_FUNC)&C_simples_do_impute, 16},
                                                {"C_simples_init_impute", (DL_FUNC)&C_simples_init_impute, 7},
                                                {"C_simples_init_cluster", (DL_FUNC)&C_simples_init_cluster, 6},
