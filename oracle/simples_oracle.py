@@ -245,7 +245,7 @@ LASSO_MODE = "exact"            # "exact" | "glmnet": which solver mstep_from_st
 GLMNET_THRESH = 1e-7            # glmnet's default `thresh` (R/EM_impute.R:257-259 passes none)
 
 
-def lasso_glmnet_compat(A, rhs, kappa, N, sum_y, sum_y2, thresh=GLMNET_THRESH, maxit=100000, info=None):
+def lasso_glmnet_compat(A, rhs, kappa, N, sum_y, sum_y2, thresh=GLMNET_THRESH, maxit=100000, info=None, vp=None):
     """The lasso of R/EM_impute.R:257-259 as glmnet itself solves it, from the Gram form.
 
     glmnet (>= 2.0-16, ``family="gaussian"``, ``standardize=F``, ``intercept=F``, one user
@@ -263,6 +263,8 @@ def lasso_glmnet_compat(A, rhs, kappa, N, sum_y, sum_y2, thresh=GLMNET_THRESH, m
 
     ``A`` = X'X (K x K), ``rhs`` = X'y, ``kappa`` = N * lambda_user (the penalty on the
     0.5 * RSS scale, as in ``lasso_solve``); ``N, sum_y, sum_y2`` describe the response.
+    ``vp`` = per-coordinate penalty factors AFTER glmnet's rescale to sum K (None = all 1;
+    0 = unpenalised, as the cluster intercepts of R/SIMPLE.R:343-349).
     Returns the coefficients on the original scale.  ``info`` (dict) receives ``passes``.
     """
     A = np.asarray(A, dtype=np.float64)
@@ -274,15 +276,16 @@ def lasso_glmnet_compat(A, rhs, kappa, N, sum_y, sum_y2, thresh=GLMNET_THRESH, m
     xv = np.diag(C).copy()
     g = np.asarray(rhs, dtype=np.float64) / N / ys
     alm = float(kappa) / N / ys
+    vp = np.ones(K) if vp is None else np.asarray(vp, dtype=np.float64)
     a = np.zeros(K)
-    ix = np.abs(g) > 2.0 * alm                       # strong rule with alm0 = 0 (single user lambda)
+    ix = np.abs(g) > 2.0 * alm * vp                  # strong rule with alm0 = 0 (single user lambda)
     active = np.zeros(K, dtype=bool)
     nlp = 0
 
     def update(k, cols):
         ak = a[k]
         u = g[k] + ak * xv[k]
-        v = abs(u) - alm
+        v = abs(u) - alm * vp[k]
         nk = math.copysign(v, u) / xv[k] if v > 0.0 else 0.0
         if nk == ak:
             return 0.0
@@ -308,7 +311,7 @@ def lasso_glmnet_compat(A, rhs, kappa, N, sum_y, sum_y2, thresh=GLMNET_THRESH, m
             excl = ~ix
             if excl.any():
                 gex = np.asarray(rhs, dtype=np.float64)[excl] / N / ys - C[np.ix_(excl, np.ones(K, bool))] @ a
-                viol = np.abs(gex) > alm
+                viol = np.abs(gex) > alm * vp[excl]
                 if viol.any():
                     idx = np.flatnonzero(excl)[viol]
                     ix[idx] = True
@@ -977,7 +980,14 @@ def lq_regress_ref(dat, resp, sigma, z, Ef, Varf, penl=1, resid_mode=0):
         # glmnet(lambda = penalty K0/(M0+K0), penalty.factor = c(0.., 1..)) with the internal rescale of the
         # penalty factors to sum to M0 + K0  ==  kappa = penl / var(Y_aug) on the loadings, 0 on the intercepts
         kappa = np.concatenate([np.zeros(M0), np.full(K0, penl / np.var(Y_aug, ddof=1))])   # :341-349
-        coef = lasso_solve(W_aug.T @ W_aug, W_aug.T @ Y_aug, kappa)
+        if LASSO_MODE == "glmnet":      # what glmnet's own stopping rule returns (test only)
+            Nq = Y_aug.size
+            lam_user = penl / Nq / np.var(Y_aug, ddof=1) * K0 / (M0 + K0)                    # :341, :345
+            vpq = np.concatenate([np.zeros(M0), np.full(K0, (M0 + K0) / K0)])               # rescaled penalty.factor
+            coef = lasso_glmnet_compat(W_aug.T @ W_aug, W_aug.T @ Y_aug, Nq * lam_user, Nq, Y_aug.sum(),
+                                       float(Y_aug @ Y_aug), vp=vpq)
+        else:
+            coef = lasso_solve(W_aug.T @ W_aug, W_aug.T @ Y_aug, kappa)
         tempmu, coeff = coef[:M0], coef[M0:]                                 # :351-352
         sg = 0.0
         for m in range(M0):                                                  # :354-364
@@ -992,6 +1002,8 @@ def lq_regress_ref(dat, resp, sigma, z, Ef, Varf, penl=1, resid_mode=0):
 def lq_regress_fast(dat, resp, sigma, z, Ef, Varf, penl=1, resid_mode=0):
     """Same result from cell-additive statistics; the M0 unpenalised intercepts are profiled out
     (their block of the Gram matrix is diagonal), leaving a K0-dimensional lasso per gene."""
+    if LASSO_MODE == "glmnet":          # glmnet iterates the (M0 + K0)-dimensional problem: use the literal formulation
+        return lq_regress_ref(dat, resp, sigma, z, Ef, Varf, penl=penl, resid_mode=resid_mode)
     Gq, n = dat.shape
     M0 = z.shape[1]
     K0 = Ef[0].shape[1]

@@ -464,3 +464,17 @@ def test_expected_impute_is_the_sampler_mean_and_tail_safe():
         drop = ua < pd[i]
         x = np.where(drop, ms[i] + sds[i] * special.ndtri(ub), ms[i] + sds[i] * O.trunc_z(ub, r[i]))
         assert abs(x.mean() - got[i]) < 5 * x.std() / math.sqrt(x.size)
+
+
+def test_r_golden_loader_plumbing(tmp_path):
+    """tests/test_r_golden.py can only meet real R output outside this image.  This runs it end to end against a directory
+    in the same layout written by the ORACLE (glmnet-compatible stopping rule standing in for R): file names, shapes,
+    column-major order, dims.txt, band computation.  It pins nothing -- it makes sure the loader is not dead code."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = str(tmp_path / "golden")
+    subprocess.run([sys.executable, os.path.join(root, "tests", "helpers", "fake_r_golden.py"), gold], check=True, cwd=root)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_r_golden.py"), "-q", "-m", "not gpu",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, cwd=root, env=dict(os.environ, SIMPLES_R_GOLDEN=gold))
+    assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

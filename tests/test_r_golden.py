@@ -132,8 +132,8 @@ def test_oracle_vs_R_lq_regression():
     sig = np.ones((Glq, M0))
     # SIMPLE() was called with init_imp = NULL: the inverted branch of R/SIMPLE.R:354-359 (Q16) => resid_mode 0
     exact, compat = _both_modes(lambda: O.lq_regress_fast(dat[lq], dat[lq], sig, z, Ef, Varf, penl=1, resid_mode=0))
-    _assert_in_band(_f64("C_lq_beta", Glq, K0), exact["beta"], compat["beta"], "lq beta")
-    _assert_in_band(_f64("C_lq_sigma", Glq, M0), exact["sigma"], compat["sigma"], "lq sigma")
+    _assert_in_band(_f64("C_lq_beta", Glq, K0), exact[1], compat[1], "lq beta")        # (mu, beta, sigma)
+    _assert_in_band(_f64("C_lq_sigma", Glq, M0), exact[2], compat[2], "lq sigma")
 
 
 def test_oracle_vs_R_do_impute_deterministic_part():
@@ -198,6 +198,6 @@ def test_cuda_vs_R_ztruncnorm_and_lq(sb):
                     cutoff=d["cutoff"], resid_mode=0, impute=False)
     exact, compat = _both_modes(lambda: O.lq_regress_fast(dat[lq], dat[lq], np.ones((Glq, M0)), z, Ef, Varf, penl=1,
                                                           resid_mode=0))
-    assert rel(got["beta"], exact["beta"]) <= 1e-8 and rel(got["sigma"], exact["sigma"]) <= 1e-8
-    _assert_in_band(_f64("C_lq_beta", Glq, K0), got["beta"], compat["beta"], "lq beta")
-    _assert_in_band(_f64("C_lq_sigma", Glq, M0), got["sigma"], compat["sigma"], "lq sigma")
+    assert rel(got["beta"], exact[1]) <= 1e-8 and rel(got["sigma"], exact[2]) <= 1e-8
+    _assert_in_band(_f64("C_lq_beta", Glq, K0), got["beta"], compat[1], "lq beta")
+    _assert_in_band(_f64("C_lq_sigma", Glq, M0), got["sigma"], compat[2], "lq sigma")
