@@ -139,3 +139,13 @@ def test_expect_mode_matches_oracle_20k_cells(sb):
     assert np.array_equal(other["Y"], got["Y"]) and np.array_equal(other["beta"], got["beta"])     # tape-independent
     samp = sb.EM_impute(*em_args(st, M0, K0, 3), **kw)
     assert not np.array_equal(samp["Y"], got["Y"])
+
+
+def test_r_golden_loader_plumbing_gpu(tmp_path):
+    """The CUDA half of tests/test_r_golden.py executed end to end against the oracle stand-in directory (see
+    tests/helpers/fake_r_golden.py): a plumbing check of the loader, not a parity pin."""
+    gold = str(tmp_path / "golden")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "helpers", "fake_r_golden.py"), gold], check=True, cwd=ROOT)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_r_golden.py"), "-q", "-m", "gpu",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, SIMPLES_R_GOLDEN=gold))
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

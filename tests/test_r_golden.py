@@ -194,7 +194,7 @@ def test_cuda_vs_R_ztruncnorm_and_lq(sb):
     z = _f64("C1_out_z", n, M0)
     Ef = [np.ascontiguousarray(m) for m in np.split(_f64("C1_out_Ef", n, K0 * M0), M0, axis=1)]
     Varf = [np.ascontiguousarray(m) for m in np.split(_f64("C1_out_Varf", K0, K0 * M0), M0, axis=1)]
-    got = sb.lq_fit(dat[lq], None, np.ones((Glq, M0)), np.full((Glq, M0), 0.5), z, Ef, Varf, None, penl=1,
+    got = sb.lq_fit(dat[lq], np.ones((Glq, M0)), np.full((Glq, M0), 0.5), z, Ef, Varf, None, penl=1,
                     cutoff=d["cutoff"], resid_mode=0, impute=False)
     exact, compat = _both_modes(lambda: O.lq_regress_fast(dat[lq], dat[lq], np.ones((Glq, M0)), z, Ef, Varf, penl=1,
                                                           resid_mode=0))
