@@ -253,7 +253,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     s.n_alloc = c->n_alloc;
     CKR(c->dalloc(&s.P, size_t(c->NS_max) * na * d.NQP));
     CKR(c->dalloc(&s.S2, size_t(c->NS_max) * na));
-    CKR(c->dalloc(&s.proj_part, size_t(NUM_SMS_B200) * 128 * (d.NQP + 1)));
+    CKR(c->dalloc(&s.proj_part, size_t(PROJ_MAX_SPLIT) * NUM_SMS_B200 * 128 * (d.NQP + 1)));
     CKR(c->dalloc(&s.V, na * d.VS));
     CKR(c->dalloc(&s.zsum, na));
     CKR(c->dalloc(&s.Fh, na * d.FS));
@@ -267,6 +267,8 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.cc.offq, size_t(M0) * K0));
     CKR(c->dalloc(&s.cc.cmu, size_t(M0)));
     CKR(c->dalloc(&s.cc.logpi, size_t(M0)));
+    CKR(c->dalloc(&s.cc.Vj, size_t(M0) * K0 * K0));
+    CKR(c->dalloc(&s.cc.jst, size_t(M0)));
     s.ncta_cell = std::min((n + 63) / 64, NUM_SMS_B200 * 8);
     CKR(c->dalloc(&s.part_cell, size_t(s.ncta_cell) * (2 * M0 + 1)));
     CKR(c->dalloc(&c->cellsum_main, size_t(2 * M0 + 1)));

@@ -117,10 +117,17 @@ __global__ void __launch_bounds__(128) k_cluster(PrepArgs a, const double* part,
     double* sRed = sM + K0 * K0;     // [2]
     double* sW = sRed + 2;           // [32] rotation parameters of one Jacobi round
     const int nG2 = NS * K0 * K0, nOff = M0 * K0, NE = prep_ne(K0, M0, NS);
-    auto total = [&](int e) {
-        double s = 0.0;
-        for (int p = 0; p < nparts; ++p) s += part[size_t(p) * NE + e];
-        return s;
+    auto total = [&](int e) {          // fixed order, four independent chains so that the L2 loads pipeline
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int p = 0;
+        for (; p + 4 <= nparts; p += 4) {
+            s0 += part[size_t(p) * NE + e];
+            s1 += part[size_t(p + 1) * NE + e];
+            s2 += part[size_t(p + 2) * NE + e];
+            s3 += part[size_t(p + 3) * NE + e];
+        }
+        for (; p < nparts; ++p) s0 += part[size_t(p) * NE + e];
+        return (s0 + s1) + (s2 + s3);
     };
     for (int e = threadIdx.x; e < K0 * K0 + 2 * K0 + 2; e += blockDim.x) {
         if (e < K0 * K0) {
@@ -166,8 +173,16 @@ __global__ void __launch_bounds__(128) k_cluster(PrepArgs a, const double* part,
             }
         }
         __syncwarp();
-        warp_sym_sqrt(sA, sV, sLi, sW, K0, lane);
+        // warm start from the previous call's eigenvectors (M_m moves little between EM iterations); a cold start every
+        // 8th call bounds the loss of orthogonality that accumulates through the rotations
+        const int jst = a.cc.jst ? a.cc.jst[m] : 0;
+        const bool warm = jst > 0 && jst < 8;
+        warp_sym_sqrt(sA, sV, sLi, sW, K0, lane, warm ? a.cc.Vj + size_t(m) * K0 * K0 : nullptr);
         for (int e = lane; e < K0 * K0; e += 32) a.cc.Mh[size_t(m) * K0 * K0 + e] = sLi[e];
+        if (a.cc.jst) {
+            for (int e = lane; e < K0 * K0; e += 32) a.cc.Vj[size_t(m) * K0 * K0 + e] = sV[e];
+            if (lane == 0) a.cc.jst[m] = warm ? jst + 1 : 1;
+        }
     }
 }
 

@@ -7,6 +7,8 @@
 // cp.async.bulk.tensor) + Q[32][QS] + isg[32].  The m-tile row -> cell map rho(g) = 2(g&3) + (g>>2)
 // makes every DMMA A-fragment load hit 32 distinct banks under the 128B swizzle.
 // (A ring of 256-byte 1-D bulk copies was TMA-issue bound at ~1 TB/s: profiles/r01_notes.md.)
+#include <algorithm>
+
 #include "ptx.cuh"
 #include "state.h"
 #include "tmap.h"
@@ -165,6 +167,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_proj(const __grid_constant__ CUt
     }
 }
 
+// gene split of the last partial round: S in 1..PROJ_MAX_SPLIT minimising ceil(rem S / NUM_SMS) / S, >= 4 chunks per part
+int proj_pick_split(int rem, int nchunks) {
+    if (rem <= 0) return 1;
+    int best = 1;
+    double cost = 1.0;                    // S = 1: one whole round
+    for (int S = 2; S <= PROJ_MAX_SPLIT && nchunks / S >= 4; ++S) {
+        const double c = double((rem * S + NUM_SMS_B200 - 1) / NUM_SMS_B200) / S + 0.004 * S;     // small cost per extra partial row
+        if (c < cost - 1e-9) {
+            cost = c;
+            best = S;
+        }
+    }
+    return best;
+}
+
 template <int NT>
 void launch_nt(const ProjArgs& a, const CUtensorMap& tm, cudaStream_t st) {
     constexpr int QS = NT * 8 + 4;
@@ -176,18 +193,17 @@ void launch_nt(const ProjArgs& a, const CUtensorMap& tm, cudaStream_t st) {
     const int ntiles = (a.n + TC - 1) / TC;
     const int nchunks = a.ldG / GC;
     // Full rounds of NUM_SMS tiles run as they are; a last partial round of `rem` tiles is split along the genes into
-    // S parts per tile (rem * S <= NUM_SMS items) so that it costs 1/S of a round instead of a whole one.
+    // S parts per tile so that it costs ceil(rem S / NUM_SMS) / S of a round instead of a whole one (a small shard of a
+    // strongly scaled run is ALL tail: 98 tiles at 12.5k cells -> 3 parts, 2 rounds of a third).
     const int head = (ntiles / NUM_SMS_B200) * NUM_SMS_B200, rem = ntiles - head;
-    int S = (rem > 0 && a.part) ? NUM_SMS_B200 / rem : 1;
-    if (S > 8) S = 8;
-    while (S > 1 && nchunks / S < 4) --S;
+    const int S = a.part ? proj_pick_split(rem, nchunks) : 1;
     if (S <= 1) {
         const int grid = ntiles < NUM_SMS_B200 ? ntiles : NUM_SMS_B200;
         k_proj<NT><<<grid, THREADS, smem, st>>>(tm, a, stages, 0, ntiles, 1);
         return;
     }
     if (head > 0) k_proj<NT><<<NUM_SMS_B200, THREADS, smem, st>>>(tm, a, stages, 0, head, 1);
-    k_proj<NT><<<rem * S, THREADS, smem, st>>>(tm, a, stages, head, rem * S, S);
+    k_proj<NT><<<std::min(rem * S, NUM_SMS_B200), THREADS, smem, st>>>(tm, a, stages, head, rem * S, S);
     const int rows = rem * TC;
     k_proj_reduce<<<(rows * (a.NQP + 1) + 255) / 256, 256, 0, st>>>(a, head * TC, rows, S);
 }
@@ -197,9 +213,7 @@ void launch_nt(const ProjArgs& a, const CUtensorMap& tm, cudaStream_t st) {
 int proj_launches(int n, int ldG, bool have_scratch) {
     const int ntiles = (n + TC - 1) / TC, nchunks = ldG / GC;
     const int head = (ntiles / NUM_SMS_B200) * NUM_SMS_B200, rem = ntiles - head;
-    int S = (rem > 0 && have_scratch) ? NUM_SMS_B200 / rem : 1;
-    if (S > 8) S = 8;
-    while (S > 1 && nchunks / S < 4) --S;
+    const int S = have_scratch ? proj_pick_split(rem, nchunks) : 1;
     return S <= 1 ? 1 : (head > 0 ? 3 : 2);
 }
 

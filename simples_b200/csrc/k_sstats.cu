@@ -75,6 +75,21 @@ __global__ void __launch_bounds__(SSW * 32) k_sstats(SstatsArgs a, int cells_per
     }
 }
 
+// fixed-order sum of `np` partials with stride `stride`: four independent accumulators so that the loads pipeline
+// (one running sum is a chain of np dependent FP64 adds behind np L2 round trips)
+__device__ __forceinline__ double sum_parts(const double* p, size_t stride, int np) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int q = 0;
+    for (; q + 4 <= np; q += 4) {
+        s0 += p[size_t(q) * stride];
+        s1 += p[size_t(q + 1) * stride];
+        s2 += p[size_t(q + 2) * stride];
+        s3 += p[size_t(q + 3) * stride];
+    }
+    for (; q < np; ++q) s0 += p[size_t(q) * stride];
+    return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void k_finalize_stats(FinalizeArgs a, size_t count) {
     const int K0 = a.d.K0, M0 = a.d.M0, ldG = a.d.ldG, NVP = a.d.NVP;
     const size_t nC = a.skip_head ? a.head : size_t(ldG) * NVP, nR = a.skip_head ? 0 : ldG;
@@ -84,22 +99,22 @@ __global__ void k_finalize_stats(FinalizeArgs a, size_t count) {
         double s = 0.0;
         if (a.skip_head && i < nC) continue;
         if (i < nC) {
-            for (int p = 0; p < a.splitK; ++p) s += a.part_ms[size_t(p) * nC + i];
+            s = sum_parts(a.part_ms + i, nC, a.splitK);
         } else if (i < nC + nR) {
             const size_t j = i - nC;
             const double* pr = a.part_ms + size_t(a.splitK) * nC;
-            for (int p = 0; p < a.splitK; ++p) s += pr[size_t(p) * nR + j];
+            s = sum_parts(pr + j, nR, a.splitK);
         } else if (i < nC + nR + nS) {
             const size_t j = i - nC - nR;
             const int m = int(j / (K0 * K0)), e = int(j - size_t(m) * K0 * K0);
-            for (int p = 0; p < a.nsplit_ss; ++p) s += a.part_ss[(size_t(p) * M0 + m) * NE + e];
+            s = sum_parts(a.part_ss + size_t(m) * NE + e, size_t(M0) * NE, a.nsplit_ss);
         } else if (i < nC + nR + nS + nA) {
             const size_t j = i - nC - nR - nS;
             const int m = int(j / K0), k = int(j - size_t(m) * K0);
-            for (int p = 0; p < a.nsplit_ss; ++p) s += a.part_ss[(size_t(p) * M0 + m) * NE + K0 * K0 + k];
+            s = sum_parts(a.part_ss + size_t(m) * NE + K0 * K0 + k, size_t(M0) * NE, a.nsplit_ss);
         } else {
             const size_t j = i - nC - nR - nS - nA;
-            for (int p = 0; p < a.ncta_cell; ++p) s += a.part_cell[size_t(p) * RC + j];
+            s = sum_parts(a.part_cell + j, size_t(RC), a.ncta_cell);
         }
         a.stats[i] = s;
     }

@@ -76,8 +76,32 @@ __device__ inline void warp_chol_solve(const double* L, double* b, int K, int la
 // the usual Jacobi coupling, so their parameters are computed together by K'/2 lanes and the column / row updates of
 // all pairs are spread over the warp.  A round costs three warp barriers instead of three per rotation (the cyclic
 // ordering made cluster_prep the longest replicated kernel of a strongly scaled run: profiles/r02_notes.md).
-__device__ inline void warp_sym_sqrt(double* A, double* V, double* R, double* W, int K, int lane) {
-    for (int e = lane; e < K * K; e += 32) V[e] = ((e / K) == (e % K)) ? 1.0 : 0.0;
+// Vwarm (optional, K x K orthogonal, global or shared): eigenvectors of a NEARBY matrix (the previous EM iteration's);
+// A is first rotated into that basis, where it is almost diagonal, and the Jacobi sweeps continue from there (2 sweeps
+// instead of ~7).  On return V holds the eigenvectors of the input A either way.
+__device__ inline void warp_sym_sqrt(double* A, double* V, double* R, double* W, int K, int lane,
+                                     const double* Vwarm = nullptr) {
+    if (Vwarm) {
+        for (int e = lane; e < K * K; e += 32) V[e] = Vwarm[e];
+        __syncwarp();
+        for (int e = lane; e < K * K; e += 32) {          // R = A V
+            const int i = e / K, j = e - i * K;
+            double s = 0.0;
+            for (int p = 0; p < K; ++p) s = fma(A[i * K + p], V[p * K + j], s);
+            R[e] = s;
+        }
+        __syncwarp();
+        for (int e = lane; e < K * K; e += 32) {          // A = V' R, symmetrised
+            const int i = e / K, j = e - i * K;
+            if (i > j) continue;
+            double s = 0.0;
+            for (int p = 0; p < K; ++p) s = fma(V[p * K + i], R[p * K + j], s);
+            A[i * K + j] = s;
+            A[j * K + i] = s;
+        }
+    } else {
+        for (int e = lane; e < K * K; e += 32) V[e] = ((e / K) == (e % K)) ? 1.0 : 0.0;
+    }
     __syncwarp();
     const int Ke = (K + 1) & ~1, H = Ke >> 1;          // H <= 16 pairs per round
     double* Wc = W;

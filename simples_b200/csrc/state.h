@@ -24,6 +24,7 @@ constexpr int GPAD = 64;     // ldG granularity
 constexpr int MAXK = 32;     // K0 <= 32
 constexpr int MAXM = 32;     // M0 <= 32
 constexpr int NUM_SMS_B200 = 148;
+constexpr int PROJ_MAX_SPLIT = 8;   // k_proj: parts per tile of the gene-split last round
 
 enum KernelClass {
     KC_PROJ = 0,      // estep_project   (DMMA)
@@ -58,6 +59,8 @@ struct ClusterConsts {   // device pointers, produced by cluster_prep
     double* offq;   // [M0][K0]   mu_m' (B / sigma_q)   q = M0-1 (stale beta2, Q1) -- used for the quadratic form in MC passes
     double* cmu;    // [M0]       sum_g mu_gm^2 / sigma_gm
     double* logpi;  // [M0]
+    double* Vj;     // [M0][K0][K0] eigenvectors of Mm from the previous cluster_prep (warm start of the Jacobi sweeps)
+    int* jst;       // [M0] cluster_prep calls since the last cold start (0: none yet)
 };
 
 struct DevState {
@@ -102,7 +105,7 @@ inline void ensure_dyn_smem_k(K kernel, size_t bytes) { ensure_dyn_smem(reinterp
 struct ProjArgs {
     const double* Y; const double* Q; const double* isg; double* P; double* S2;
     int n, ldG, NQP, QS;
-    double* part;   // scratch [NUM_SMS * 128][NQP + 1] for the gene-split tail tiles (nullptr: no split)
+    double* part;   // scratch [PROJ_MAX_SPLIT * NUM_SMS * 128][NQP + 1] for the gene-split tail tiles (nullptr: no split)
 };
 void launch_proj(const ProjArgs& a, const CUtensorMap& tmapY, cudaStream_t st);   // tmapY: box {16 genes, 128 cells}
 int proj_launches(int n, int ldG, bool have_scratch);
