@@ -298,9 +298,9 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
               stream=None, out=None):
     """Multiple imputation at fixed parameters on B200 -- drop-in for
     ``do_impute`` (R/do_impute.R:29-160).  Returns loglik, impt, impt_var, EF,
-    varF, consensus_cluster.  ``consensus=False`` (or sharded cells) returns
-    ``consensus_cluster=None``: the n x n matrix (R/do_impute.R:61) is only
-    materialised on request and on a single rank."""
+    varF, consensus_cluster.  ``consensus=True``: the n x n matrix of R/do_impute.R:61 (also when this process
+    drives several GPUs: every device fills its row block).  With ``comm`` (one process per GPU) the default is
+    ``None``; ``consensus="rows"`` returns this rank's row block, n_local x n_total.  ``consensus=False``: ``None``."""
     lib = _lib.load()
     Y = _f(Y)
     G, n = Y.shape
@@ -324,8 +324,9 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
         setattr(a, k, _ptr(keep[k]))
     a.mcmc, a.burnin, a.cutoff = int(mcmc), int(burnin), float(cutoff)
     a.seed, a.ref_compat_flags = int(seed) & 0xFFFFFFFFFFFFFFFF, int(ref_compat)
-    want_cons = bool(consensus) and comm is None and _lib.load().simples_device_count() <= 1
+    want_cons = (bool(consensus) and comm is None) or (comm is not None and consensus == "rows")
     a.want_consensus = int(want_cons)
+    n_cols = n if comm is None else int(comm.n_total)
     cw = None
     if comm is not None:
         cw = _Comm(comm)
@@ -336,7 +337,7 @@ def do_impute(dat, Y, beta, lambda_, sigma, mu, pi, pos_mean=None, pos_sd=None, 
                 impt=out.get("impt") if out.get("impt") is not None else np.empty((G, n), order="F"),
                 impt_var=out.get("impt_var") if out.get("impt_var") is not None else np.empty((G, n), order="F"),
                 EF=np.zeros((n, K0), order="F"), varF=np.zeros((n, K0), order="F"),
-                consensus_cluster=np.zeros((n, n), order="F") if want_cons else None)
+                consensus_cluster=np.zeros((n, n_cols), order="F") if want_cons else None)
     for k in ("impt", "impt_var"):
         _check_out(bufs[k], (G, n), "F", k)
     o = MiOut()

@@ -1098,8 +1098,9 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
     if (!a->dat || !a->Y || !a->beta || !a->lambda || !a->sigma || !a->mu || !a->pi || !a->pg)
         return fail(SIMPLES_EINVAL, "dat, Y, beta, lambda, sigma, mu, pi and pg are required");
     if (a->mcmc < 1 || a->burnin < 0) return fail(SIMPLES_EINVAL, "mcmc must be >= 1 and burnin >= 0");
-    if (a->want_consensus && (a->allreduce || a->n_total > a->n))
-        return fail(SIMPLES_EINVAL, "consensus_cluster is single-rank only");
+    const bool cons_sharded = a->want_consensus && o->consensus_cluster && a->n_total > a->n;
+    if (cons_sharded && (a->n_total > 2000000000LL / 8 || !(a->allreduce || g_rank_comm)))
+        return fail(SIMPLES_EINVAL, "sharded consensus_cluster needs an all-reduce and n_total < 2.5e8");
     CKR(ensure_device());
 
     std::unique_ptr<simples_ctx> guard(new simples_ctx());
@@ -1144,7 +1145,19 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
     CKR(c->dalloc(&c->rVF, size_t(n) * K0));
     const int nit = a->mcmc + a->burnin;
     CKR(c->dalloc(&c->tot_mi, size_t(nit) * (2 * M0 + 1)));
-    if (a->want_consensus && o->consensus_cluster) CKR(c->dalloc(&c->cons, size_t(n) * n));
+    // consensus_cluster (R/do_impute.R:61,96).  One shard: n x n.  Sharded: this shard's ROW BLOCK, n_local x n_total,
+    // from the full z of every recorded sweep (each shard writes its rows into a zeroed n_total x M0 buffer and the
+    // all-reduce sums the disjoint blocks).
+    double* zall = nullptr;
+    const long long ntot = a->n_total > 0 ? a->n_total : n;
+    if (a->want_consensus && o->consensus_cluster) {
+        if (cons_sharded) {
+            CKR(c->dalloc(&c->cons, size_t(ntot) * n));
+            CKR(c->dalloc(&zall, size_t(ntot) * M0));
+        } else {
+            CKR(c->dalloc(&c->cons, size_t(n) * n));
+        }
+    }
     const double pi_const = (c->compat & SIMPLES_COMPAT_PI) ? 3.14159265359 : M_PI;
 
     using clk_mi = std::chrono::steady_clock;
@@ -1158,7 +1171,16 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
         c->sweep = unsigned(it - 1);
         CKR(e_pass(c, true, false, true, true, rec, false, pi_const, fused && it > 1));   // :69-104, :107, :112
         launch_finalize_cell(s.part_cell, s.ncta_cell, M0, c->tot_mi + size_t(it - 1) * (2 * M0 + 1), c->stream);   // :89
-        if (rec && c->cons) launch_consensus(s.z, c->cons, n, M0, c->stream);   // :96
+        if (rec && c->cons) {                                                   // :96
+            if (zall) {
+                CK(cudaMemsetAsync(zall, 0, size_t(ntot) * M0 * 8, c->stream));
+                CK(cudaMemcpyAsync(zall + size_t(a->cell_offset) * M0, s.z, size_t(n) * M0 * 8, cudaMemcpyDeviceToDevice, c->stream));
+                CKR(allreduce(c, zall, size_t(ntot) * M0));
+                launch_consensus_rows(s.z, zall, c->cons, n, int(ntot), M0, c->stream);
+            } else {
+                launch_consensus(s.z, c->cons, n, M0, c->stream);
+            }
+        }
         if (fused) CKR(run_mcpass(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));
         else CKR(run_sweep(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));   // :109-136, :140-141
         if (rec) launch_mi_record_factors(d, s.W, s.z, s.cc.Mm, c->rEF, c->rF2, c->rVF, c->stream);   // :143-147
@@ -1205,8 +1227,16 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
             }
     }
     if (o->consensus_cluster && c->cons) {
-        launch_scale(c->cons, size_t(n) * n, 1.0 / a->mcmc, c->stream);
-        CK(cudaMemcpyAsync(o->consensus_cluster, c->cons, size_t(n) * n * 8, cudaMemcpyDefault, c->stream));
+        if (zall) {      // row block: device [n_total columns][n_local rows] -> the caller's column-major matrix whose leading
+                         // dimension is io_ld (the full n) in a one-process multi-GPU run, n_local for a rank's own block
+            launch_scale(c->cons, size_t(ntot) * n, 1.0 / a->mcmc, c->stream);
+            const size_t ldh = c->io_ld ? size_t(c->io_ld) : size_t(n);
+            CK(cudaMemcpy2DAsync(o->consensus_cluster, ldh * 8, c->cons, size_t(n) * 8, size_t(n) * 8, size_t(ntot),
+                                 cudaMemcpyDefault, c->stream));
+        } else {
+            launch_scale(c->cons, size_t(n) * n, 1.0 / a->mcmc, c->stream);
+            CK(cudaMemcpyAsync(o->consensus_cluster, c->cons, size_t(n) * n * 8, cudaMemcpyDefault, c->stream));
+        }
         CK(cudaStreamSynchronize(c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -1217,8 +1247,6 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
 int do_impute_sharded(const simples_mi_args* a, simples_mi_out* o) {
     if (!a || !o) return fail(SIMPLES_EINVAL, "null argument");
     CKR(check_common(a->G, a->n, a->M0, a->K0, a->MB));
-    if (a->want_consensus && o->consensus_cluster)
-        return fail(SIMPLES_EINVAL, "consensus_cluster (n x n) is not materialised when the cells are sharded over devices");
     if (a->celltype)
         for (int i = 0; i < a->n; ++i)
             if (a->celltype[i] < 1 || a->celltype[i] > a->MB) return fail(SIMPLES_EINVAL, "celltype must be in 1..ncol(pg)");
@@ -1232,7 +1260,6 @@ int do_impute_sharded(const simples_mi_args* a, simples_mi_out* o) {
         la.dat = a->dat + size_t(c0) * G;
         la.Y = a->Y + size_t(c0) * G;
         la.celltype = a->celltype ? a->celltype + c0 : nullptr;
-        la.want_consensus = 0;
         la.n_total = a->n;
         la.cell_offset = c0;
         la.allreduce = nccl_allreduce_cb;
@@ -1242,7 +1269,7 @@ int do_impute_sharded(const simples_mi_args* a, simples_mi_out* o) {
         lo.impt_var = o->impt_var ? o->impt_var + size_t(c0) * G : nullptr;
         lo.EF = o->EF ? o->EF + c0 : nullptr;
         lo.varF = o->varF ? o->varF + c0 : nullptr;
-        lo.consensus_cluster = nullptr;
+        lo.consensus_cluster = (a->want_consensus && o->consensus_cluster) ? o->consensus_cluster + c0 : nullptr;   // row block
         return do_impute_one(&la, &lo, a->n, r == 0);
     });
 }

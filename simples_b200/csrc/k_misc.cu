@@ -148,6 +148,16 @@ __global__ void k_consensus(const double* z, double* cons, int n, int M0) {
     cons[size_t(j) * n + i] += s;   // symmetric; column-major n x n
 }
 
+// Sharded consensus (R/do_impute.R:96): this shard's row block of z z', rows = local cells, columns = ALL cells.
+// cons is column-major [n_total][n_local]: cons[j * nl + i] += <z_loc[i], z_all[j]>.
+__global__ void k_consensus_rows(const double* zloc, const double* zall, double* cons, int nl, int ntot, int M0) {
+    const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+    if (i >= nl || j >= ntot) return;
+    double s = 0.0;
+    for (int m = 0; m < M0; ++m) s = fma(zloc[size_t(i) * M0 + m], zall[size_t(j) * M0 + m], s);
+    cons[size_t(j) * nl + i] += s;
+}
+
 // Yimp0 chunk (R/SIMPLE.R:421-426): out[i][g] = (sum_m mu[g,m] z[i,m] + sum_k beta[g,k] Wbar[i,k]) gsd[g] + gmean[g],
 // Wbar_i = sum_m z_im Ef_m[i,] (first K0 columns of the M-step operand row V_i).
 __global__ void k_yimp0(Dims d, const double* mu, const double* beta, const double* z, const double* V, const double* gmean,
@@ -299,6 +309,11 @@ void launch_yimp0(const Dims& d, const double* mu, const double* beta, const dou
 void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t st) {
     dim3 grid((n + 15) / 16, (n + 15) / 16), block(16, 16);
     k_consensus<<<grid, block, 0, st>>>(z, cons, n, M0);
+}
+
+void launch_consensus_rows(const double* zloc, const double* zall, double* cons, int nl, int ntot, int M0, cudaStream_t st) {
+    dim3 grid((ntot + 15) / 16, (nl + 15) / 16), block(16, 16);
+    k_consensus_rows<<<grid, block, 0, st>>>(zloc, zall, cons, nl, ntot, M0);
 }
 
 void launch_count_nonfinite(const double* p, size_t count, unsigned long long* out, cudaStream_t st) {

@@ -279,6 +279,7 @@ void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec
 void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
                               double* rVF, cudaStream_t st);
 void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t st);
+void launch_consensus_rows(const double* zloc, const double* zall, double* cons, int nl, int ntot, int M0, cudaStream_t st);
 void launch_yimp0(const Dims& d, const double* mu, const double* beta, const double* z, const double* V, const double* gmean,
                   const double* gsd, double* out, int cell0, int ncell, cudaStream_t st);
 

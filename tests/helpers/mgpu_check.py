@@ -21,7 +21,8 @@ sh = sb.CellShard(n)
 part = sb.EM_impute(sh.cols(st["Y"]), sh.cols(st["Y0"]), st["pg"], M0, K0, 0.1, 4, st["beta"], st["sigma"], st["lam"],
                     st["pi"], sh.rows(st["z"]), celltype=sh.rows(st["celltype"]), comm=sh, **kw)
 mi = sb.do_impute(sh.cols(st["Y0"]), part["Y"], part["beta"], part["lambda"], part["sigma"], part["mu"], part["pi"],
-                  part["geneM"], part["geneSd"], sh.rows(st["celltype"]), mcmc=3, burnin=1, pg=st["pg"], seed=5, comm=sh)
+                  part["geneM"], part["geneSd"], sh.rows(st["celltype"]), mcmc=3, burnin=1, pg=st["pg"], seed=5, comm=sh,
+                  consensus="rows")
 ok = True
 msgs = []
 # the same sharded call with the all-reduce inside the library (its own NCCL rank communicator, no Python callback)
@@ -35,7 +36,7 @@ assert shn.n_allreduce == 0 and sb.load().simples_comm_nranks() == world
 if rank == 0:
     full = sb.EM_impute(*em_args(st, M0, K0, 4), celltype=st["celltype"], **kw)
     fmi = sb.do_impute(st["Y0"], full["Y"], full["beta"], full["lambda"], full["sigma"], full["mu"], full["pi"],
-                       full["geneM"], full["geneSd"], st["celltype"], mcmc=3, burnin=1, pg=st["pg"], seed=5, consensus=False)
+                       full["geneM"], full["geneSd"], st["celltype"], mcmc=3, burnin=1, pg=st["pg"], seed=5, consensus=True)
     for k in ("loglik", "pi", "mu", "sigma", "beta", "lambda", "geneM"):
         e = rel(part[k], full[k]); msgs.append(f"{k}={e:.1e}"); ok &= e <= 1e-9
     a, b = sh.bounds[0], sh.bounds[1]
@@ -43,6 +44,7 @@ if rank == 0:
         e = rel(part[k], sl); msgs.append(f"{k}[shard0]={e:.1e}"); ok &= e <= 1e-8
     e = abs(mi["loglik"] - fmi["loglik"]) / abs(fmi["loglik"]); msgs.append(f"mi.loglik={e:.1e}"); ok &= e <= 1e-9
     e = rel(mi["impt"], fmi["impt"][:, a:b]); msgs.append(f"mi.impt[shard0]={e:.1e}"); ok &= e <= 1e-8
+    e = rel(mi["consensus_cluster"], fmi["consensus_cluster"][a:b, :]); msgs.append(f"mi.consensus[rows of shard0]={e:.1e}"); ok &= e <= 1e-9
     print(json.dumps({"world": world, "ok": bool(ok), "allreduces_em+mi": sh.n_allreduce, "errs": msgs}), flush=True)
 # ---- run-level driver, cells sharded: init fit, hq EM, lq fit, all-gene EM, MI and the clustering start ----
 import oracle as O

@@ -106,7 +106,7 @@ def test_single_process_multi_gpu_c_abi(sb):
     st = make_case(3001, 700, 4, 4, K0, M0, seed=31)
     kw = dict(celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=13, num_mc=2)
     one = sb.EM_impute(*em_args(st, M0, K0, 4), **kw)
-    mi_kw = dict(mcmc=3, burnin=1, pg=st["pg"], seed=5, consensus=False)
+    mi_kw = dict(mcmc=3, burnin=1, pg=st["pg"], seed=5, consensus=True)
     mi_args = (st["Y0"], one["Y"], one["beta"], one["lambda"], one["sigma"], one["mu"], one["pi"], one["geneM"],
                one["geneSd"], st["celltype"])
     mi_one = sb.do_impute(*mi_args, **mi_kw)
@@ -122,6 +122,7 @@ def test_single_process_multi_gpu_c_abi(sb):
         assert rel(two["Ef"][m], one["Ef"][m]) <= 1e-8
     assert abs(mi_two["loglik"] - mi_one["loglik"]) <= 1e-9 * abs(mi_one["loglik"])
     assert rel(mi_two["impt"], mi_one["impt"]) <= 1e-8 and rel(mi_two["EF"], mi_one["EF"]) <= 1e-8
+    assert rel(mi_two["consensus_cluster"], mi_one["consensus_cluster"]) <= 1e-9     # row blocks filled by the two devices
 
 
 def test_expect_mode_matches_oracle_20k_cells(sb):
