@@ -42,12 +42,18 @@ __device__ __host__ inline StatView stat_view(const double* st, const Dims& d, i
 
 // Exact active-set polish of a coordinate-descent iterate (one warp, lane k owns coordinate k):
 // solve A_SS x = rhs_S - kappa sign_S and verify the KKT conditions.  On success b is overwritten.
-__device__ bool lasso_polish(const double* A, int K, double rhs, double kappa, double& b, double* L, double* xs, int* idx,
-                             int lane) {
+// Returns 0 on success (b overwritten), 1 when the restricted system is not positive definite / nothing to adopt,
+// 2 when a coordinate of the restricted solution changes sign (the support is too large), 3 when an inactive coordinate
+// violates the KKT conditions (the support is too small).  For 2 and 3 `cand` receives the restricted solution of the
+// lane's coordinate with sign-flipped coordinates set to 0 -- a much better restart point for coordinate descent than
+// waiting for a coefficient to creep to zero.
+__device__ int lasso_polish(const double* A, int K, double rhs, double kappa, double& b, double* L, double* xs, int* idx,
+                            int lane, double& cand) {
     const bool kl = lane < K;
+    cand = b;
     const unsigned act = __ballot_sync(0xffffffffu, kl && b != 0.0);
     const int ns = __popc(act);
-    if (ns == 0) return __ballot_sync(0xffffffffu, kl && fabs(rhs) > kappa * (1.0 + 1e-12)) == 0u;
+    if (ns == 0) return __ballot_sync(0xffffffffu, kl && fabs(rhs) > kappa * (1.0 + 1e-12)) == 0u ? 0 : 1;
     const int pos = __popc(act & ((1u << lane) - 1u));
     const bool mine = (act >> lane) & 1u;
     if (mine) {
@@ -63,7 +69,7 @@ __device__ bool lasso_polish(const double* A, int K, double rhs, double kappa, d
     warp_cholesky(L, ns, lane);
     bool bad = false;
     for (int i = 0; i < ns; ++i) bad |= !(L[i * ns + i] > 0.0);
-    if (bad) return false;
+    if (bad) return 1;
     // (L L') x = xs: forward / backward substitution, each row a warp-wide dot product (ns <= 32)
     for (int i = 0; i < ns; ++i) {
         const double part = (lane < i) ? L[i * ns + lane] * xs[lane] : 0.0;
@@ -80,13 +86,15 @@ __device__ bool lasso_polish(const double* A, int K, double rhs, double kappa, d
         __syncwarp();
     }
     const double xm = mine ? xs[pos] : 0.0;
-    if (__ballot_sync(0xffffffffu, mine && ((xm > 0.0) != (b > 0.0) || xm == 0.0))) return false;
+    const bool flip = mine && ((xm > 0.0) != (b > 0.0) || xm == 0.0);
+    cand = flip ? 0.0 : xm;
+    if (__ballot_sync(0xffffffffu, flip)) return 2;
     double gk = rhs;
     if (kl && !mine)
         for (int i = 0; i < ns; ++i) gk -= A[lane * K + idx[i]] * xs[i];
-    if (__ballot_sync(0xffffffffu, kl && !mine && fabs(gk) > kappa * (1.0 + 1e-10) + 1e-300)) return false;
+    if (__ballot_sync(0xffffffffu, kl && !mine && fabs(gk) > kappa * (1.0 + 1e-10) + 1e-300)) return 3;
     if (mine) b = xm;
-    return true;
+    return 0;
 }
 
 // min 0.5 b'Ab - rhs'b + kappa |b|_1 : cyclic coordinate descent from 0 (glmnet's start) + exact polish.
@@ -105,24 +113,27 @@ __device__ double lasso_solve(const double* A, int K, double rhs, double kappa, 
                               int debug) {
     double b = 0.0, r = rhs;
     const bool kl = lane < K;
+    // lane k owns coordinate k: its diagonal entry and reciprocal stay in registers, so a coordinate step is
+    // [own candidate: fma, soft threshold, multiply] -> ONE shuffle of the step -> residual update; the round-1 loop
+    // broadcast r_k and b_k (two shuffles) and divided by A_kk inside the chain (the kernel lasts as long as its slowest
+    // gene, so the length of this chain is the kernel's duration)
+    const double akk = kl ? A[lane * K + lane] : 1.0, ikk = 1.0 / akk;
     unsigned pat_p = 0u, pat_n = 0u, fail_p = ~0u, fail_n = ~0u;
-    int stable = 0, last_fail = -1000;
+    int stable = 0, last_fail = -1000, adopted = 0;
     for (int sweep = 0; sweep < 20000; ++sweep) {
-        double maxd = 0.0, maxb = 1.0;
+        double maxd = 0.0;
         for (int k = 0; k < K; ++k) {
-            const double akk = A[k * K + k];
-            const double rk = __shfl_sync(0xffffffffu, r, k), bk = __shfl_sync(0xffffffffu, b, k);
-            const double t = rk + akk * bk;
+            const double t = fma(akk, b, r);
             const double at = fabs(t) - kappa;
-            const double bn = at > 0.0 ? copysign(at, t) / akk : 0.0;
-            const double dlt = bn - bk;
+            const double bn = at > 0.0 ? copysign(at, t) * ikk : 0.0;
+            const double dlt = __shfl_sync(0xffffffffu, bn - b, k);
             if (dlt != 0.0) {
-                if (kl) r -= dlt * A[lane * K + k];
+                if (kl) r = fma(-dlt, A[lane * K + k], r);
                 if (lane == k) b = bn;
             }
             maxd = fmax(maxd, fabs(dlt));
-            maxb = fmax(maxb, fabs(bn));
         }
+        const double maxb = fmax(1.0, warp_max(kl ? fabs(b) : 0.0));
         const bool done = maxd <= 1e-15 * maxb;
         // The exact polish costs several sweeps and can only succeed once the active set has settled: try it when the
         // sign pattern has been the same for three sweeps (a pattern that failed is retried 16 sweeps later, when the
@@ -133,13 +144,32 @@ __device__ double lasso_solve(const double* A, int K, double rhs, double kappa, 
         pat_n = nn;
         const bool fresh = !(np == fail_p && nn == fail_n) || sweep - last_fail >= 16;
         if (done || (stable >= 2 && fresh)) {
-            if (lasso_polish(A, K, rhs, kappa, b, L, xs, idx, lane) || done) {
+            double cand;
+            const int st = lasso_polish(A, K, rhs, kappa, b, L, xs, idx, lane, cand);
+            if (st == 0 || done) {
                 lasso_note(sweep + 1, lane, debug);
                 return b;
             }
             fail_p = np;
             fail_n = nn;
             last_fail = sweep;
+            if (st >= 2 && adopted < 12) {
+                // Active-set step: continue from the exact solution on the current support with the sign-flipped
+                // coordinates dropped (st = 2) / the violating coordinates about to enter by the next sweep (st = 3).
+                // Acceptance is still only by the KKT check above, so this can shorten the path but not change the answer;
+                // the objective is convex, coordinate descent converges from any restart point.
+                ++adopted;
+                b = kl ? cand : 0.0;
+                double rr = rhs;
+                for (int j = 0; j < K; ++j) {
+                    const double bj = __shfl_sync(0xffffffffu, b, j);
+                    if (kl) rr = fma(-bj, A[lane * K + j], rr);
+                }
+                r = rr;
+                stable = 0;
+                fail_p = fail_n = ~0u;
+                last_fail = -1000;
+            }
         }
     }
     lasso_note(20000, lane, debug);
