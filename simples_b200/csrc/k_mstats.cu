@@ -15,12 +15,12 @@ constexpr int KC = 32;      // cells per stage
 constexpr int YS = 68;      // smem row stride of the Y stage (== 4 mod 16)
 constexpr int NCW = 4;      // consumer warps (16 genes each)
 constexpr int THREADS = (NCW + 1) * 32;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;   // ring depth: 4, or fewer when that lets two CTAs share an SM (wide operands)
 
 __host__ __device__ constexpr size_t stage_bytes(int VS) { return size_t(KC) * YS * 8 + size_t(KC) * VS * 8 + KC * 8; }
 
 template <int NT>
-__global__ void __launch_bounds__(THREADS) k_mstats(MstatsArgs a, int cps) {
+__global__ void __launch_bounds__(THREADS) k_mstats(MstatsArgs a, int cps, int STAGES) {
     constexpr int VS = NT * 8 + 4;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -118,11 +118,15 @@ __global__ void __launch_bounds__(THREADS) k_mstats(MstatsArgs a, int cps) {
 template <int NT>
 void launch_nt(const MstatsArgs& a, cudaStream_t st) {
     constexpr int VS = NT * 8 + 4;
-    const size_t smem = 128 + STAGES * stage_bytes(VS);
+    // two resident CTAs (8 consumer warps) keep the DMMA pipe fed; with one CTA per SM the K0 = M0 = 20 operand (NT = 6)
+    // ran at 52 % of the DGEMM rate against 76 % at NT = 3 (profiles/r02_notes.md)
+    int stages = MAX_STAGES;
+    while (stages > 2 && 2 * (128 + stages * stage_bytes(VS) + 1024) > 227 * 1024) --stages;
+    const size_t smem = 128 + stages * stage_bytes(VS);
     ensure_dyn_smem_k(k_mstats<NT>, size_t(int(smem)));
     const int cps = (((a.n + a.splitK - 1) / a.splitK) + KC - 1) / KC * KC;
     dim3 grid(a.ldG / MT, a.splitK);
-    k_mstats<NT><<<grid, THREADS, smem, st>>>(a, cps);
+    k_mstats<NT><<<grid, THREADS, smem, st>>>(a, cps, stages);
 }
 
 __global__ void k_reduce_parts(const double* part, double* out, size_t count, int nparts) {
