@@ -240,7 +240,7 @@ int setup_common(simples_ctx* c, int G, int n, int M0, int K0, int MB, long long
     CKR(c->dalloc(&s.sdsA, size_t(ldG) * M0));
     CKR(c->dalloc(&s.isdA, size_t(ldG) * M0));
     CKR(c->dalloc(&s.musdA, size_t(ldG) * M0));
-    CKR(c->dalloc(&s.igs, size_t(ldG)));
+    CKR(c->dalloc(&s.gmig, size_t(ldG) * 2));
     CKR(c->dalloc(&s.BM, size_t(ldG) * d.QS));
     CKR(c->dalloc(&s.gv, size_t(ldG) * 4));
     CKR(c->dalloc(&s.mc_counter, 1));
@@ -427,7 +427,7 @@ int e_pass(simples_ctx* c, bool update_z, bool stale_q, bool sample, bool draw_m
 int run_prep(simples_ctx* c) {
     DevState& s = c->s;
     P p(c, KC_PREP, 2);
-    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.igs, s.cc, 0,
+    PrepArgs pa{s.d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.gmig, s.cc, 0,
                 s.BM, s.gv, s.part_prep};
     if (c->profile) {                      // serial on the main stream so the per-class events mean something
         launch_prep(pa, c->stream, c->stream);
@@ -460,8 +460,7 @@ int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2) {
     sa.isdA = s.isdA;
     sa.musdA = s.musdA;
     sa.pg = s.pg;
-    sa.gmean = s.gmean;
-    sa.igs = s.igs;
+    sa.gmig = s.gmig;
     sa.n_alloc = s.n_alloc;
     sa.im = s.im;
     sa.celltype0 = s.celltype0;

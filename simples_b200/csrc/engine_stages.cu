@@ -122,7 +122,7 @@ int simples_lq_fit(const simples_lq_args* a, simples_lq_out* o) {
     CK(cudaGetLastError());
     tr.mark("statistics+regression");
     if (a->impute) {                            // R/SIMPLE.R:376-411
-        PrepArgs pa{d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.igs, s.cc, 0,
+        PrepArgs pa{d, s.beta, s.sigma, s.mu, s.lam, s.pi, s.gmean, s.gsd, s.Q, s.isg, s.Qs, s.sdsA, s.isdA, s.musdA, s.gmig, s.cc, 0,
                     nullptr, nullptr, s.part_prep};
         launch_prep(pa, c->stream, c->stream);
         CKR(run_sweep(c, false, nullptr, nullptr));

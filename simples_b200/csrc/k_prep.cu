@@ -29,7 +29,8 @@ __global__ void k_build_ops(PrepArgs a) {
         a.isdA[size_t(g) * M0 + m] = 1.0 / sdv;
         a.musdA[size_t(g) * M0 + m] = a.mu[size_t(g) * M0 + m] * sd;
     }
-    a.igs[g] = 1.0 / sd;
+    a.gmig[size_t(g) * 2 + 0] = mean;
+    a.gmig[size_t(g) * 2 + 1] = 1.0 / sd;
     if (a.BM) {            // fused MC pass operands (cluster-shared sigma: column 0)
         double* bmr = a.BM + size_t(g) * d.QS;
         for (int k = 0; k < K0; ++k) bmr[k] = a.beta[size_t(g) * K0 + k];

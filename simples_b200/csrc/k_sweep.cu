@@ -7,8 +7,10 @@
 //   2. the set bits of the 8 mask words are compacted (ballot + popc) into a dense work list, so
 //      the expensive per-entry sampler runs with full lanes instead of ~44 % (the zero fraction);
 //   3. each list entry draws from the Philox tape and writes the centred value to Y.
-// Gene-chunk parameters (Qs, sds, 1/sds, pg, mean, 1/sd) are double-buffered in shared memory with
-// cp.async.
+// Gene-chunk parameters (Qs, sds, 1/sds, mu sd, pg, {mean, 1/sd}) travel through a three-stage shared-memory ring filled by
+// the TMA engine (bulk copies completing on an mbarrier).  The warps of a CTA are not synchronised per chunk: the LAST warp
+// to leave a stage (counted with a shared-memory atomic) refills it, so nobody ever waits for a free stage and a fast warp
+// may run up to two chunks ahead of the slowest one.
 #include <cmath>
 #include <cstdlib>
 
@@ -23,6 +25,7 @@ constexpr int SW = 8;          // warps per CTA
 constexpr int SC = SW * 8;     // cells per CTA
 constexpr int SG = 32;         // genes per chunk (= one mask word)
 constexpr int MSS = 34;        // row stride of the per-warp ms tile (doubles)
+constexpr int NST = 3;         // stages of the parameter ring (2 when a third one would cost a resident CTA)
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -31,7 +34,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct ChunkBuf {
-    double *Q, *sds, *isd, *musd, *pg, *gm, *igs;
+    double *Q, *sds, *isd, *musd, *pg;
+    double2* gi;       // {gene mean, 1 / gene sd}
 };
 
 __device__ __forceinline__ ChunkBuf chunk_buf(double* base, int FS, int M0, int MB) {
@@ -41,13 +45,12 @@ __device__ __forceinline__ ChunkBuf chunk_buf(double* base, int FS, int M0, int 
     b.isd = b.sds + SG * M0;
     b.musd = b.isd + SG * M0;
     b.pg = b.musd + SG * M0;
-    b.gm = b.pg + SG * MB;
-    b.igs = b.gm + SG;
+    b.gi = reinterpret_cast<double2*>(b.pg + SG * MB);
     return b;
 }
 __host__ __device__ inline int chunk_doubles(int FS, int M0, int MB) { return SG * FS + 3 * SG * M0 + SG * MB + 2 * SG; }
 
-// one thread: TMA bulk copies of the six parameter spans of gene chunk `chunk`, completing on `bar`
+// one thread: TMA bulk copies of the parameter spans of gene chunk `chunk`, completing on `bar`
 __device__ __forceinline__ void load_chunk_bulk(const SweepArgs& a, const ChunkBuf& b, int chunk, uint64_t* bar) {
     const int g0 = chunk * SG, FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB;
     mbar_arrive_expect_tx(bar, uint32_t(chunk_doubles(FS, M0, MB)) * 8u);
@@ -56,8 +59,13 @@ __device__ __forceinline__ void load_chunk_bulk(const SweepArgs& a, const ChunkB
     bulk_g2s(b.isd, a.isdA + size_t(g0) * M0, SG * M0 * 8, bar);
     bulk_g2s(b.musd, a.musdA + size_t(g0) * M0, SG * M0 * 8, bar);
     bulk_g2s(b.pg, a.pg + size_t(g0) * MB, SG * MB * 8, bar);
-    bulk_g2s(b.gm, a.gmean + g0, SG * 8, bar);
-    bulk_g2s(b.igs, a.igs + g0, SG * 8, bar);
+    bulk_g2s(b.gi, a.gmig + size_t(g0) * 2, SG * 16, bar);
+}
+
+__device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
 }
 
 // NKS = number of K-steps of 4 held as register A-fragments (K0 <= 4 NKS); MINB = resident CTAs per SM aimed at
@@ -65,15 +73,16 @@ template <int NKS, int MINB>
 __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__ SweepArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB, ldG = a.d.ldG, n = a.d.n;
-    const int KST = a.d.NFP / 4;
+    const int KST = a.d.NFP / 4, nst = a.nst;
     const int CD = chunk_doubles(FS, M0, MB);
     // Shared-memory layout: fixed-size blocks first (barriers, then one statically laid out block per warp) so that
     // all per-warp addressing is `warp base + compile-time offset`; the runtime-sized parameter buffers follow.
     constexpr int WBLK = 8 * MSS * 8 + 256 * 8 + 768 + 64;      // bytes per warp: ms tile | dub | codes | cell info
     unsigned char* smb = reinterpret_cast<unsigned char*>(sm);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smb);                            // full[2], empty[2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smb);                            // full[NST]: the stage's chunk has landed
+    unsigned* cnt = reinterpret_cast<unsigned*>(smb + 32);                        // cnt[NST]:  warps that have left the stage
     unsigned char* wblk = smb + 64 + (threadIdx.x >> 5) * WBLK;
-    double* sBuf = reinterpret_cast<double*>(smb + 64 + SW * WBLK);               // [2][CD] parameter chunks
+    double* sBuf = reinterpret_cast<double*>(smb + 64 + SW * WBLK);               // [NST][CD] parameter chunks
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cell0 = blockIdx.x * SC;
     const int wc0 = cell0 + warp * 8;           // first cell of this warp
@@ -94,18 +103,18 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
     const int cbeg = int((long long)nchunks_all * blockIdx.y / gridDim.y);
     const int cend = int((long long)nchunks_all * (blockIdx.y + 1) / gridDim.y);
     const int nchunks = cend - cbeg;
-    // Parameter pipeline: two buffers with full / empty mbarriers.  Warps are NOT barrier-synchronised per chunk:
-    // a warp starts chunk c as soon as full[c & 1] has completed; thread 0 refills a buffer once all 8 warps have
-    // released it (the warps of a CTA drift by at most one chunk).
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_init(&bars[2], SW);
-        mbar_init(&bars[3], SW);
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&full[s], 1);
+            cnt[s] = 0u;
+        }
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0 && nchunks > 0) load_chunk_bulk(a, chunk_buf(sBuf, FS, M0, MB), cbeg, &bars[0]);
+    if (tid == 0) {
+        for (int s = 0; s < nst && s < nchunks; ++s) load_chunk_bulk(a, chunk_buf(sBuf + s * CD, FS, M0, MB), cbeg + s, &full[s]);
+    }
 
     double* msW = reinterpret_cast<double*>(wblk);                     // [8][MSS] conditional means / deltas
     double* dub = msW + 8 * MSS;                                       // [256]    list values
@@ -113,26 +122,38 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
     unsigned char* dcode = list + 256;                                 // [256] Dc (front) / back list codes
     unsigned char* xcode = list + 512;                                 // [256] uncertain entries
     int* cellinfo = reinterpret_cast<int*>(list + 768);                // [8][2] (im, celltype)
+    const unsigned lt = (1u << lane) - 1u;
 
+    // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes), fetched one chunk ahead
+    const bool mlane = lane < 8 && wc0 + lane < n;
+    unsigned wnext = (mlane && nchunks > 0) ? a.mask[size_t(cbeg) * a.n_alloc + wc0 + lane] : 0u;
+    int st = 0;                 // ring stage of the current chunk
+    unsigned use = 0;           // how often the ring has wrapped (= ci / nst)
     for (int ci = 0; ci < nchunks; ++ci) {
         const int chunk = cbeg + ci;                   // absolute gene-chunk index
-        const int sb_ = ci & 1;
-        if (tid == 0 && ci + 1 < nchunks) {            // refill the other buffer for the next chunk
-            if (ci >= 1) mbar_wait(&bars[2 + (sb_ ^ 1)], ((ci - 1) >> 1) & 1);
-            load_chunk_bulk(a, chunk_buf(sBuf + (sb_ ^ 1) * CD, FS, M0, MB), chunk + 1, &bars[sb_ ^ 1]);
-        }
-        __syncwarp();
-        mbar_wait(&bars[sb_], (ci >> 1) & 1);           // this chunk's parameters have landed
-        const ChunkBuf b = chunk_buf(sBuf + sb_ * CD, FS, M0, MB);
+        const unsigned word = wnext;
+        wnext = (mlane && ci + 1 < nchunks) ? a.mask[size_t(chunk + 1) * a.n_alloc + wc0 + lane] : 0u;
+        mbar_wait(&full[st], use & 1u);                // this chunk's parameters have landed
+        const ChunkBuf b = chunk_buf(sBuf + st * CD, FS, M0, MB);
 
-        // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes)
-        unsigned word = 0u;
-        if (lane < 8 && wc0 + lane < n) word = a.mask[size_t(chunk) * a.n_alloc + wc0 + lane];
-        if (__ballot_sync(0xffffffffu, word != 0u) == 0u) {
-            if (lane == 0) mbar_arrive(&bars[2 + sb_]);
-            continue;
-        }
+        auto finish = [&](int r, int gl, double x, bool trunc) {
+            // clamp to the cutoff (truncated draws, R/EM_impute.R:191-192) and to [lower, upper] (:196-197) -- the three
+            // bounds are folded into two on the host (+-inf when the sweep does not clip); plain compare-and-select, the
+            // operands are never NaN
+            const double h = trunc ? a.hi_trunc : a.hi;
+            x = x > h ? h : x;
+            x = x < a.lo ? a.lo : x;
+            const double2 gi = b.gi[gl];
+            const double v = (x - gi.x) * gi.y;
+            const size_t o = size_t(wc0 + r) * ldG + chunk * SG + gl;
+            a.Y[o] = v;
+            if (a.rec1) {
+                a.rec1[o] += v;
+                a.rec2[o] += v * v;
+            }
+        };
 
+        if (__ballot_sync(0xffffffffu, word != 0u) != 0u) {
         // ---- 1. conditional means of the 8 x 32 block ----
         double acc[4][2];
 #pragma unroll
@@ -149,8 +170,8 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int g0 = nt * 8 + 2 * t;
-                acc[nt][0] += b.musd[g0 * M0 + img] + b.gm[g0];
-                acc[nt][1] += b.musd[(g0 + 1) * M0 + img] + b.gm[g0 + 1];
+                acc[nt][0] += b.musd[g0 * M0 + img] + b.gi[g0].x;
+                acc[nt][1] += b.musd[(g0 + 1) * M0 + img] + b.gi[g0 + 1].x;
             }
         }
 #pragma unroll
@@ -162,11 +183,21 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const unsigned w = __shfl_sync(0xffffffffu, word, r);
-            if ((w >> lane) & 1u) list[total + __popc(w & ((1u << lane) - 1u))] = (unsigned char)((r << 5) | lane);
+            if ((w >> lane) & 1u) list[total + __popc(w & lt)] = (unsigned char)((r << 5) | lane);
             total += __popc(w);
         }
         __syncwarp();
 
+        if (a.expect) {      // SIMPLES_MODE_EXPECT (warp-uniform): every entry gets its conditional expectation, no variates
+#pragma unroll 1
+            for (int e = lane; e < total; e += 32) {
+                const int code = list[e];
+                const int r = code >> 5, gl = code & 31;
+                const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
+                finish(r, gl, expect_entry(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct], a.cutoff),
+                       false);
+            }
+        } else {
         // ---- 3a. classify every zero entry with an FP32 screen of the Bernoulli test ----
         // Phi(r) in float by Abramowitz-Stegun 7.1.26 (|err| < 5e-7 incl. MUFU.RCP / MUFU.EX2); an entry whose
         // test statistic clears the +-4e-6 band has a CERTAIN outcome:
@@ -175,24 +206,6 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
         //   U : inside the band (~1e-5 of the entries) -> exact FP64 decision
         int nDc = 0, nS = 0, nU = 0;
         const int rounds = (total + 31) >> 5;
-        if (a.expect) {      // SIMPLES_MODE_EXPECT (warp-uniform): every entry gets its conditional expectation, no variates
-#pragma unroll 1
-            for (int e = lane; e < total; e += 32) {
-                const int code = list[e];
-                const int r = code >> 5, gl = code & 31;
-                const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
-                const double x = expect_entry(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct], a.cutoff);
-                double xx = x;
-                if (a.clip) {
-                    xx = fmin(xx, a.upper);
-                    xx = fmax(xx, a.lower);
-                }
-                a.Y[size_t(wc0 + r) * ldG + chunk * SG + gl] = (xx - b.gm[gl]) * b.igs[gl];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[2 + sb_]);
-            continue;
-        }
 #pragma unroll 2
         for (int it = 0; it < rounds; ++it) {
             const int e = it * 32 + lane;
@@ -221,41 +234,28 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             const bool isD = valid && (d < -4e-6f);
             const bool isT = valid && (d > 4e-6f);
             const bool cen = fabs(ub - 0.5) <= 0.425;
-            const bool toDc = isD && cen, toS = (isD && !cen) || isT, toU = valid && !isD && !isT;
+            const bool toDc = isD && cen, toS = (isD && !cen) || isT;
             const unsigned bDc = __ballot_sync(0xffffffffu, toDc);
             const unsigned bS = __ballot_sync(0xffffffffu, toS);
-            const unsigned bU = __ballot_sync(0xffffffffu, toU);
-            const unsigned lt = (1u << lane) - 1u;
-            if (toDc) {
-                const int pos = nDc + __popc(bDc & lt);
-                dcode[pos] = (unsigned char)code;
-                dub[pos] = ub;
-            } else if (toS) {
-                const int pos = 255 - (nS + __popc(bS & lt));
-                dcode[pos] = (unsigned char)code;
-                dub[pos] = isT ? -ub : ub;
-            } else if (toU) {
-                xcode[nU + __popc(bU & lt)] = (unsigned char)code;
+            const unsigned bV = __ballot_sync(0xffffffffu, valid);
+            {   // front list (Dc) grows upwards from 0, back list (S) downwards from 255: one store pair for either
+                const int p = __popc((toDc ? bDc : bS) & lt);
+                const int pos = toDc ? nDc + p : 255 - nS - p;
+                if (toDc || toS) {
+                    dcode[pos] = (unsigned char)code;
+                    dub[pos] = isT ? -ub : ub;
+                }
+            }
+            const unsigned bU = bV & ~(bDc | bS);
+            if (bU) {                                               // rare (~1e-5 of the entries)
+                if ((bU >> lane) & 1u) xcode[nU + __popc(bU & lt)] = (unsigned char)code;
+                nU += __popc(bU);
             }
             nDc += __popc(bDc);
             nS += __popc(bS);
-            nU += __popc(bU);
         }
         __syncwarp();
 
-        auto finish = [&](int r, int gl, double x) {
-            if (a.clip) {
-                x = fmin(x, a.upper);
-                x = fmax(x, a.lower);
-            }
-            const double v = (x - b.gm[gl]) * b.igs[gl];
-            const size_t o = size_t(wc0 + r) * ldG + chunk * SG + gl;
-            a.Y[o] = v;
-            if (a.rec1) {
-                a.rec1[o] += v;
-                a.rec2[o] += v * v;
-            }
-        };
         // ---- 3b. T-stage: for the certain "expressed but <= cutoff" entries of the back list compute the quantile
         //      argument ub * Phi(r) (the only place the FP64 pnorm runs) and re-file them by quantile region:
         //      central -> appended to the Dc list, tail -> compacted back list.  Stored value < 0 marks a
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
                     const double ms = msW[r * MSS + gl];
                     const double rr = (a.cutoff - ms) * b.isd[gl * M0 + im];
                     if (rr < -30.0) {                // deep tail: log-space Newton, finished right here (cold)
-                        finish(r, gl, fma(b.sds[gl * M0 + im], trunc_z_deep(-v, rr), ms));
+                        finish(r, gl, fma(b.sds[gl * M0 + im], trunc_z_deep(-v, rr), ms), false);
                         toTail = false;
                     } else {
                         const double q = -v * pnorm(rr);
@@ -298,15 +298,13 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
                 __syncwarp();                        // every lane has read its slot before slots are rewritten
                 const unsigned bC = __ballot_sync(0xffffffffu, toC);
                 const unsigned bT = __ballot_sync(0xffffffffu, toTail);
-                const unsigned lt = (1u << lane) - 1u;
-                if (toC) {
-                    const int pos = nDc + __popc(bC & lt);
-                    dcode[pos] = (unsigned char)code;
-                    dub[pos] = arg;
-                } else if (toTail) {
-                    const int pos = 255 - (nTail + __popc(bT & lt));
-                    dcode[pos] = (unsigned char)code;
-                    dub[pos] = arg;
+                {
+                    const int p = __popc((toC ? bC : bT) & lt);
+                    const int pos = toC ? nDc + p : 255 - nTail - p;
+                    if (toC || toTail) {
+                        dcode[pos] = (unsigned char)code;
+                        dub[pos] = arg;
+                    }
                 }
                 nDc += __popc(bC);
                 nTail += __popc(bT);
@@ -319,9 +317,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             const int code = dcode[e];
             const double v = dub[e];
             const int r = code >> 5, gl = code & 31;
-            double x = fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_central(fabs(v)), msW[r * MSS + gl]);
-            if (v < 0.0) x = fmin(x, a.cutoff);
-            finish(r, gl, x);
+            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_central(fabs(v)), msW[r * MSS + gl]), v < 0.0);
         }
         // ---- 3c'. tail quantiles ----
 #pragma unroll 1
@@ -329,9 +325,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             const int code = dcode[255 - e];
             const double v = dub[255 - e];
             const int r = code >> 5, gl = code & 31;
-            double x = fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_tail(fabs(v)), msW[r * MSS + gl]);
-            if (v < 0.0) x = fmin(x, a.cutoff);
-            finish(r, gl, x);
+            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_tail(fabs(v)), msW[r * MSS + gl]), v < 0.0);
         }
         // ---- 3c''. dense block: the whole back list, arguments in place, either quantile region ----
         if (inplace) {
@@ -341,7 +335,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
                 const int code = dcode[255 - e];
                 const double v = dub[255 - e];
                 const int r = code >> 5, gl = code & 31;
-                if (v != 0.0) finish(r, gl, quantile_draw(msW[r * MSS + gl], b.sds[gl * M0 + cellinfo[r * 2]], a.cutoff, v));
+                if (v != 0.0) finish(r, gl, quantile_draw(msW[r * MSS + gl], b.sds[gl * M0 + cellinfo[r * 2]], a.cutoff, v), v < 0.0);
             }
         }
         // ---- 3d. inside the screening band: exact FP64 Bernoulli test and draw ----
@@ -353,10 +347,20 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             double ua, ub;
             entry_uniforms(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + wc0 + r), (uint32_t)(chunk * SG + gl), ua, ub);
             finish(r, gl, sample_entry(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct],
-                                       a.cutoff, ua, ub));
+                                       a.cutoff, ua, ub), false);
         }
+        }   // sampling mode
+        }   // block has zero entries
+        // ---- leave the stage; the last warp out refills it with the chunk `nst` further on ----
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[2 + sb_]);     // this warp no longer reads the chunk's parameters
+        if (lane == 0) {
+            const unsigned old = atom_add_acq_rel(&cnt[st], 1u);
+            if (old == SW * (use + 1u) - 1u && ci + nst < nchunks) load_chunk_bulk(a, b, chunk + nst, &full[st]);
+        }
+        if (++st == nst) {
+            st = 0;
+            ++use;
+        }
     }
 }
 
@@ -370,10 +374,18 @@ static void launch_variant(const SweepArgs& a, dim3 grid, size_t smem, cudaStrea
 
 void launch_sweep(SweepArgs a, cudaStream_t st) {
     philox_round_keys(a.seed, a.rk);
-    const size_t smem = sizeof(double) * (size_t(SW) * 8 * MSS + 2 * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) +
-                        SW * 256 * sizeof(double) + SW * 768 + SW * 16 * sizeof(int) + 64;
+    a.hi = a.clip ? a.upper : HUGE_VAL;
+    a.lo = a.clip ? a.lower : -HUGE_VAL;
+    a.hi_trunc = std::min(a.cutoff, a.hi);
+    auto smem_for = [&](int nst) {
+        return sizeof(double) * (size_t(SW) * 8 * MSS + nst * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) + SW * 256 * sizeof(double) +
+               SW * 768 + SW * 16 * sizeof(int) + 64;
+    };
+    auto resident_for = [](size_t smem) { return smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1); };
+    a.nst = resident_for(smem_for(NST)) == resident_for(smem_for(2)) ? NST : 2;
+    const size_t smem = smem_for(a.nst);
     const int tiles = (a.d.n + SC - 1) / SC;
-    const int resident = smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1);
+    const int resident = resident_for(smem);
     // gridDim.y splits the gene range: more, smaller CTAs even out the tail of the last wave.  Measured on B200 at
     // 12.5k-100k cells x 2000 genes (profiles/r02_notes.md): 5-8 parts are within 1 % of each other and up to 15 % faster
     // than the wave-count model of round 1 at the small shards of a strongly scaled run; keep >= 8 chunks per CTA.

@@ -7,7 +7,7 @@
 //   Q      [NS][ldG][QS]   projection operand  [B/sigma_s | mu_m/sigma_cs(m) | 0-pad]
 //   isg    [NS][ldG]       1/sigma_s
 //   Qs     [ldG][FS]       sweep operand       [B*sd | 0-pad]
-//   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  musdA = mu*sd,  igs [ldG] = 1/sd
+//   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  musdA = mu*sd,  gmig [ldG][2] = {gene mean, 1/sd}
 //   P      [NS][n][NQP]    Y^T Q          S2 [NS][n]   sum_g Y^2/sigma_s
 //   V      [n][VS]         M-step operand [Wbar (K0) | z (M0) | sum_m sqrt z_m (1) | 0-pad],  zsum [n]
 //   Fh     [n][FS]         sweep operand  [f_i (K0) | 0-pad]   (the membership m_i is in im[n])
@@ -68,7 +68,7 @@ struct DevState {
     double *Y, *beta, *sigma, *mu, *pg, *gmean, *gsd, *lam, *pi, *z;
     uint32_t* mask;
     int32_t* celltype0;
-    double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs, *P, *S2, *V, *zsum, *Fh, *W;
+    double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *gmig, *P, *S2, *V, *zsum, *Fh, *W;
     double *BM, *gv;     // fused MC pass operands: [ldG][QS] rows [B_g | mu_g | 0], [ldG][4] {isd, sds, mean, 1/sd}
     unsigned* mc_counter;
     double* proj_part;   // k_proj tail-split scratch
@@ -129,10 +129,12 @@ void launch_cell(const CellArgs& a, cudaStream_t st);
 
 struct SweepArgs {
     Dims d;
-    double* Y; const uint32_t* mask; const double *Qs, *Fh, *sdsA, *isdA, *musdA, *pg, *gmean, *igs;
+    double* Y; const uint32_t* mask; const double *Qs, *Fh, *sdsA, *isdA, *musdA, *pg, *gmig;
     int n_alloc;
     const int32_t *im, *celltype0;
     double cutoff, lower, upper;
+    double hi, lo, hi_trunc;   // clamp bounds folded by launch_sweep: [lower, upper] or +-inf, min(cutoff, hi)
+    int nst;                   // parameter ring depth, chosen by launch_sweep
     int clip;
     unsigned long long seed; unsigned sweep;
     uint32_t rk[20];       // Philox round keys, filled by launch_sweep
@@ -185,7 +187,7 @@ void launch_finalize_cell(const double* part_cell, int ncta, int M0, double* out
 
 struct PrepArgs {
     Dims d; const double *beta, *sigma, *mu, *lam, *pi, *gmean, *gsd;
-    double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *igs; ClusterConsts cc; int stale_q;
+    double *Q, *isg, *Qs, *sdsA, *isdA, *musdA, *gmig; ClusterConsts cc; int stale_q;
     double *BM, *gv;     // may be nullptr
     double* part_prep;   // k_gram partials: prep_scratch_doubles()
 };
