@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
     double* Pb = Pa + 8 * PWS;                                               // [8][PWS]  x2 source for W, mu column (general path only)
     double* llw = Pa + (NS == 1 ? 1 : 2) * 8 * PWS;                          // [8][M0]
     double* zw = llw + 8 * M0;                                               // [8][M0]
-    double* wsw = zw + 8 * M0;                                               // [8][KPS]  W of the sampled cluster
+    double* sqw = zw + 8 * M0;                                               // [8][M0]   sqrt(z), formed once per (cell, cluster)
+    double* wsw = sqw + 8 * M0;                                              // [8][KPS]  W of the sampled cluster
     double* epw = wsw + 8 * KPS;                                             // [8][KR]   factor normals
     p += CW * pw_doubles;
     int* imw = reinterpret_cast<int*>(p) + warp * 8;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         double ls = 0.0;
         for (int m = t; m < M0; m += 4) {
-            const double e = exp(llw[g * M0 + m] - mx);
+            const double e = exp_neg(llw[g * M0 + m] - mx);
             zw[g * M0 + m] = e;
             ls += e;
         }
@@ -156,16 +157,17 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
             } else {
                 z = rv ? a.z[size_t(cell) * M0 + m] : 0.0;
             }
-            zw[g * M0 + m] = rv ? z : 0.0;
+            z = rv ? z : 0.0;
+            zw[g * M0 + m] = z;
+            sqw[g * M0 + m] = sqrt_unit(z);
         }
         if (t == 0 && rv) tot_acc += log(ls) + mx;
         __syncwarp();
         if (ml) {
             double s = 0.0, c = 0.0;
             for (int r = 0; r < 8; ++r) {
-                const double z = zw[r * M0 + lane];
-                s += z;
-                c += sqrt(z);
+                s += zw[r * M0 + lane];
+                c += sqw[r * M0 + lane];
             }
             nz_acc += s;
             c_acc += c;
@@ -269,12 +271,12 @@ __global__ void __launch_bounds__(CW * 32, (KSX <= 4 ? 4 : 2)) k_cell(CellArgs a
                 if (a.write_Vg) {
                     double* vg = a.Vg + size_t(cell) * VGS + K0 * M0;
                     vg[m] = z;
-                    vg[M0 + m] = sqrt(z);
+                    vg[M0 + m] = sqw[g * M0 + m];
                 }
             }
             for (int m = 0; m < M0; ++m) {
                 zs += zw[g * M0 + m];
-                zq += sqrt(zw[g * M0 + m]);
+                zq += sqw[g * M0 + m];
             }
             if (t == 0) {
                 a.zsum[cell] = zs;
@@ -339,7 +341,7 @@ __global__ void k_finalize_cell(const double* part, int ncta, int R, double* out
 void launch_cell(const CellArgs& a, cudaStream_t st) {
     const int M0 = a.d.M0, K0 = a.d.K0;
     const int KS = (K0 + 3) / 4, NT = (K0 + 7) / 8, KR = 4 * KS, KPS = 8 * NT + 4, PWS = a.d.NQP + 4;
-    const int pw_doubles = (a.d.NS == 1 ? 1 : 2) * 8 * PWS + 8 * M0 * 2 + 8 * KPS + 8 * KR;
+    const int pw_doubles = (a.d.NS == 1 ? 1 : 2) * 8 * PWS + 8 * M0 * 3 + 8 * KPS + 8 * KR;
     const size_t fixed = sizeof(double) * (size_t(2) * M0 * KR + 3 * M0 + CW * (2 * M0 + 1) + size_t(CW) * pw_doubles) +
                          sizeof(int) * CW * 8;
     // The padded M_m tables (M0 * KR * KPS doubles, 19 KB at K0 = M0 = 10) are read through L1 instead of being

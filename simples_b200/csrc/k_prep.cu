@@ -27,7 +27,7 @@ __global__ void k_build_ops(PrepArgs a) {
         const double sdv = sqrt(a.sigma[size_t(g) * M0 + m]) * sd;
         a.sdsA[size_t(g) * M0 + m] = sdv;
         a.isdA[size_t(g) * M0 + m] = 1.0 / sdv;
-        a.musdA[size_t(g) * M0 + m] = a.mu[size_t(g) * M0 + m] * sd;
+        a.musdA[size_t(g) * M0 + m] = fma(a.mu[size_t(g) * M0 + m], sd, mean);
     }
     a.gmig[size_t(g) * 2 + 0] = mean;
     a.gmig[size_t(g) * 2 + 1] = 1.0 / sd;

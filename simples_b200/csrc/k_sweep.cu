@@ -3,7 +3,7 @@
 //
 // A warp owns 8 cells and walks the genes in 32-gene chunks (= one mask word per cell):
 //   1. ms(8 cells x 32 genes) = Fh * Qs^T by FP64 DMMA (Fh_i = f_i, Qs_g = B_g sd_g; depth K0, A-fragments in
-//      registers) + mu_g,m(i) sd_g + mean_g gathered from the chunk parameters -> per-warp shared-memory tile;
+//      registers) + (mu_g,m(i) sd_g + mean_g) gathered from the chunk parameters -> per-warp shared-memory tile;
 //   2. the set bits of the 8 mask words are compacted (ballot + popc) into a dense work list, so
 //      the expensive per-entry sampler runs with full lanes instead of ~44 % (the zero fraction);
 //   3. each list entry draws from the Philox tape and writes the centred value to Y.
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
     const int CD = chunk_doubles(FS, M0, MB);
     // Shared-memory layout: fixed-size blocks first (barriers, then one statically laid out block per warp) so that
     // all per-warp addressing is `warp base + compile-time offset`; the runtime-sized parameter buffers follow.
-    constexpr int WBLK = 8 * MSS * 8 + 256 * 8 + 768 + 64;      // bytes per warp: ms tile | dub | codes | cell info
+    constexpr int WBLK = 8 * MSS * 8 + 256 * 8 + 768 + 128;     // bytes per warp: ms tile | dub | codes | cell info
     unsigned char* smb = reinterpret_cast<unsigned char*>(sm);
     uint64_t* full = reinterpret_cast<uint64_t*>(smb);                            // full[NST]: the stage's chunk has landed
     unsigned* cnt = reinterpret_cast<unsigned*>(smb + 32);                        // cnt[NST]:  warps that have left the stage
@@ -94,9 +94,10 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
     }
     if (lane < 8) {
         const int cell = wc0 + lane;
-        int* ci = reinterpret_cast<int*>(wblk + 8 * MSS * 8 + 256 * 8 + 768);
-        ci[lane * 2 + 0] = cell < n ? a.im[cell] : 0;
-        ci[lane * 2 + 1] = cell < n ? a.celltype0[cell] : 0;
+        // per cell: cluster, cell type and the cell's two Philox counter words (global cell index: low word, high word << 8)
+        const unsigned long long gc = (unsigned long long)(a.d.cell_offset + cell);
+        reinterpret_cast<int4*>(wblk + 8 * MSS * 8 + 256 * 8 + 768)[lane] =
+            make_int4(cell < n ? a.im[cell] : 0, cell < n ? a.celltype0[cell] : 0, int(uint32_t(gc)), int(uint32_t(gc >> 32) << 8));
     }
     // gridDim.y splits the gene range (wave-quantisation fix: more, smaller CTAs); this CTA walks chunks [cbeg, cend)
     const int nchunks_all = ldG / SG;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
     unsigned char* list = reinterpret_cast<unsigned char*>(dub + 256); // [256] all zero entries
     unsigned char* dcode = list + 256;                                 // [256] Dc (front) / back list codes
     unsigned char* xcode = list + 512;                                 // [256] uncertain entries
-    int* cellinfo = reinterpret_cast<int*>(list + 768);                // [8][2] (im, celltype)
+    int* cellinfo = reinterpret_cast<int*>(list + 768);                // [8][4] (im, celltype, counter words)
     const unsigned lt = (1u << lane) - 1u;
 
     // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes), fetched one chunk ahead
@@ -136,6 +137,8 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
         mbar_wait(&full[st], use & 1u);                // this chunk's parameters have landed
         const ChunkBuf b = chunk_buf(sBuf + st * CD, FS, M0, MB);
 
+        const size_t blk0 = size_t(wc0) * ldG + chunk * SG;
+        double* const yblk = a.Y + blk0;
         auto finish = [&](int r, int gl, double x, bool trunc) {
             // clamp to the cutoff (truncated draws, R/EM_impute.R:191-192) and to [lower, upper] (:196-197) -- the three
             // bounds are folded into two on the host (+-inf when the sweep does not clip); plain compare-and-select, the
@@ -145,11 +148,12 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             x = x < a.lo ? a.lo : x;
             const double2 gi = b.gi[gl];
             const double v = (x - gi.x) * gi.y;
-            const size_t o = size_t(wc0 + r) * ldG + chunk * SG + gl;
-            a.Y[o] = v;
+            const int o = r * ldG + gl;                 // offset inside the warp's 8 x 32 block (32-bit arithmetic)
+            yblk[o] = v;
             if (a.rec1) {
-                a.rec1[o] += v;
-                a.rec2[o] += v * v;
+                const size_t ro = blk0 + o;
+                a.rec1[ro] += v;
+                a.rec2[ro] += v * v;
             }
         };
 
@@ -165,13 +169,13 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
                 for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], fr[ks], b.Q[(nt * 8 + g) * FS + ks * 4 + t]);
             }
         }
-        {   // + mu_{g, m(i)} sd_g + mean_g for the lane's cell g and its genes nt*8 + 2t, +1
-            const int img = cellinfo[g * 2];
+        {   // + (mu_{g, m(i)} sd_g + mean_g) for the lane's cell g and its genes nt*8 + 2t, +1
+            const int img = cellinfo[g * 4];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int g0 = nt * 8 + 2 * t;
-                acc[nt][0] += b.musd[g0 * M0 + img] + b.gi[g0].x;
-                acc[nt][1] += b.musd[(g0 + 1) * M0 + img] + b.gi[g0 + 1].x;
+                acc[nt][0] += b.musd[g0 * M0 + img];
+                acc[nt][1] += b.musd[(g0 + 1) * M0 + img];
             }
         }
 #pragma unroll
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             for (int e = lane; e < total; e += 32) {
                 const int code = list[e];
                 const int r = code >> 5, gl = code & 31;
-                const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
+                const int im = cellinfo[r * 4], ct = cellinfo[r * 4 + 1];
                 finish(r, gl, expect_entry(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct], a.cutoff),
                        false);
             }
@@ -212,10 +216,10 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             const bool valid = e < total;
             const int code = valid ? list[e] : 0;
             const int r = code >> 5, gl = code & 31;
-            const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
+            const int4 cinf = reinterpret_cast<const int4*>(cellinfo)[r];
+            const int im = cinf.x, ct = cinf.y;
             const double ms = msW[r * MSS + gl];
-            const unsigned long long gc = (unsigned long long)(a.d.cell_offset + wc0 + r);
-            const Philox4 px = philox4x32_10_keys((uint32_t)(chunk * SG + gl), (uint32_t)gc, a.sweep, (uint32_t)(gc >> 32) << 8, a.rk);
+            const Philox4 px = philox4x32_10_keys((uint32_t)(chunk * SG + gl), (uint32_t)cinf.z, a.sweep, (uint32_t)cinf.w, a.rk);
             const double ub = u52(px.x2, px.x3);
             const float rf = (float)((a.cutoff - ms) * b.isd[gl * M0 + im]);
             const float ax = fabsf(rf) * 0.70710678f;
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
                 const int code = valid ? dcode[255 - e] : 0;
                 const double v = valid ? dub[255 - e] : 1.0;
                 const int r = code >> 5, gl = code & 31;
-                const int im = cellinfo[r * 2];
+                const int im = cellinfo[r * 4];
                 const bool isT = v < 0.0;
                 double arg = v;                      // tail-quantile dropout: stays a tail entry as it is
                 bool toC = false, toTail = valid;
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             const int code = dcode[e];
             const double v = dub[e];
             const int r = code >> 5, gl = code & 31;
-            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_central(fabs(v)), msW[r * MSS + gl]), v < 0.0);
+            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 4]], qnorm_central(fabs(v)), msW[r * MSS + gl]), v < 0.0);
         }
         // ---- 3c'. tail quantiles ----
 #pragma unroll 1
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
             const int code = dcode[255 - e];
             const double v = dub[255 - e];
             const int r = code >> 5, gl = code & 31;
-            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 2]], qnorm_tail(fabs(v)), msW[r * MSS + gl]), v < 0.0);
+            finish(r, gl, fma(b.sds[gl * M0 + cellinfo[r * 4]], qnorm_tail(fabs(v)), msW[r * MSS + gl]), v < 0.0);
         }
         // ---- 3c''. dense block: the whole back list, arguments in place, either quantile region ----
         if (inplace) {
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
                 const int code = dcode[255 - e];
                 const double v = dub[255 - e];
                 const int r = code >> 5, gl = code & 31;
-                if (v != 0.0) finish(r, gl, quantile_draw(msW[r * MSS + gl], b.sds[gl * M0 + cellinfo[r * 2]], a.cutoff, v), v < 0.0);
+                if (v != 0.0) finish(r, gl, quantile_draw(msW[r * MSS + gl], b.sds[gl * M0 + cellinfo[r * 4]], a.cutoff, v), v < 0.0);
             }
         }
         // ---- 3d. inside the screening band: exact FP64 Bernoulli test and draw ----
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
         for (int e = lane; e < nU; e += 32) {
             const int code = xcode[e];
             const int r = code >> 5, gl = code & 31;
-            const int im = cellinfo[r * 2], ct = cellinfo[r * 2 + 1];
+            const int im = cellinfo[r * 4], ct = cellinfo[r * 4 + 1];
             double ua, ub;
             entry_uniforms(a.seed, a.sweep, (unsigned long long)(a.d.cell_offset + wc0 + r), (uint32_t)(chunk * SG + gl), ua, ub);
             finish(r, gl, sample_entry(msW[r * MSS + gl], b.sds[gl * M0 + im], b.isd[gl * M0 + im], b.pg[gl * MB + ct],
@@ -379,7 +383,7 @@ void launch_sweep(SweepArgs a, cudaStream_t st) {
     a.hi_trunc = std::min(a.cutoff, a.hi);
     auto smem_for = [&](int nst) {
         return sizeof(double) * (size_t(SW) * 8 * MSS + nst * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) + SW * 256 * sizeof(double) +
-               SW * 768 + SW * 16 * sizeof(int) + 64;
+               SW * 768 + SW * 32 * sizeof(int) + 64;
     };
     auto resident_for = [](size_t smem) { return smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1); };
     a.nst = resident_for(smem_for(NST)) == resident_for(smem_for(2)) ? NST : 2;

@@ -74,8 +74,9 @@ __device__ __forceinline__ double fast_rcp(double y) {
 
 // exp(h) for h <= 0: 2^k * e^r with the exponent patched in directly; below -700 (denormal / underflow
 // territory, only reached from the cold |x| > 8 pnorm path) it defers to the library exp.
+template <bool CHECK = true>
 __device__ __forceinline__ double exp_neg(double h) {
-    if (h < -700.0) return exp(h);
+    if (CHECK && h < -700.0) return exp(h);
     const double MAGIC = 6755399441055744.0;                    // 1.5 * 2^52: round-to-nearest-integer trick
     const double t = fma(h, 1.4426950408889634074, MAGIC);
     const double kd = t - MAGIC;
@@ -89,11 +90,12 @@ __device__ __forceinline__ double exp_neg(double h) {
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
-// exp(-y^2/2) with the rounding error of y*y compensated
+// exp(-y^2/2) with the rounding error of y*y compensated; CHECK = false when the caller guarantees |y| < 37
+template <bool CHECK = true>
 __device__ __forceinline__ double exp_mhalfsq(double y) {
     const double h = -0.5 * y * y;
     const double l = fma(-0.5 * y, y, -h);
-    const double e = exp_neg(h);
+    const double e = exp_neg<CHECK>(h);
     return fma(e, l, e);
 }
 
@@ -148,7 +150,7 @@ static __device__ __noinline__ double pnorm_full(double x) {
 __device__ __forceinline__ double pnorm(double x) {
     const double y = fabs(x);
     if (y <= 8.0) {
-        const double lo = exp_mhalfsq(y) * pn_mid_ratio(y);
+        const double lo = exp_mhalfsq<false>(y) * pn_mid_ratio(y);
         return x < 0.0 ? lo : 1.0 - lo;
     }
     return pnorm_full(x);
@@ -196,11 +198,39 @@ __device__ __forceinline__ double fast_sqrt(double x) {
     return fma(fma(-g, g, x), h, g);
 }
 
-// Phi^-1(p) for |p - 0.5| > 0.425 (AS241 tails)
+// log(1+f)/s - 2 coefficients of the fdlibm e_log.c kernel (s = f/(2+f); remainder < 2^-58.45)
+static __constant__ double kLG[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                     2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                     1.479819860511658591e-01};
+
+// log(x) for positive NORMAL x (no zero / denormal / inf / nan handling): the fdlibm algorithm -- x = 2^k m with
+// m in [sqrt(1/2), sqrt(2)), log m = f - (f^2/2 - s (f^2/2 + R(s^2))) -- with the division by the Newton reciprocal.
+// ~35 instructions against ~70 of the library routine (whose special cases and double-double tail are not needed here);
+// relative error < 2e-16 (checked against numpy in tests/test_oracle.py::test_device_math_restatement).
+__device__ __forceinline__ double log_normal(double x) {
+    int hi = __double2hiint(x);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000;                    // mantissa above sqrt(2): halve it, k + 1
+    const double m = __hiloint2double(hi | (i ^ 0x3ff00000), __double2loint(x));
+    k += i >> 20;
+    const double f = m - 1.0;
+    const double s = f * fast_rcp(2.0 + f);
+    const double z = s * s;
+    const double R = z * horner8<7>(kLG, z);
+    const double hfsq = 0.5 * f * f;
+    const double dk = static_cast<double>(k);
+    return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+}
+
+// sqrt of a responsibility z in [0, 1]: the Newton form above 1e-30, the library routine below (zero, denormals)
+__device__ __forceinline__ double sqrt_unit(double z) { return z > 1e-30 ? fast_sqrt(z) : sqrt(z); }
+
+// Phi^-1(p) for |p - 0.5| > 0.425 (AS241 tails); min(p, 1 - p) must be a normal number (>= 2.3e-308)
 __device__ __forceinline__ double qnorm_tail(double p) {
     const double q = p - 0.5;
     const double pp = q < 0.0 ? p : 1.0 - p;
-    double r = fast_sqrt(-log(pp));
+    double r = fast_sqrt(-log_normal(pp));
     double v;
     if (r <= 5.0) {
         r -= 1.6;
@@ -219,7 +249,7 @@ __device__ __forceinline__ double qnorm(double p) {
         return q * horner8<8>(kQA, r) * fast_rcp(horner8<8>(kQB, r));
     }
     const double pp = q < 0.0 ? p : 1.0 - p;
-    double r = sqrt(-log(pp));
+    double r = fast_sqrt(-log_normal(pp));            // min(p, 1 - p) is a normal number at every call site
     double v;
     if (r <= 5.0) {
         r -= 1.6;

@@ -7,7 +7,7 @@
 //   Q      [NS][ldG][QS]   projection operand  [B/sigma_s | mu_m/sigma_cs(m) | 0-pad]
 //   isg    [NS][ldG]       1/sigma_s
 //   Qs     [ldG][FS]       sweep operand       [B*sd | 0-pad]
-//   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  musdA = mu*sd,  gmig [ldG][2] = {gene mean, 1/sd}
+//   sdsA   [ldG][M0]       sqrt(sigma)*sd,  isdA = 1/sdsA,  musdA = mu*sd + mean,  gmig [ldG][2] = {gene mean, 1/sd}
 //   P      [NS][n][NQP]    Y^T Q          S2 [NS][n]   sum_g Y^2/sigma_s
 //   V      [n][VS]         M-step operand [Wbar (K0) | z (M0) | sum_m sqrt z_m (1) | 0-pad],  zsum [n]
 //   Fh     [n][FS]         sweep operand  [f_i (K0) | 0-pad]   (the membership m_i is in im[n])

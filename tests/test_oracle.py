@@ -212,7 +212,7 @@ def test_device_math_restatement():
     """NumPy restatement of csrc/math64.cuh (Cody pnorm mid formula, AS241 qnorm, Taylor exp) with the
     device's own coefficient tables vs scipy.special -- the functions the oracle uses."""
     T = _device_tables()
-    assert set(T) >= {"kQA", "kQB", "kQC", "kQD", "kQE", "kQF", "kPC", "kPD", "kEX"}
+    assert set(T) >= {"kQA", "kQB", "kQC", "kQD", "kQE", "kQF", "kPC", "kPD", "kEX", "kLG"}
 
     def horner(c, x):
         r = np.full_like(x, c[-1])
@@ -233,15 +233,30 @@ def test_device_math_restatement():
     z[~cen] = np.where(q[~cen] < 0, -v, v)
     zr = special.ndtri(p)
     assert np.max(np.abs(z - zr) / np.maximum(np.abs(zr), 1e-300)) < 5e-15
-    # pnorm: the single mid-range formula the hot path uses on |x| <= 8
+    # log_normal (fdlibm kernel, used by qnorm_tail): positive normal arguments down to the smallest tail argument
+    xl = np.concatenate([10.0 ** -np.linspace(0, 300, 30001), np.linspace(1e-3, 2.0, 20001)])
+    mant, ex = np.frexp(xl)                           # xl = mant 2^ex, mant in [0.5, 1)
+    big = mant * 2 > math.sqrt(2.0)                   # device: m in [sqrt(1/2), sqrt(2))
+    m = np.where(big, mant, mant * 2)
+    k = np.where(big, ex, ex - 1).astype(float)
+    f = m - 1.0
+    sl = f / (2.0 + f)
+    zl = sl * sl
+    R = zl * horner(T["kLG"], zl)
+    hfsq = 0.5 * f * f
+    lg = k * 6.93147180369123816490e-01 - ((hfsq - (sl * (hfsq + R) + k * 1.90821492927058770002e-10)) - f)
+    nz = np.abs(np.log(xl)) > 1e-3
+    assert np.max(np.abs(lg - np.log(xl))[nz] / np.abs(np.log(xl))[nz]) < 3e-16 and np.max(np.abs(lg - np.log(xl))) < 2e-13
+    # pnorm: the single mid-range formula the hot path uses on |x| <= 8 (Horner form of Cody's two polynomials)
     c, d = T["kPC"], T["kPD"]
     y = np.linspace(0, 8, 80001)
-    xn = c[8] * y
-    xd = y.copy()
-    for i in range(7):
-        xn = (xn + c[i]) * y
-        xd = (xd + d[i]) * y
-    ratio = (xn + c[7]) / (xd + d[7])                 # device: Phi(-y) = exp_mhalfsq(y) * ratio (compensated exp)
+    xn = np.full_like(y, c[8])
+    xd = y + d[0]
+    xn = xn * y + c[0]
+    for i in range(1, 8):
+        xn = xn * y + c[i]
+        xd = xd * y + d[i]
+    ratio = xn / xd                                   # device: Phi(-y) = exp_mhalfsq(y) * ratio (compensated exp)
     ref = 0.5 * special.erfcx(y / math.sqrt(2.0))      # == Phi(-y) exp(y^2/2)
     err = np.abs(ratio - ref) / ref
     assert err[(y >= 0.67) & (y <= 5.65)].max() < 2e-15 and err[y > 5.65].max() < 3e-13 and err.max() < 6e-12   # as documented in math64.cuh
