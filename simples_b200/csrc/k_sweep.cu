@@ -21,8 +21,7 @@
 namespace sb {
 namespace {
 
-constexpr int SW = 8;          // warps per CTA
-constexpr int SC = SW * 8;     // cells per CTA
+constexpr int SW = 8;          // default warps per CTA (template parameter SWT of the kernel)
 constexpr int SG = 32;         // genes per chunk (= one mask word)
 constexpr int MSS = 34;        // row stride of the per-warp ms tile (doubles)
 constexpr int NST = 3;         // stages of the parameter ring (2 when a third one would cost a resident CTA)
@@ -62,15 +61,36 @@ __device__ __forceinline__ void load_chunk_bulk(const SweepArgs& a, const ChunkB
     bulk_g2s(b.gi, a.gmig + size_t(g0) * 2, SG * 16, bar);
 }
 
+// mbarrier wait that sleeps between polls: a blocked warp must not spend issue slots the working warps need
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
+
 __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* p, unsigned v) {
     unsigned old;
     asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
     return old;
 }
 
-// NKS = number of K-steps of 4 held as register A-fragments (K0 <= 4 NKS); MINB = resident CTAs per SM aimed at
-template <int NKS, int MINB>
-__global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__ SweepArgs a) {
+// NKS = number of K-steps of 4 held as register A-fragments (K0 <= 4 NKS); MINB = resident CTAs per SM aimed at;
+// SWT = warps per CTA (8 cells each)
+template <int NKS, int MINB, int SWT>
+__global__ void __launch_bounds__(SWT * 32, MINB) k_sweep(const __grid_constant__ SweepArgs a) {
+    constexpr int SW = SWT, SC = SWT * 8;
     extern __shared__ __align__(16) double sm[];
     const int FS = a.d.FS, M0 = a.d.M0, MB = a.d.MB, ldG = a.d.ldG, n = a.d.n;
     const int KST = a.d.NFP / 4, nst = a.nst;
@@ -85,15 +105,13 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
     double* sBuf = reinterpret_cast<double*>(smb + 64 + SW * WBLK);               // [NST][CD] parameter chunks
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int cell0 = blockIdx.x * SC;
-    const int wc0 = cell0 + warp * 8;           // first cell of this warp
-    double fr[NKS];                             // A-fragments f[cell g][4 ks + t] of the warp's 8 cells
-    {
-        const int cell = wc0 + g;
-#pragma unroll
-        for (int ks = 0; ks < NKS; ++ks) fr[ks] = (ks < KST && cell < n) ? a.Fh[size_t(cell) * FS + ks * 4 + t] : 0.0;
-    }
+    // The 8-cell groups of the CTA ROTATE over the warps: in chunk ci warp w owns group (w + ci) mod SW.  The number of zero
+    // entries is a property of the cell (capture efficiency), so with a fixed assignment the warp holding the sparsest
+    // cells ran ahead until the ring stopped it and then spun on the barrier of every chunk (36 % of the waits blocked,
+    // 6.8 % of all executed instructions: profiles/r02_notes.md section 8); rotating evens the work out within 8 chunks.
+    // Cost: the A-fragments (3 doubles per lane, L1-resident) are re-read per chunk.
     if (lane < 8) {
-        const int cell = wc0 + lane;
+        const int cell = cell0 + warp * 8 + lane;
         // per cell: cluster, cell type and the cell's two Philox counter words (global cell index: low word, high word << 8)
         const unsigned long long gc = (unsigned long long)(a.d.cell_offset + cell);
         reinterpret_cast<int4*>(wblk + 8 * MSS * 8 + 256 * 8 + 768)[lane] =
@@ -122,19 +140,30 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
     unsigned char* list = reinterpret_cast<unsigned char*>(dub + 256); // [256] all zero entries
     unsigned char* dcode = list + 256;                                 // [256] Dc (front) / back list codes
     unsigned char* xcode = list + 512;                                 // [256] uncertain entries
-    int* cellinfo = reinterpret_cast<int*>(list + 768);                // [8][4] (im, celltype, counter words)
     const unsigned lt = (1u << lane) - 1u;
 
-    // mask words of the warp's 8 cells (chunk-major mask => 32 contiguous bytes), fetched one chunk ahead
-    const bool mlane = lane < 8 && wc0 + lane < n;
-    unsigned wnext = (mlane && nchunks > 0) ? a.mask[size_t(cbeg) * a.n_alloc + wc0 + lane] : 0u;
+    // mask words of the group's 8 cells (chunk-major mask => 32 contiguous bytes), fetched one chunk ahead
+    auto mask_word = [&](int chunk, int grp) {
+        const int cell = cell0 + grp * 8 + lane;
+        return (lane < 8 && cell < n) ? a.mask[size_t(chunk) * a.n_alloc + cell] : 0u;
+    };
+    unsigned wnext = nchunks > 0 ? mask_word(cbeg, warp) : 0u;
     int st = 0;                 // ring stage of the current chunk
     unsigned use = 0;           // how often the ring has wrapped (= ci / nst)
-    for (int ci = 0; ci < nchunks; ++ci) {
+    int grp = warp;             // this chunk's cell group
+    for (int ci = 0; ci < nchunks; ++ci, grp = (grp + 1 == SW ? 0 : grp + 1)) {
         const int chunk = cbeg + ci;                   // absolute gene-chunk index
+        const int wc0 = cell0 + grp * 8;               // its first cell
+        const int* cellinfo = reinterpret_cast<const int*>(smb + 64 + grp * WBLK + 8 * MSS * 8 + 256 * 8 + 768);   // [8][4]
         const unsigned word = wnext;
-        wnext = (mlane && ci + 1 < nchunks) ? a.mask[size_t(chunk + 1) * a.n_alloc + wc0 + lane] : 0u;
-        mbar_wait(&full[st], use & 1u);                // this chunk's parameters have landed
+        wnext = ci + 1 < nchunks ? mask_word(chunk + 1, grp + 1 == SW ? 0 : grp + 1) : 0u;
+        double fr[NKS];                                // A-fragments f[cell g][4 ks + t] of the group's 8 cells
+        {
+            const int cell = wc0 + g;
+#pragma unroll
+            for (int ks = 0; ks < NKS; ++ks) fr[ks] = (ks < KST && cell < n) ? __ldg(a.Fh + size_t(cell) * FS + ks * 4 + t) : 0.0;
+        }
+        mbar_wait_backoff(&full[st], use & 1u);        // this chunk's parameters have landed
         const ChunkBuf b = chunk_buf(sBuf + st * CD, FS, M0, MB);
 
         const size_t blk0 = size_t(wc0) * ldG + chunk * SG;
@@ -370,10 +399,10 @@ __global__ void __launch_bounds__(SW * 32, MINB) k_sweep(const __grid_constant__
 
 }  // namespace
 
-template <int NKS, int MINB>
-static void launch_variant(const SweepArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-    ensure_dyn_smem_k(k_sweep<NKS, MINB>, smem);
-    k_sweep<NKS, MINB><<<grid, SW * 32, smem, st>>>(a);
+template <int NKS, int MINB, int SWT>
+static void launch_variant(const SweepArgs& a, int tiles, int gsplit, size_t smem, cudaStream_t st) {
+    ensure_dyn_smem_k(k_sweep<NKS, MINB, SWT>, smem);
+    k_sweep<NKS, MINB, SWT><<<dim3(tiles, gsplit), SWT * 32, smem, st>>>(a);
 }
 
 void launch_sweep(SweepArgs a, cudaStream_t st) {
@@ -381,32 +410,32 @@ void launch_sweep(SweepArgs a, cudaStream_t st) {
     a.hi = a.clip ? a.upper : HUGE_VAL;
     a.lo = a.clip ? a.lower : -HUGE_VAL;
     a.hi_trunc = std::min(a.cutoff, a.hi);
+    const int kst = a.d.NFP / 4;
+    // warps per CTA: 8 (3 CTAs of <= 80 registers per SM).  The 64-register builds with 10 x 3 and 16 x 2 resident warps
+    // were measured at C3 (profiles/r02_notes.md section 8): 1.70 ms and 1.57 ms against 1.57 ms -- the kernel is bound by
+    // dispatch (FP64 instructions take two slots), not by latency, so more resident warps buy nothing.
+    const int sw = SW;
     auto smem_for = [&](int nst) {
-        return sizeof(double) * (size_t(SW) * 8 * MSS + nst * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) + SW * 256 * sizeof(double) +
-               SW * 768 + SW * 32 * sizeof(int) + 64;
+        return sizeof(double) * (size_t(sw) * 8 * MSS + nst * chunk_doubles(a.d.FS, a.d.M0, a.d.MB)) + sw * 256 * sizeof(double) +
+               sw * 768 + sw * 32 * sizeof(int) + 64;
     };
-    auto resident_for = [](size_t smem) { return smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1); };
-    a.nst = resident_for(smem_for(NST)) == resident_for(smem_for(2)) ? NST : 2;
+    auto resident_for = [](size_t smem) { return int(std::min<size_t>(8, (227 * 1024) / (smem + 1024))); };
+    a.nst = resident_for(smem_for(NST)) >= 3 || resident_for(smem_for(NST)) == resident_for(smem_for(2)) ? NST : 2;
     const size_t smem = smem_for(a.nst);
-    const int tiles = (a.d.n + SC - 1) / SC;
     const int resident = resident_for(smem);
+    const int tiles = (a.d.n + sw * 8 - 1) / (sw * 8);
     // gridDim.y splits the gene range: more, smaller CTAs even out the tail of the last wave.  Measured on B200 at
     // 12.5k-100k cells x 2000 genes (profiles/r02_notes.md): 5-8 parts are within 1 % of each other and up to 15 % faster
     // than the wave-count model of round 1 at the small shards of a strongly scaled run; keep >= 8 chunks per CTA.
     int gsplit = std::min(6, std::max(1, (a.d.ldG / SG) / 8));
-    {
-        (void)resident;
-        if (const char* e = getenv("SIMPLES_SWEEP_GSPLIT")) {       // tuning override
-            const int v = atoi(e);
-            if (v >= 1 && (a.d.ldG / SG) / v >= 1) gsplit = v;
-        }
+    if (const char* e = getenv("SIMPLES_SWEEP_GSPLIT")) {       // tuning override
+        const int v = atoi(e);
+        if (v >= 1 && (a.d.ldG / SG) / v >= 1) gsplit = v;
     }
-    const dim3 grid(tiles, gsplit);
-    const int kst = a.d.NFP / 4;
-    if (kst <= 3) launch_variant<3, 3>(a, grid, smem, st);
-    else if (kst <= 6 && resident == 3) launch_variant<6, 3>(a, grid, smem, st);
-    else if (kst <= 6) launch_variant<6, 2>(a, grid, smem, st);
-    else launch_variant<8, 2>(a, grid, smem, st);
+    if (kst <= 3) launch_variant<3, 3, SW>(a, tiles, gsplit, smem, st);
+    else if (kst <= 6 && resident >= 3) launch_variant<6, 3, SW>(a, tiles, gsplit, smem, st);
+    else if (kst <= 6) launch_variant<6, 2, SW>(a, tiles, gsplit, smem, st);
+    else launch_variant<8, 2, SW>(a, tiles, gsplit, smem, st);
 }
 
 }  // namespace sb
