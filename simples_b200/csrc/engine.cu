@@ -472,6 +472,8 @@ int run_sweep(simples_ctx* c, bool clip, double* rec1, double* rec2) {
     sa.sweep = c->sweep;
     sa.rec1 = rec1;
     sa.rec2 = rec2;
+    sa.mi_gbase = c->mi_gbase;
+    sa.mi_off = c->mi_off;
     sa.expect = c->kind == 0 && (c->compat & SIMPLES_MODE_EXPECT) != 0;
     launch_sweep(sa, c->stream);
     CK(cudaGetLastError());
@@ -1137,8 +1139,12 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
         CK(cudaStreamSynchronize(c->stream));
     }
     launch_center(s.Y, s.gmean, s.gsd, n, ldG, 0, 1, c->stream);   // Y <- (Y - pos_mean) / pos_sd  (:50)
-    CKR(c->dalloc(&c->rec1, na * ldG));
-    CKR(c->dalloc(&c->rec2, na * ldG));
+    // accumulators of the recorded sweeps: one slot per zero entry, in the order of the sweep's own work lists
+    CKR(c->dalloc(&c->mi_gbase, na / 8));
+    CKR(c->dalloc(&c->mi_off, (na / 8) * size_t(ldG / 32)));
+    launch_mi_index(s.mask, int(na), c->n_alloc, ldG / 32, c->mi_gbase, c->mi_off, c->stream);
+    CKR(c->dalloc(&c->rec1, 2 * (size_t(c->nnz0) + 8)));     // interleaved {sum v, sum v^2}
+    c->rec2 = c->rec1;
     CKR(c->dalloc(&c->rEF, size_t(n) * K0));
     CKR(c->dalloc(&c->rF2, size_t(n) * K0));
     CKR(c->dalloc(&c->rVF, size_t(n) * K0));
@@ -1164,7 +1170,7 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
     if (trace_mi) cudaStreamSynchronize(c->stream);
     const auto tm0 = clk_mi::now();
     CKR(run_prep(c));   // parameters are fixed: cluster constants computed once, not per sweep
-    const bool fused = use_fused_mc(c);   // each sweep then also projects the updated Y for the next sweep's E-pass
+    const bool fused = false;   // the fused MC pass has no compact-accumulator variant (and is slower: profiles/r02_notes.md 2.1)
     for (int it = 1; it <= nit; ++it) {                                       // :67
         const bool rec = it > a->burnin;
         c->sweep = unsigned(it - 1);
@@ -1202,13 +1208,13 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
     }
     if (o->impt)
         CKR(fetch_big(c, o->impt, [&](double* dst, size_t c0, size_t nc) {
-            launch_mi_finalize(s.Y + c0 * ldG, s.mask, c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean, s.gsd, dst, nullptr,
-                               int(nc), int(c0), c->n_alloc, G, ldG, a->mcmc, c->stream);
+            launch_mi_finalize(s.Y + c0 * ldG, s.mask, c->rec1, c->rec2, s.gmean, s.gsd, dst, nullptr, int(nc), int(c0),
+                               c->n_alloc, G, ldG, a->mcmc, c->mi_gbase, c->mi_off, c->stream);
         }));
     if (o->impt_var)
         CKR(fetch_big(c, o->impt_var, [&](double* dst, size_t c0, size_t nc) {
-            launch_mi_finalize(s.Y + c0 * ldG, s.mask, c->rec1 + c0 * ldG, c->rec2 + c0 * ldG, s.gmean, s.gsd, nullptr, dst,
-                               int(nc), int(c0), c->n_alloc, G, ldG, a->mcmc, c->stream);
+            launch_mi_finalize(s.Y + c0 * ldG, s.mask, c->rec1, c->rec2, s.gmean, s.gsd, nullptr, dst, int(nc), int(c0),
+                               c->n_alloc, G, ldG, a->mcmc, c->mi_gbase, c->mi_off, c->stream);
         }));
     if (o->EF || o->varF) {
         std::vector<double> ef(size_t(n) * K0), f2(size_t(n) * K0), vf(size_t(n) * K0);

@@ -105,6 +105,8 @@ struct simples_ctx {
     int nsplit_g = 0;
     // MI
     int mcmc = 0, burnin = 0, want_consensus = 0;
+    unsigned long long* mi_gbase = nullptr;   // slot table of the compact accumulators rec1 / rec2 (state.h, SweepArgs)
+    uint32_t* mi_off = nullptr;
     double *rec1 = nullptr, *rec2 = nullptr, *rEF = nullptr, *rF2 = nullptr, *rVF = nullptr, *cons = nullptr, *tot_mi = nullptr;
     // timing
     std::vector<cudaEvent_t> iter_ev;

@@ -97,19 +97,67 @@ __global__ void k_uncenter(const double* Y, double* out, const double* gmean, co
     }
 }
 
+// Slot table of the compact MI accumulators.  One thread per 8-cell group: off[g][w] = zero entries of the group in the
+// chunks before w, tot[g] = zero entries of the group.
+__global__ void k_mi_group_counts(const uint32_t* mask, int n_alloc, int nwords, int ngroups, uint32_t* off, unsigned long long* tot) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    uint32_t run = 0;
+    for (int w = 0; w < nwords; ++w) {
+        off[size_t(g) * nwords + w] = run;
+        const uint4* p = reinterpret_cast<const uint4*>(mask + size_t(w) * n_alloc + size_t(g) * 8);
+        const uint4 a = p[0], b = p[1];
+        run += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+    }
+    tot[g] = run;
+}
+// exclusive scan of tot[0..ngroups) in place (one CTA: contiguous segment per thread, then a scan of the segment sums)
+__global__ void __launch_bounds__(1024) k_mi_scan(unsigned long long* tot, int ngroups) {
+    __shared__ unsigned long long seg[1024];
+    const int per = (ngroups + 1023) / 1024, b = threadIdx.x * per, e = min(ngroups, b + per);
+    unsigned long long s = 0;
+    for (int i = b; i < e; ++i) s += tot[i];
+    seg[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const unsigned long long v = seg[i];
+            seg[i] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    unsigned long long run = seg[threadIdx.x];
+    for (int i = b; i < e; ++i) {
+        const unsigned long long v = tot[i];
+        tot[i] = run;
+        run += v;
+    }
+}
+
 __global__ void k_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2,
                               const double* gmean, const double* gsd, double* impt, double* impt_var, int n, int cell0,
-                              int n_alloc, int G, int ldG, int mcmc) {
+                              int n_alloc, int G, int ldG, int mcmc, const unsigned long long* gbase, const uint32_t* off) {
     const size_t total = size_t(n) * G;
+    const int nwords = ldG / 32;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const size_t c = i / G;
         const int g = int(i - c * G);
         const size_t o = c * ldG + g;
-        const bool zero = (mask[size_t(g >> 5) * n_alloc + cell0 + c] >> (g & 31)) & 1u;
+        const size_t cell = size_t(cell0) + c;
+        const int w = g >> 5, bit = g & 31;
+        const uint32_t* mw = mask + size_t(w) * n_alloc;
+        const uint32_t word = mw[cell];
         double m1, v;
-        if (zero) {
-            m1 = rec1[o] / mcmc;
-            v = rec2[o] / mcmc - m1 * m1;
+        if ((word >> bit) & 1u) {
+            // slot = group base + block offset + entries of the block's earlier rows + earlier genes of this row
+            const size_t grp = cell >> 3;
+            size_t slot = gbase[grp] + off[grp * nwords + w] + __popc(word & ((1u << bit) - 1u));
+            for (size_t r = grp << 3; r < cell; ++r) slot += __popc(mw[r]);
+            const double2 q = reinterpret_cast<const double2*>(rec1)[slot];      // {sum v, sum v^2} (rec2 unused)
+            m1 = q.x / mcmc;
+            v = q.y / mcmc - m1 * m1;
         } else {
             m1 = Y[o];     // constant over sweeps: mean = Y, variance = 0
             v = 0.0;
@@ -293,9 +341,15 @@ void launch_uncenter(const double* Y, double* out, const double* gmean, const do
 }
 void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2, const double* gmean,
                         const double* gsd, double* impt, double* impt_var, int n, int cell0, int n_alloc, int G, int ldG,
-                        int mcmc, cudaStream_t st) {
+                        int mcmc, const unsigned long long* gbase, const uint32_t* off, cudaStream_t st) {
     k_mi_finalize<<<gs_grid(size_t(n) * G), 256, 0, st>>>(Y, mask, rec1, rec2, gmean, gsd, impt, impt_var, n, cell0, n_alloc, G,
-                                                          ldG, mcmc);
+                                                          ldG, mcmc, gbase, off);
+}
+void launch_mi_index(const uint32_t* mask, int n, int n_alloc, int nwords, unsigned long long* gbase, uint32_t* off,
+                     cudaStream_t st) {
+    const int ngroups = (n + 7) / 8;
+    k_mi_group_counts<<<(ngroups + 127) / 128, 128, 0, st>>>(mask, n_alloc, nwords, ngroups, off, gbase);
+    k_mi_scan<<<1, 1024, 0, st>>>(gbase, ngroups);
 }
 void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
                               double* rVF, cudaStream_t st) {

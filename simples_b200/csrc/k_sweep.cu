@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(SWT * 32, MINB) k_sweep(const __grid_constant_
 
         const size_t blk0 = size_t(wc0) * ldG + chunk * SG;
         double* const yblk = a.Y + blk0;
+        const size_t rec0 = a.rec1 ? size_t(a.mi_gbase[wc0 >> 3]) + a.mi_off[size_t(wc0 >> 3) * (ldG / SG) + chunk] : 0;
         auto finish = [&](int r, int gl, double x, bool trunc) {
             // clamp to the cutoff (truncated draws, R/EM_impute.R:191-192) and to [lower, upper] (:196-197) -- the three
             // bounds are folded into two on the host (+-inf when the sweep does not clip); plain compare-and-select, the
@@ -179,10 +180,14 @@ __global__ void __launch_bounds__(SWT * 32, MINB) k_sweep(const __grid_constant_
             const double v = (x - gi.x) * gi.y;
             const int o = r * ldG + gl;                 // offset inside the warp's 8 x 32 block (32-bit arithmetic)
             yblk[o] = v;
-            if (a.rec1) {
-                const size_t ro = blk0 + o;
-                a.rec1[ro] += v;
-                a.rec2[ro] += v * v;
+            if (a.rec1) {      // do_impute: slot = block base + position of the entry in the block's list (row-major)
+                const unsigned* wl = reinterpret_cast<const unsigned*>(list);
+                const size_t slot = rec0 + wl[8 + r] + __popc(wl[r] & ((1u << gl) - 1u));
+                double2* rp = reinterpret_cast<double2*>(a.rec1) + slot;      // {sum v, sum v^2}
+                double2 q = *rp;
+                q.x += v;
+                q.y = fma(v, v, q.y);
+                *rp = q;
             }
         };
 
@@ -288,6 +293,19 @@ __global__ void __launch_bounds__(SWT * 32, MINB) k_sweep(const __grid_constant_
             nS += __popc(bS);
         }
         __syncwarp();
+        if (a.rec1) {        // the list is consumed: keep the 8 mask words and their exclusive prefix counts in its place
+            unsigned pre = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const unsigned w = __shfl_sync(0xffffffffu, word, r);
+                if (lane == r) {
+                    reinterpret_cast<unsigned*>(list)[r] = w;
+                    reinterpret_cast<unsigned*>(list)[8 + r] = pre;
+                }
+                pre += __popc(w);
+            }
+            __syncwarp();
+        }
 
         // ---- 3b. T-stage: for the certain "expressed but <= cutoff" entries of the back list compute the quantile
         //      argument ub * Phi(r) (the only place the FP64 pnorm runs) and re-file them by quantile region:

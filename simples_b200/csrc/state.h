@@ -138,7 +138,12 @@ struct SweepArgs {
     int clip;
     unsigned long long seed; unsigned sweep;
     uint32_t rk[20];       // Philox round keys, filled by launch_sweep
-    double *rec1, *rec2;   // optional do_impute accumulators (same layout as Y), nullptr otherwise
+    // optional do_impute accumulators (nullptr otherwise), COMPACT: one slot per zero entry, ordered by (8-cell group,
+    // 32-gene chunk, cell row, gene) = the order of the sweep's own work lists, so a warp's updates of a block fall into
+    // ~113 consecutive slots (the dense G x n layout of round 1 cost a scattered read-modify-write per entry)
+    double *rec1, *rec2;   // rec1: interleaved {sum v, sum v^2} per slot; rec2 is not used by k_sweep (non-null = record)
+    const unsigned long long* mi_gbase;   // [ngroups]          first slot of the 8-cell group
+    const uint32_t* mi_off;               // [ngroups][nwords]  first slot of the block inside its group
     int expect;            // SIMPLES_MODE_EXPECT: conditional expectation instead of a draw
 };
 void launch_sweep(SweepArgs a, cudaStream_t st);
@@ -277,7 +282,10 @@ void launch_div_cols(double* A, const double* d, size_t rows, int cols, cudaStre
 void launch_uncenter(const double* Y, double* out, const double* gmean, const double* gsd, int n, int G, int ldG, cudaStream_t st);
 void launch_mi_finalize(const double* Y, const uint32_t* mask, const double* rec1, const double* rec2, const double* gmean,
                         const double* gsd, double* impt, double* impt_var, int n, int cell0, int n_alloc, int G, int ldG, int mcmc,
-                        cudaStream_t st);
+                        const unsigned long long* gbase, const uint32_t* off, cudaStream_t st);
+// slot table of the compact do_impute accumulators (mask is fixed for the whole call): returns nothing, fills gbase / off
+void launch_mi_index(const uint32_t* mask, int n, int n_alloc, int nwords, unsigned long long* gbase, uint32_t* off,
+                     cudaStream_t st);
 void launch_mi_record_factors(const Dims& d, const double* W, const double* z, const double* Mm, double* rEF, double* rF2,
                               double* rVF, cudaStream_t st);
 void launch_consensus(const double* z, double* cons, int n, int M0, cudaStream_t st);
