@@ -1170,11 +1170,11 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
     if (trace_mi) cudaStreamSynchronize(c->stream);
     const auto tm0 = clk_mi::now();
     CKR(run_prep(c));   // parameters are fixed: cluster constants computed once, not per sweep
-    const bool fused = false;   // the fused MC pass has no compact-accumulator variant (and is slower: profiles/r02_notes.md 2.1)
+    // (the opt-in fused MC pass is an EM-only path: it has no compact-accumulator variant and is slower, profiles/r02_notes.md 2.1)
     for (int it = 1; it <= nit; ++it) {                                       // :67
         const bool rec = it > a->burnin;
         c->sweep = unsigned(it - 1);
-        CKR(e_pass(c, true, false, true, true, rec, false, pi_const, fused && it > 1));   // :69-104, :107, :112
+        CKR(e_pass(c, true, false, true, true, rec, false, pi_const, false));   // :69-104, :107, :112
         launch_finalize_cell(s.part_cell, s.ncta_cell, M0, c->tot_mi + size_t(it - 1) * (2 * M0 + 1), c->stream);   // :89
         if (rec && c->cons) {                                                   // :96
             if (zall) {
@@ -1186,8 +1186,7 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
                 launch_consensus(s.z, c->cons, n, M0, c->stream);
             }
         }
-        if (fused) CKR(run_mcpass(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));
-        else CKR(run_sweep(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));   // :109-136, :140-141
+        CKR(run_sweep(c, false, rec ? c->rec1 : nullptr, rec ? c->rec2 : nullptr));   // :109-136, :140-141
         if (rec) launch_mi_record_factors(d, s.W, s.z, s.cc.Mm, c->rEF, c->rF2, c->rVF, c->stream);   // :143-147
     }
     CK(cudaGetLastError());

@@ -26,12 +26,6 @@ constexpr int SG = 32;         // genes per chunk (= one mask word)
 constexpr int MSS = 34;        // row stride of the per-warp ms tile (doubles)
 constexpr int NST = 3;         // stages of the parameter ring (2 when a third one would cost a resident CTA)
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 struct ChunkBuf {
     double *Q, *sds, *isd, *musd, *pg;
     double2* gi;       // {gene mean, 1 / gene sd}
