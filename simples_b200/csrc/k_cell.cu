@@ -379,7 +379,9 @@ __global__ void __launch_bounds__(CW * 32, (KS <= 4 ? 4 : 2)) k_cell_fast(CellAr
     const int ngroups = (n + 7) / 8;
     const int VGS = K0 * M0 + 2 * M0;
     const double* off1 = a.stale_q ? sOffq : sOff;                           // pass-1 offsets (Q1: stale beta2 in MC passes)
-    const double* MpL = a.cc.MmP + t * KPS + g;                              // this lane's B-fragment corner of M_0
+    // this lane's B-fragment corner of M_0.  The padded M_m tables (19 KB at K0 = M0 = 10) stay in global memory, read with
+    // an L1 evict-last policy; a shared-memory copy per CTA was measured equal (0.0999 vs 0.0997 ms) and costs a resident CTA
+    const double* MpL = a.cc.MmP + t * KPS + g;
     const int lane_r0 = lane / NQP, lane_c0 = lane - lane_r0 * NQP;
     bool kv[NT][2];                                                          // column < K0 (global stores only)
 #pragma unroll
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(CW * 32, (KS <= 4 ? 4 : 2)) k_cell_fast(CellAr
         const bool rv = cell < n;
         // ---- stage the P rows of the 8 cells (contiguous in P; (row, column) of the padded tile advance without a division) ----
         for (int idx = lane, r = lane_r0, c = lane_c0; idx < 8 * NQP; idx += 32) {
-            Pa[r * PWS + c] = (cell0 + r < n) ? a.P[size_t(cell0) * NQP + idx] : 0.0;
+            Pa[r * PWS + c] = (cell0 + r < n) ? ldg_stream(a.P + size_t(cell0) * NQP + idx) : 0.0;
             c += 32;
             while (c >= NQP) {
                 c -= NQP;
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(CW * 32, (KS <= 4 ? 4 : 2)) k_cell_fast(CellAr
                 for (int nt = 0; nt < NT; ++nt) {
                     double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) dmma(c0, c1, av[ks], __ldg(Mp + 4 * ks * KPS + nt * 8));
+                    for (int ks = 0; ks < KS; ++ks) dmma(c0, c1, av[ks], ldg_keep(Mp + 4 * ks * KPS + nt * 8));
                     const double2 o2 = *reinterpret_cast<const double2*>(off + nt * 8 + 2 * t);
                     qd = fma(c0, px[nt][0] - o2.x, fma(c1, px[nt][1] - o2.y, qd));
                 }
@@ -525,18 +527,18 @@ __global__ void __launch_bounds__(CW * 32, (KS <= 4 ? 4 : 2)) k_cell_fast(CellAr
                 for (int nt = 0; nt < NT; ++nt) {
                     double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) dmma(c0, c1, av[ks], __ldg(Mp + 4 * ks * KPS + nt * 8));
+                    for (int ks = 0; ks < KS; ++ks) dmma(c0, c1, av[ks], ldg_keep(Mp + 4 * ks * KPS + nt * 8));
                     wb[nt][0] = fma(zm, c0, wb[nt][0]);
                     wb[nt][1] = fma(zm, c1, wb[nt][1]);
                     if (m == im_g) *reinterpret_cast<double2*>(wsw + g * KPS + nt * 8 + 2 * t) = make_double2(c0, c1);
                     if (rv) {
                         if (a.write_W) {
-                            if (kv[nt][0]) wr[nt * 8] = c0;
-                            if (kv[nt][1]) wr[nt * 8 + 1] = c1;
+                            if (kv[nt][0]) __stcs(wr + nt * 8, c0);
+                            if (kv[nt][1]) __stcs(wr + nt * 8 + 1, c1);
                         }
                         if (a.write_Vg) {
-                            if (kv[nt][0]) vg[nt * 8] = zm * c0;
-                            if (kv[nt][1]) vg[nt * 8 + 1] = zm * c1;
+                            if (kv[nt][0]) __stcs(vg + nt * 8, zm * c0);
+                            if (kv[nt][1]) __stcs(vg + nt * 8 + 1, zm * c1);
                         }
                     }
                 }

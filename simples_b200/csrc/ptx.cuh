@@ -91,6 +91,18 @@ __device__ __forceinline__ void bulk_wait() {
 // make generic-proxy smem writes visible to the async proxy (before a bulk store)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// read-only global loads with an L1 policy: keep (small tables every warp re-reads) / do not allocate (streamed once)
+__device__ __forceinline__ double ldg_keep(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
