@@ -13,5 +13,9 @@ packages (glmnet, Rsolnp, msm, mixtools).  The oracle therefore restates
 ``R/EM_impute.R`` and ``R/do_impute.R`` line by line and is pinned by
 self-consistency only (literal augmented-design M-step vs sufficient
 statistics, dense MVN density vs Woodbury, KKT residuals); see DESIGN.md.
+
+``simples_oracle.py`` is the NumPy restatement; ``simples_oracle_c.c`` + ``accel.py`` are the multi-threaded C (OpenMP) /
+BLAS build of its O(n G) loops -- the CPU baseline ``bench.py`` times -- held to the NumPy statements by
+``tests/test_oracle_c.py``.
 """
 from .simples_oracle import *  # noqa: F401,F403

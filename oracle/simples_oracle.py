@@ -727,7 +727,12 @@ def _mstep_literal(Yc, z, Wm, Ms, nz, beta, sigma, lam, mu, M0, K0, it, penl, ma
 
 def _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
                est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
-               seed, compat, literal, shards=None, trace=None, cell0=0, expect=False):
+               seed, compat, literal, shards=None, trace=None, cell0=0, expect=False, accel=None):
+    # accel: oracle.accel.Accel() swaps the O(n G) loops for their multi-threaded C / BLAS build (same arithmetic up to
+    # rounding; the CPU baseline of bench.py), None = the NumPy statements below
+    epass, factor_means, sample_sweep, local_stats = (
+        (globals()[k] for k in ("epass", "factor_means", "sample_sweep", "local_stats")) if accel is None else
+        (accel.epass, accel.factor_means, accel.sample_sweep, accel.local_stats))
     pi_const = PI_REF if compat & COMPAT_PI else math.pi
     z = None if z is None else np.array(z, dtype=np.float64)
     Yc, gene_mean, gene_sd, mu = _prologue(Y, z, mu, M0, lower, upper, compat)
@@ -803,12 +808,14 @@ def em_impute_ref(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=N
 def em_impute_fast(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu=None, celltype=None,
                    penl=1, est_z=2, max_lambda=True, est_lam=2, impt_it=5, sigma0=100, pi_alpha=1,
                    num_mc=3, lower=-np.inf, upper=np.inf, seed=0, compat=COMPAT_DEFAULT,
-                   shards=None, trace=None, cell0=0, mode="sample"):
+                   shards=None, trace=None, cell0=0, mode="sample", accel=None):
     """Same algorithm with the sufficient-statistic M-step; ``shards`` = list of
-    cell boundaries emulating the multi-GPU partition + all-reduce."""
+    cell boundaries emulating the multi-GPU partition + all-reduce; ``accel`` = ``oracle.accel.Accel()`` for the
+    multi-threaded C / BLAS build of the O(n G) loops."""
     return _em_impute(Y, Y0, pg, M0, K0, cutoff, iter, beta, sigma, lam, pi, z, mu, celltype, penl,
                       est_z, max_lambda, est_lam, impt_it, sigma0, pi_alpha, num_mc, lower, upper,
-                      seed, compat, literal=False, shards=shards, trace=trace, cell0=cell0, expect=(mode == "expect"))
+                      seed, compat, literal=False, shards=shards, trace=trace, cell0=cell0, expect=(mode == "expect"),
+                      accel=accel)
 
 
 # ----------------------------------------------------------------------------
