@@ -386,7 +386,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg[dom]["bytes"], "ms_per_launch": kern[dom]["ms_per_launch"],
                 "fp64_tflops": kern[dom]["fp64_tflops"], "fp64_peak_tflops": f64_peak, "fp64_peak_source": f64_src,
                 "issue_roofline": issue,
-                "note": "impute_sweep is bound by instruction issue of the per-entry sampler (Philox + FP64 pnorm/qnorm: 17 warp "
+                "note": "impute_sweep is bound by instruction issue of the per-entry sampler (Philox + FP64 pnorm/qnorm: 15 warp "
                         "instructions per zero entry, issue slots 73 % busy), not by HBM: see issue_roofline, DESIGN.md section 4 "
                         "and profiles/r02_notes.md; the GEMM kernels estep_project / mstep_stats run at 66-68 % of measured HBM "
                         "and 76-80 % of measured FP64 DGEMM (kernels[...])"}
