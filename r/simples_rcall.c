@@ -2,8 +2,8 @@
  * .Call shim between R and libsimples_b200.so (include/simples_b200.h).
  *
  * SHIPPED AS SOURCE: neither R nor its headers exist in the build image.  tests/test_r_shim.py compiles this file
- * unmodified against a stand-in for the R API (tests/helpers/rstub) and drives it on the GPU; R itself never ran it.  A maintainer of JunLiuLab/SIMPLEs adds it as src/simples_rcall.c,
- * links with -lsimples_b200, and replaces the bodies of R/EM_impute.R:75-339 and R/do_impute.R:29-160
+ * unmodified against a stand-in for the R API (tests/helpers/rstub) and drives it on the GPU; R itself never ran it.
+ * A maintainer of JunLiuLab/SIMPLEs adds it as src/simples_rcall.c, links with -lsimples_b200, and replaces the bodies of R/EM_impute.R:75-339 and R/do_impute.R:29-160
  * with r/EM_impute_b200.R.  Argument order is the reference's own (R/EM_impute.R:75-78,
  * R/do_impute.R:29-30); every matrix is passed as the REAL() pointer of an R double matrix
  * (column-major), which is exactly the layout the C ABI takes, so no copies are made on the way in.
