@@ -263,3 +263,32 @@ def test_dot_call_init_impute_matches_the_python_mirror(R):
     got_imp, got_pg = (ref["impute"], ref["pg"]) if isinstance(ref, dict) else (ref[0], ref[1])
     assert np.array_equal(out["impute"], np.asarray(got_imp)) and np.array_equal(out["pg"], np.asarray(got_pg))
     R.L.rstub_free_all()
+
+
+@pytest.mark.gpu
+def test_dot_call_lq_fit_and_init_cluster_match_the_python_mirror(R):
+    """The call sites inside SIMPLE() / SIMPLE_B() (r/SIMPLE_b200.R): clustering start and lq-gene step."""
+    import simples_b200 as sb
+    st = _em_case(seed=6)
+    M0, K0 = 2, 4
+    em = sb.EM_impute(st["Y"], st["Y0"], st["pg"], M0, K0, 0.1, 3, st["beta"], st["sigma"], st["lam"], st["pi"], st["z"],
+                      celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=3)
+    rng = np.random.default_rng(8)
+    Gq, n = 40, st["Y"].shape[1]
+    dat = np.maximum(rng.normal(0.3, 1.0, (Gq, n)), 0.0) * (rng.uniform(size=(Gq, n)) < 0.4)       # lq genes: mostly zeros
+    sig = np.full((Gq, M0), 1.0)
+    pg = np.full((Gq, int(np.max(st["celltype"]))), 0.6)            # one column per cell type (R/SIMPLE.R:312-373)
+    for resp, mode in ((None, 0), (dat + 0.1, 1)):
+        out = R.py(R.call("C_simples_lq_fit", R.mat(dat), R.nil() if resp is None else R.mat(resp), R.mat(sig), R.mat(pg),
+                          R.mat(em["z"]), R.rlist([R.mat(e) for e in em["Ef"]]), R.rlist([R.mat(v) for v in em["Varf"]]),
+                          R.ivec(st["celltype"]), R.vec(1.0), R.vec(0.1), R.ivec(mode), R.vec(11.0)))
+        assert list(out) == ["mu", "beta", "sigma", "Y"]
+        ref = sb.lq_fit(dat, sig, pg, em["z"], em["Ef"], em["Varf"], celltype=st["celltype"], penl=1, cutoff=0.1, resp=resp,
+                        resid_mode=mode, seed=11)
+        for k in ("mu", "beta", "sigma", "Y"):
+            assert np.array_equal(out[k], np.asarray(ref[k]).reshape(out[k].shape)), (k, mode)
+    X = st["Y"]
+    cl = R.py(R.call("C_simples_init_cluster", R.mat(X), R.ivec(5), R.ivec(3), R.ivec(20), R.ivec(30), R.vec(2.0)))
+    assert cl.dtype == np.int32 and cl.shape == (n,) and set(cl) <= {1, 2, 3}
+    assert np.array_equal(cl, sb.init_cluster(X, 5, 3, seed=2, nstart=20, iter_max=30))
+    R.L.rstub_free_all()
