@@ -152,7 +152,8 @@ typedef struct simples_mi_args {
 } simples_mi_args;
 
 typedef struct simples_mi_out {     /* R/do_impute.R:158-159 */
-    double *loglik;                 /* 1: mean(tot[-1:-burnin])                        */
+    double *loglik;                 /* 1: mean(tot[-1:-burnin]); burnin = 0 still drops
+                                       the first sweep, as R's index -1:0 does          */
     double *impt;                   /* G x n                                           */
     double *impt_var;               /* G x n                                           */
     double *EF;                     /* n x K0                                          */

@@ -863,7 +863,9 @@ def do_impute_ref(dat, Y, beta, lam, sigma, mu, pi, pos_mean=None, pos_sd=None, 
                 rF2 += Wm[m] ** 2 * z[:, m][:, None]
                 rVF += z[:, m][:, None] * np.diag(Ms[m])[None, :]
     varF = rF2 / mcmc - (rEF / mcmc) ** 2 + rVF / mcmc                       # :156-157
-    return dict(loglik=float(np.mean(tot[burnin:])),                          # :158
+    # :158 mean(tot[-1:-burnin]); for burnin = 0 R's index -1:0 = c(-1, 0) still drops the first sweep (Q21)
+    kept = tot[max(burnin, 1):]
+    return dict(loglik=float(np.mean(kept)) if kept.size else float("nan"),
                 impt=(rec1 / mcmc) * pos_sd[:, None] + pos_mean[:, None],
                 impt_var=rec2 / mcmc - (rec1 / mcmc) ** 2, EF=rEF / mcmc, varF=varF,
                 consensus_cluster=None if cons is None else cons / mcmc)

@@ -1201,9 +1201,12 @@ int do_impute_one(const simples_mi_args* a, simples_mi_out* o, long long io_ld, 
     if (o->loglik && c->write_shared) {
         std::vector<double> t(size_t(nit) * (2 * M0 + 1));
         CK(cudaMemcpy(t.data(), c->tot_mi, t.size() * 8, cudaMemcpyDefault));
+        // mean(tot[-1:-burnin]) (R/do_impute.R:158).  For burnin = 0 the index is -1:0 = c(-1, 0), which still drops the
+        // first sweep (Q21): the mean runs over tot[2..mcmc] and is NaN when mcmc = 1, exactly as in R.
+        const int first = a->burnin > 0 ? a->burnin : 1;
         double sacc = 0.0;
-        for (int it = a->burnin; it < nit; ++it) sacc += t[size_t(it) * (2 * M0 + 1) + 2 * M0];
-        *o->loglik = sacc / a->mcmc;
+        for (int it = first; it < nit; ++it) sacc += t[size_t(it) * (2 * M0 + 1) + 2 * M0];
+        *o->loglik = nit > first ? sacc / double(nit - first) : std::nan("");
     }
     if (o->impt)
         CKR(fetch_big(c, o->impt, [&](double* dst, size_t c0, size_t nc) {

@@ -645,3 +645,20 @@ def test_do_impute_small_models(sb, K0, M0):
     ref, got = O.do_impute_ref(*args, **kw), sb.do_impute(*args, **kw)
     assert rel(got["impt"], ref["impt"]) <= 1e-6 and abs(got["loglik"] - ref["loglik"]) <= 1e-8 * abs(ref["loglik"])
     assert rel(got["EF"], ref["EF"]) <= 1e-7 and rel(got["consensus_cluster"], ref["consensus_cluster"]) <= 1e-8
+
+
+def test_do_impute_burnin_zero_drops_the_first_sweep(sb):
+    """Q21: `mean(tot[-1:-burnin])` (R/do_impute.R:158) with burnin = 0 indexes with -1:0 = c(-1, 0), i.e. the first
+    sweep is still dropped from the log-likelihood mean (and mcmc = 1 gives NaN); everything else records all sweeps."""
+    K0, M0 = 3, 2
+    st = make_case(120, 96, 2, 2, K0, M0, seed=51)
+    em = O.em_impute_fast(*em_args(st, M0, K0, 2), celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=2)
+    args = (st["Y0"], em["Y"], em["beta"], em["lambda"], em["sigma"], em["mu"], em["pi"], em["geneM"], em["geneSd"],
+            st["celltype"])
+    kw = dict(pg=st["pg"], cutoff=0.1, seed=8)
+    g0, r0 = sb.do_impute(*args, mcmc=3, burnin=0, **kw), O.do_impute_ref(*args, mcmc=3, burnin=0, **kw)
+    g1 = sb.do_impute(*args, mcmc=2, burnin=1, **kw)               # same chain, first sweep as burn-in
+    assert g0["loglik"] == g1["loglik"]
+    assert abs(g0["loglik"] - r0["loglik"]) <= 1e-8 * abs(r0["loglik"]) and rel(g0["impt"], r0["impt"]) <= 1e-6
+    assert not np.allclose(g0["impt"], g1["impt"])                  # burnin = 0 records the first sweep, burnin = 1 does not
+    assert np.isnan(sb.do_impute(*args, mcmc=1, burnin=0, **kw)["loglik"])

@@ -493,3 +493,18 @@ def test_r_golden_loader_plumbing(tmp_path):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_r_golden.py"), "-q", "-m", "not gpu",
                         "-p", "no:cacheprovider"], capture_output=True, text=True, cwd=root, env=dict(os.environ, SIMPLES_R_GOLDEN=gold))
     assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_do_impute_burnin_zero_index_quirk():
+    """Q21: R's `tot[-1:-burnin]` with burnin = 0 is `tot[c(-1, 0)]`: the first sweep is dropped from the mean
+    (R/do_impute.R:158); with mcmc = 1 nothing is left and R returns NaN."""
+    K0, M0 = 3, 2
+    st = make_case(80, 64, 2, 2, K0, M0, seed=51)
+    em = O.em_impute_fast(*em_args(st, M0, K0, 2), celltype=st["celltype"], impt_it=1, est_z=1, est_lam=1, seed=2)
+    args = (st["Y0"], em["Y"], em["beta"], em["lambda"], em["sigma"], em["mu"], em["pi"], em["geneM"], em["geneSd"],
+            st["celltype"])
+    kw = dict(pg=st["pg"], cutoff=0.1, seed=8, consensus=False)
+    a = O.do_impute_ref(*args, mcmc=3, burnin=0, **kw)
+    b = O.do_impute_ref(*args, mcmc=2, burnin=1, **kw)              # same chain, first sweep as burn-in
+    assert a["loglik"] == b["loglik"] and not np.allclose(a["impt"], b["impt"])
+    assert math.isnan(O.do_impute_ref(*args, mcmc=1, burnin=0, **kw)["loglik"])
