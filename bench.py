@@ -56,36 +56,73 @@ def fp64_peak():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region: through NVML (pynvml, ~1 ms per sample, so
+    even a 70 ms region yields dozens of samples) when it is importable, else by polling `nvidia-smi` (one sample per
+    ~0.1 s)."""
+
+    _NVML_REASONS = {0x08: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x04: "sw_power_cap"}
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
         self.reasons = set()
         self.maxmhz = None
+        self.source = None
         self._halt = threading.Event()
+        self._nvml = None
+        try:                                   # initialised here, outside the timed region
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxmhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self._nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        except Exception:  # noqa: BLE001
+            mask = 0
+        for bit, nme in self._NVML_REASONS.items():
+            if mask & bit:
+                self.reasons.add(nme)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.maxmhz = float(out[1])
+        for nme, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(nme)
+
+    def run(self):
+        self.source = "nvml" if self._nvml is not None else "nvidia-smi"
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.maxmhz = float(out[1])
-                for nme, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nme)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:  # noqa: BLE001
-                pass
-            self._halt.wait(0.1)
+                if self._nvml is not None:     # NVML failed mid-run: fall back to the command-line tool
+                    self._nvml, self.source = None, "nvidia-smi"
+            self._halt.wait(0.002 if self._nvml is not None else 0.1)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": self.source}
 
 
 def make_workload(n, rank, pinned):
